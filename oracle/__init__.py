@@ -1,0 +1,2 @@
+"""Test infrastructure: CPU oracles.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import from here."""
