@@ -99,7 +99,7 @@ def test_sweep_monotone():
 
 def test_batch_c():
     imgs = np.stack([synth_image(48, 40, 4095, s) for s in range(5)])
-    nb = np.array([300, 0, 17, 600, 50], np.int64)
+    nb = np.array([100, 0, 17, 150, 50], np.int64)
     pays = np.zeros((5, 80), np.uint8)
     for u in range(5):
         p = random_payload(int(nb[u]), u)
