@@ -1,0 +1,229 @@
+"""ctypes binding of libpeeb200.so (the C ABI declared in include/peeb200.h).
+
+There is no CPU fallback: if the shared library is missing, cannot be built, or
+no sm_100 device is visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+import weakref
+
+import numpy as np
+
+from . import build as _build
+
+PEEB_OK = 0
+PEEB_E_CUDA = -1
+PEEB_E_CAPACITY = -2
+PEEB_E_INVALID = -3
+PEEB_E_UNSUPPORTED = -4
+MOMENTS = 12
+INFO = 8
+INFO_KEYS = ("T", "n_bits", "capacity", "cap0", "cap1", "n_flagged", "sse", "status")
+
+_vp, _i32, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/peeb200.h declares
+SIGNATURES = {
+    "peeb_abi_version": (_i32, []),
+    "peeb_last_error": (C.c_char_p, []),
+    "peeb_device_count": (_i32, [_vp]),
+    "peeb_ws_create": (_i32, [_i32, _vp]),
+    "peeb_ws_destroy": (_i32, [_vp]),
+    "peeb_ws_sync": (_i32, [_vp]),
+    "peeb_ws_stream": (_vp, [_vp]),
+    "peeb_ws_set_option": (_i32, [_vp, _i32, _i32]),
+    "peeb_host_alloc": (_i32, [_sz, _vp]),
+    "peeb_host_free": (_i32, [_vp]),
+    "peeb_dev_alloc": (_i32, [_vp, _sz, _vp]),
+    "peeb_dev_free": (_i32, [_vp, _vp]),
+    "peeb_memcpy_h2d": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "peeb_memcpy_d2h": (_i32, [_vp, _vp, _vp, _sz, _vp]),
+    "peeb_prof_enable": (_i32, [_vp, _i32]),
+    "peeb_prof_get": (_i32, [_vp, _i32, _vp, _vp]),
+    "peeb_prof_name": (C.c_char_p, [_i32]),
+    "peeb_moments_batch": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp]),
+    "peeb_moments_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "peeb_hist_planes": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "peeb_hist_planes_h": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "peeb_planes_unpack": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "peeb_planes_unpack_h": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "peeb_planes_pack": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "peeb_planes_pack_h": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "peeb_tile_moments": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "peeb_tile_moments_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "peeb_lsb_embed": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "peeb_lsb_embed_h": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "peeb_compact_bits": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
+    "peeb_compact_bits_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp]),
+    "peeb_payload_bytes": (_sz, [_i64]),
+    "peeb_pee_embed_batch": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
+                                    _vp, _i64, _vp, _vp]),
+    "peeb_pee_extract_batch": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
+                                      _vp, _i64, _vp, _vp]),
+    "peeb_pee_hist_batch": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "peeb_pee_embed_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "peeb_pee_extract_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "peeb_pee_hist_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class PeebError(RuntimeError):
+    """A libpeeb200 call failed (CUDA error, unsupported shape, ...)."""
+
+
+def library_path() -> str:
+    return _build.LIBPATH
+
+
+def lib():
+    """The loaded shared library.  Builds it when it is missing and nvcc is
+    available; otherwise raises -- there is no other implementation to fall
+    back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            try:
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise PeebError(
+                    f"libpeeb200.so is missing at {path} and could not be built ({exc}); "
+                    "run `python -m codec_tcc_b200.build`") from exc
+        L = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if L.peeb_abi_version() != 1:
+            raise PeebError("libpeeb200.so ABI version mismatch; rebuild with `python -m codec_tcc_b200.build --force`")
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return (lib().peeb_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == PEEB_OK:
+        return
+    msg = last_error()
+    if rc == PEEB_E_INVALID:
+        raise ValueError(f"{what}: {msg}" if what else msg)
+    raise PeebError(f"{what}: {msg} (code {rc})" if what else f"{msg} (code {rc})")
+
+
+# ---------------------------------------------------------------- workspaces
+class Workspace:
+    """One opaque peeb_ws: device scratch, streams, events.  Thread compatible."""
+
+    def __init__(self, device: int):
+        self.device = device
+        h = _vp()
+        check(lib().peeb_ws_create(device, C.byref(h)), "peeb_ws_create")
+        self.handle = h
+        self._finalizer = weakref.finalize(self, lib().peeb_ws_destroy, h)
+
+    def sync(self):
+        check(lib().peeb_ws_sync(self.handle), "peeb_ws_sync")
+
+    @property
+    def stream(self) -> int:
+        return lib().peeb_ws_stream(self.handle) or 0
+
+    def set_option(self, name: str, value: bool):
+        """'bulk' (TMA bulk band staging) / 'cluster' (cluster-resident small images)."""
+        opt = {"bulk": 0, "cluster": 1}[name]
+        check(lib().peeb_ws_set_option(self.handle, opt, 1 if value else 0), "peeb_ws_set_option")
+
+    # profiling counters (bench.py's roofline leg)
+    def prof_enable(self, on: bool):
+        check(lib().peeb_prof_enable(self.handle, 1 if on else 0))
+
+    def prof_report(self):
+        out = {}
+        for slot in range(16):
+            ms, calls = C.c_double(0), C.c_longlong(0)
+            check(lib().peeb_prof_get(self.handle, slot, C.byref(ms), C.byref(calls)))
+            if calls.value:
+                out[lib().peeb_prof_name(slot).decode()] = (ms.value, calls.value)
+        return out
+
+
+_tls = threading.local()
+
+
+def default_device() -> int:
+    env = os.environ.get("PEEB_DEVICE")
+    if env is not None:
+        return int(env)
+    lr = os.environ.get("LOCAL_RANK")
+    if lr is not None:
+        n = device_count()
+        return int(lr) % max(n, 1)
+    return 0
+
+
+def device_count() -> int:
+    n = _i32(0)
+    check(lib().peeb_device_count(C.byref(n)), "peeb_device_count")
+    return n.value
+
+
+def workspace(device: int | None = None) -> Workspace:
+    """Per-thread, per-device workspace cache."""
+    if device is None:
+        device = default_device()
+    cache = getattr(_tls, "ws", None)
+    if cache is None:
+        cache = _tls.ws = {}
+    ws = cache.get(device)
+    if ws is None:
+        ws = cache[device] = Workspace(device)
+    return ws
+
+
+# ---------------------------------------------------------------- helpers
+def ptr(a) -> int:
+    """Address of a numpy array's data (or pass an int through)."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array in page-locked host memory (full-speed, truly asynchronous
+    PCIe copies).  Freed when the array (and every view of it) is gone."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = _vp()
+    check(lib().peeb_host_alloc(max(n, 1), C.byref(p)), "peeb_host_alloc")
+    buf = (C.c_ubyte * max(n, 1)).from_address(p.value)
+    weakref.finalize(buf, lib().peeb_host_free, p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+def payload_bytes(n_bits: int) -> int:
+    return int(lib().peeb_payload_bytes(int(n_bits)))
+
+
+def as_image(a, name="image") -> np.ndarray:
+    """C-contiguous uint8/uint16 view/copy; anything else is rejected the way
+    the reference rejects it (src/codec.py:34-37)."""
+    a = np.asarray(a)
+    if a.dtype not in (np.uint8, np.uint16):
+        raise ValueError(f"{name} must be uint8 or uint16, got {a.dtype}")
+    return np.ascontiguousarray(a)

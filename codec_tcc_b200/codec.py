@@ -1,0 +1,412 @@
+"""The pixel-array functions of the reference's ``src/codec.py`` (rows a5-a9 of
+SURVEY.md section 8) with the same names, arguments, return values and error
+behaviour, executed by hand-written sm_100a kernels through the C ABI of
+``include/peeb200.h``.
+
+What stays on the host is only what the reference itself does per call in
+O(s) or on scalars: the segment plan (Python's ``random.shuffle`` with seed 42
+must be CPython's), the float64 entropy sums over the *histogram* (so that
+numpy's summation order -- and therefore the split point ``s`` -- is reproduced
+bit for bit), the exact-rational arg-max over per-tile moments, and the final
+bytes->utf-8 decoding.  There is no CPU implementation of the per-pixel work.
+
+DICOM / JPEG-XL / container I/O (src/codec.py:19-213, 601-750, 795-926) is out
+of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+from fractions import Fraction
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import check, lib, ptr, workspace
+
+__all__ = [
+    "message_to_bits", "distribute_message_segments", "calculate_entropy", "calculate_mutual_information",
+    "adaptive_modalities_decomposition", "merge_modalities", "extract_local_planes", "lsb_embed_multi_plane",
+    "lsb_embed_block_then_multiplane", "decode_message",
+]
+
+VERBOSE = False  # the reference prints from inside its numerics (src/codec.py:568,577-578); opt in to that
+
+
+# ------------------------------------------------------------------ host-side helpers
+def message_to_bits(message: str) -> str:
+    """src/codec.py:239-240: '0'/'1' string, 8 bits per character, MSB first."""
+    return "".join(format(ord(ch), "08b") for ch in message)
+
+
+def distribute_message_segments(local_planes, message_bits):
+    """src/codec.py:242-274 -> ``(segments, distributed_sizes, segment_indices)``.
+    O(s) host logic; reseeds Python's global ``random`` with 42 exactly like the
+    reference (src/codec.py:263)."""
+    s = len(local_planes)
+    total_bits = len(message_bits)
+    weights = [(s - i) ** 2 for i in range(s)]
+    weight_sum = sum(weights)
+    sizes = [max(1, int((wt / weight_sum) * total_bits)) for wt in weights]
+    surplus = sum(sizes) - total_bits
+    if surplus != 0:
+        sizes[sizes.index(max(sizes))] -= surplus
+    order = list(range(s))
+    random.seed(42)
+    random.shuffle(order)
+    segments, at = [], 0
+    for plane in order:
+        segments.append(message_bits[at:at + sizes[plane]])
+        at += sizes[plane]
+    return segments, sizes, order
+
+
+def _bits_to_packed(bits: str) -> np.ndarray:
+    """'0'/'1' string -> packed uint8 (MSB first)."""
+    if not bits:
+        return np.zeros(0, np.uint8)
+    raw = np.frombuffer(bits.encode("ascii"), dtype=np.uint8)
+    vals = raw - ord("0")
+    if vals.max() > 1:
+        raise ValueError("invalid literal for int() with base 10: message bits must be '0'/'1'")
+    return np.packbits(vals)
+
+
+def _entropy_from_counts(counts, total):
+    """numpy's own order of operations (src/codec.py:498-501), on a histogram."""
+    p = counts[counts > 0] / total
+    return -np.sum(p * np.log2(p))
+
+
+def _plane_stack(planes, what):
+    """list of equally shaped planes -> (list of C-contiguous arrays, shape, dtype)."""
+    if len(planes) == 0:
+        raise IndexError("list index out of range")  # the reference indexes planes[0]
+    arrs = [np.asarray(p) for p in planes]
+    dt = arrs[0].dtype
+    if dt not in (np.uint8, np.uint16):
+        raise ValueError(f"{what} must be uint8 or uint16 planes, got {dt}")
+    shape = arrs[0].shape
+    out = []
+    for a in arrs:
+        if a.shape != shape:
+            raise ValueError(f"{what}: all planes must share one shape")
+        out.append(np.ascontiguousarray(a if a.dtype == dt else a.astype(dt)))
+    return out, shape, dt
+
+
+def _ptr_array(arrs):
+    return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+# ------------------------------------------------------------------ a5: entropy / MI / split
+def _image_histogram(image, device=None):
+    """(hist int64[nbins], plane_ones int64[16]) from the device."""
+    img = _cabi.as_image(image, "image_array")
+    hist = np.zeros(65536, np.uint32)
+    ones = np.zeros(16, np.uint64)
+    ws = workspace(device)
+    check(lib().peeb_hist_planes_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, ptr(hist), ptr(ones)),
+          "peeb_hist_planes_h")
+    nbins = 256 if img.dtype == np.uint8 else 65536
+    return hist[:nbins].astype(np.int64), ones.astype(np.int64)
+
+
+def calculate_entropy(data_array):
+    """src/codec.py:489-502.  The histogram comes from the GPU; ``np.bincount``
+    stops at the largest value present, so trailing empty bins are cut before
+    the (order-sensitive) float sum."""
+    arr = _cabi.as_image(data_array, "data_array")
+    if arr.size == 0:
+        return -np.sum(np.zeros(0))  # the reference yields -0.0 for an empty array
+    hist, _ = _image_histogram(arr)
+    return _entropy_from_counts(hist, arr.size)
+
+
+def _plane_information(hist, ones, total, bit, nbins):
+    """I(plane; image) from the image histogram and the plane's population
+    count -- the three entropies of src/codec.py:529-554, in numpy's order.  The
+    non-empty joint bins are ``hist``'s non-empty bins, those whose value has
+    the bit clear first, then those with the bit set (index = bit*(max+1)+v,
+    src/codec.py:548)."""
+    zeros = total - ones
+    if ones == 0 or zeros == 0 or np.count_nonzero(hist) <= 1:
+        return 0.0  # src/codec.py:520-523
+    h_x = _entropy_from_counts(np.array([zeros, ones], dtype=np.int64), total)
+    h_y = _entropy_from_counts(hist, total)
+    has_bit = ((np.arange(nbins) >> bit) & 1).astype(bool)
+    joint = np.concatenate([np.where(has_bit, 0, hist), np.where(has_bit, hist, 0)])
+    h_xy = _entropy_from_counts(joint, total)
+    return max(0.0, h_x + h_y - h_xy)
+
+
+def calculate_mutual_information(bit_plane, image_array):
+    """src/codec.py:504-559 for a plane that is one of the image's own bit
+    planes (how the reference calls it, :571,:588).  Which bit it is gets
+    identified on the device: the plane's population count narrows the
+    candidates, an exact SSE of zero against the unpacked candidate confirms."""
+    img = _cabi.as_image(image_array, "image_array")
+    plane = np.ascontiguousarray(np.asarray(bit_plane))
+    if plane.shape != img.shape:
+        raise ValueError("bit_plane and image_array must have the same shape")
+    if plane.dtype != img.dtype:
+        plane = plane.astype(img.dtype)
+    hist, ones = _image_histogram(img)
+    nbins = hist.size
+    from .mse import image_moments
+    pm = image_moments(plane, plane)
+    if pm["max_a"] > 1:
+        raise NotImplementedError("bit_plane must hold 0/1 values")
+    for bit in range(8 * img.dtype.itemsize):
+        if int(ones[bit]) != pm["sum_a"]:
+            continue
+        cand = extract_bit_plane(img, bit)
+        if image_moments(cand, plane)["sse"] == 0:
+            return _plane_information(hist, int(ones[bit]), img.size, bit, nbins)
+    raise NotImplementedError("bit_plane is not a bit-plane of image_array; only that case is on the device path")
+
+
+def extract_bit_plane(image, bit, device=None):
+    """(image >> bit) & 1 with the image's dtype (src/codec.py:571)."""
+    img = _cabi.as_image(image, "image")
+    out = np.empty((1,) + img.shape, img.dtype)
+    ws = workspace(device)
+    check(lib().peeb_planes_unpack_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, int(bit), 1, ptr(out)),
+          "peeb_planes_unpack_h")
+    return out[0]
+
+
+def choose_split(image_array, beta=0.8, nbits=None):
+    """The decision of src/codec.py:573-593 -> ``(s, total_info, [mi ...])``."""
+    img = _cabi.as_image(image_array, "image_array")
+    nbits = img.dtype.itemsize * 8 if nbits is None else nbits
+    hist, ones = _image_histogram(img)
+    total = img.size
+    total_info = _entropy_from_counts(hist, total)
+    target = beta * total_info
+    acc, s, seen = 0.0, 1, []
+    for i in range(nbits):
+        o = int(ones[i]) if i < 16 else 0
+        mi = _plane_information(hist, o, total, i, hist.size) if i < 8 * img.dtype.itemsize else 0.0
+        seen.append(mi)
+        acc += mi
+        if acc >= target:
+            s = i + 1
+            break
+    return s, total_info, seen
+
+
+def adaptive_modalities_decomposition(image_array, beta=0.8, nbits=None):
+    """src/codec.py:561-599 -> ``(global_planes, local_planes)``: lists of (h, w)
+    0/1 arrays with the image's dtype, split at the first ``s`` where the
+    cumulative plane information reaches ``beta * H(image)``."""
+    img = _cabi.as_image(image_array, "image_array")
+    nbits = img.dtype.itemsize * 8 if nbits is None else nbits
+    if VERBOSE:
+        print(f"   - Profundidade de bits efetiva: {nbits}")
+    s, total_info, _ = choose_split(img, beta, nbits)
+    if VERBOSE:
+        print(f"   - Informação total da imagem: {total_info:.4f}")
+        print(f"   - Meta de retenção ({beta*100}%): {beta * total_info:.4f}")
+    planes = np.empty((max(nbits, 0),) + img.shape, img.dtype)
+    if nbits > 0 and img.size:
+        ws = workspace()
+        check(lib().peeb_planes_unpack_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, 0, nbits, ptr(planes)),
+              "peeb_planes_unpack_h")
+    bit_planes = [planes[i] for i in range(nbits)]
+    return bit_planes[s:], bit_planes[:s]
+
+
+# ------------------------------------------------------------------ a8: pack / unpack
+def merge_modalities(global_planes, local_planes):
+    """src/codec.py:215-237: OR of ``plane.astype(dtype) << k``; dtype uint16
+    when there are more than 8 planes in total, else uint8."""
+    allp = list(local_planes) + list(global_planes)
+    if not allp:
+        raise IndexError("list index out of range")
+    planes, shape, dt = _plane_stack(allp, "planes")
+    total_bits = len(planes)
+    out_dtype = np.uint16 if total_bits > 8 else np.uint8
+    out = np.zeros(shape, out_dtype)
+    use = planes[:16]  # a uint16 shifted by >= 16 contributes nothing
+    n = int(np.prod(shape)) if len(shape) else 1
+    if n == 0:
+        return out
+    ws = workspace()
+    if total_bits > 16:
+        # keep the uint16 output decision while packing only the first 16 planes
+        tmp = np.zeros(shape, np.uint16)
+        check(lib().peeb_planes_pack_h(ws.handle, _ptr_array(use), n, dt.itemsize, 16, ptr(tmp)), "peeb_planes_pack_h")
+        return tmp
+    check(lib().peeb_planes_pack_h(ws.handle, _ptr_array(use), n, dt.itemsize, len(use), ptr(out)), "peeb_planes_pack_h")
+    return out
+
+
+def extract_local_planes(stego_array, s):
+    """src/codec.py:789-793: the ``s`` least significant bit planes."""
+    img = _cabi.as_image(stego_array, "stego_array")
+    s = int(s)
+    planes = np.empty((max(s, 0),) + img.shape, img.dtype)
+    if s > 0 and img.size:
+        ws = workspace()
+        check(lib().peeb_planes_unpack_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, 0, s, ptr(planes)),
+              "peeb_planes_unpack_h")
+    return [planes[i] for i in range(s)]
+
+
+# ------------------------------------------------------------------ a6: tile variance arg-max
+def _dyadic_mean(k, n):
+    """True when the float evaluation of np.var on n values summing to k (all
+    0/1) is exact, so equal rationals give equal floats."""
+    if k == 0 or k == n:
+        return True
+    r = n // math.gcd(k, n)
+    return (r & (r - 1)) == 0
+
+
+def _best_tile_offset(ref_plane, sbs, device=None):
+    """Raster offset ``y*w + x`` of the first tile attaining the largest
+    ``float(np.var(tile))`` (src/codec.py:437-453, strict '>' so the first wins).
+    The device returns sum and sum of squares per tile (row-major over tiles)."""
+    plane = np.ascontiguousarray(ref_plane)
+    h, w = plane.shape
+    sbs = int(sbs)
+    if sbs < 1:
+        raise ValueError("range() arg 3 must not be zero" if sbs == 0 else "search_block_size must be positive")
+    ty, tx = -(-h // sbs), -(-w // sbs)
+    sums = np.zeros((ty * tx, 2), np.int64)
+    ws = workspace(device)
+    check(lib().peeb_tile_moments_h(ws.handle, ptr(plane), h, w, plane.dtype.itemsize, sbs, ptr(sums)),
+          "peeb_tile_moments_h")
+    return _tile_argmax_from_moments(plane, sbs, sums)
+
+
+def _tile_argmax_from_moments(plane, sbs, sums):
+    """Host half of the tile search: var = (n*sq - s^2)/n^2 per tile is compared
+    exactly (rationals).  When exact ties (or near ties) involve a tile whose
+    float evaluation is not exact, the reference's float result decides, so
+    ``float(np.var(tile))`` is evaluated for those few tiles only."""
+    h, w = plane.shape
+    ty, tx = -(-h // sbs), -(-w // sbs)
+    th = np.minimum(sbs, h - np.arange(ty) * sbs)
+    tw = np.minimum(sbs, w - np.arange(tx) * sbs)
+    npx = (th[:, None] * tw[None, :]).reshape(-1).astype(np.int64)
+    s1, s2 = sums[:, 0], sums[:, 1]
+    approx = (npx.astype(np.float64) * s2 - s1.astype(np.float64) ** 2) / (npx.astype(np.float64) ** 2)
+    top = approx.max()
+    short = np.flatnonzero(approx >= top - abs(top) * 1e-9 - 1e-300)
+    exact = [Fraction(int(npx[t]) * int(s2[t]) - int(s1[t]) ** 2, int(npx[t]) ** 2) for t in short]
+    best = max(exact)
+    binary = bool(np.all(s1[short] == s2[short]))  # 0/1 tiles: sum == sum of squares
+    cands = [int(t) for t, v in zip(short, exact) if v == best]
+    if binary and len(cands) == len(short) and all(_dyadic_mean(int(s1[t]), int(npx[t])) for t in cands):
+        pick = cands[0]
+    else:
+        pick, best_f = None, -1.0
+        for t in (int(v) for v in short):  # raster order over the short list
+            y, x = (t // tx) * sbs, (t % tx) * sbs
+            f = float(np.var(plane[y:y + sbs, x:x + sbs]))
+            if f > best_f:
+                best_f, pick = f, t
+    return (pick // tx) * sbs * w + (pick % tx) * sbs
+
+
+# ------------------------------------------------------------------ a6 / a7: embedders
+def _embed(local_planes, message_bits, start_offset, advance, device=None):
+    planes, shape, dt = _plane_stack(local_planes, "local_planes")
+    s = len(planes)
+    if len(shape) != 2:
+        raise ValueError("planes must be 2-D")
+    h, w = shape
+    npx = h * w
+    segments, sizes, order = distribute_message_segments(planes, message_bits)
+    start = np.zeros(s, np.int64)
+    length = np.zeros(s, np.int64)
+    bit_off = np.zeros(s, np.int64)
+    chunks, at, total_used = [], 0, 0
+    for seg, plane_idx in zip(segments, order):
+        nb = min(len(seg), npx)
+        packed = _bits_to_packed(seg[:nb])
+        start[plane_idx] = start_offset if npx else 0
+        length[plane_idx] = nb
+        bit_off[plane_idx] = 8 * at
+        chunks.append(packed)
+        at += packed.size
+        total_used += nb
+        if advance and npx:
+            start_offset = (start_offset + nb) % npx
+    payload = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+    out_planes = np.empty((s, h, w), dt)
+    bitmaps = np.empty((s, h, w), np.uint8)
+    if npx:
+        ws = workspace(device)
+        check(lib().peeb_lsb_embed_h(ws.handle, _ptr_array(planes), npx, dt.itemsize, s, ptr(start), ptr(length),
+                                     ptr(bit_off), ptr(payload) if payload.size else None, 8 * payload.size,
+                                     ptr(out_planes), ptr(bitmaps)), "peeb_lsb_embed_h")
+    stego = [out_planes[i] for i in range(s)]
+    maps = [bitmaps[i] for i in range(s)]
+    return stego, maps, total_used, [int(v) for v in length], sizes, order
+
+
+def lsb_embed_multi_plane(local_planes, message_bits):
+    """src/codec.py:276-318 -> ``(stego_planes, bitmaps, total_used,
+    segments_lengths, segment_indices)``; every plane is written from raster
+    position 0 and ``segments_lengths`` are the embedded lengths (:315)."""
+    stego, maps, used, lens, _sizes, order = _embed(local_planes, message_bits, 0, False)
+    return stego, maps, used, lens, order
+
+
+def lsb_embed_block_then_multiplane(local_planes, message_bits, search_block_size=8,
+                                    align_across_planes: bool = False):
+    """src/codec.py:412-487: start at the raster offset of the highest-variance
+    ``search_block_size`` tile of plane 0, wrap around the image end, advance
+    the start by each embedded length unless ``align_across_planes``.
+    ``segments_lengths`` are the *planned* sizes (:425,:487)."""
+    if len(local_planes) == 0:
+        raise IndexError("list index out of range")
+    ref = np.asarray(local_planes[0])
+    if ref.dtype not in (np.uint8, np.uint16):
+        raise ValueError(f"local_planes must be uint8 or uint16 planes, got {ref.dtype}")
+    start = _best_tile_offset(ref, search_block_size) if ref.size else 0
+    stego, maps, used, _lens, sizes, order = _embed(local_planes, message_bits, start, not align_across_planes)
+    return stego, maps, used, sizes, order
+
+
+# ------------------------------------------------------------------ a9: decode_message
+def _decode_bit_chunks(stego_planes, bitmaps, metadata, device=None):
+    """Per plane index: (packed bits, count) of the LSBs at the first
+    ``segments_lengths[plane]`` positions where the bitmap is non-zero
+    (src/codec.py:761-772)."""
+    s = metadata["s"]
+    chunks = [(np.zeros(0, np.uint8), 0)] * s
+    ws = workspace(device)
+    for plane_idx in metadata["segments_indices"]:
+        plane = np.ascontiguousarray(np.asarray(stego_planes[plane_idx]).reshape(-1))
+        if plane.dtype not in (np.uint8, np.uint16):
+            raise ValueError("stego planes must be uint8/uint16")
+        bm = np.ascontiguousarray(np.asarray(bitmaps[plane_idx]).reshape(-1))
+        if bm.dtype != np.uint8:
+            bm = (bm != 0).astype(np.uint8)
+        if bm.size != plane.size:
+            raise IndexError("bitmap and plane sizes differ")
+        limit = max(0, min(int(metadata["segments_lengths"][plane_idx]), plane.size))
+        bits = np.zeros(((limit + 7) // 8 + 3) // 4 * 4 + 4, np.uint8)
+        count = np.zeros(1, np.int64)
+        if plane.size and limit:
+            check(lib().peeb_compact_bits_h(ws.handle, ptr(plane), ptr(bm), plane.size, plane.dtype.itemsize, limit,
+                                            ptr(bits), ptr(count)), "peeb_compact_bits_h")
+        chunks[plane_idx] = (bits, int(count[0]))
+    return chunks
+
+
+def decode_message(stego_planes, bitmaps, metadata):
+    """src/codec.py:752-787, bug-compatible: reads LSBs only
+    where the bitmap is non-zero and concatenates the per-plane pieces by plane
+    index; whole bytes are decoded as utf-8 with replacement."""
+    chunks = _decode_bit_chunks(stego_planes, bitmaps, metadata)
+    pieces = [np.unpackbits(bits)[:cnt] for bits, cnt in chunks]
+    allbits = np.concatenate(pieces) if pieces else np.zeros(0, np.uint8)
+    nbytes = allbits.size // 8
+    raw = np.packbits(allbits[:nbytes * 8]).tobytes()
+    return raw.decode("utf-8", errors="replace")

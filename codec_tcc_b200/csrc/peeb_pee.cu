@@ -1,0 +1,1091 @@
+// Row a10: reversible Prediction-Error Expansion on sm_100a.
+//
+// Work decomposition
+//   unit  = one image of a batch (units are independent);
+//   band  = R consecutive rows of a unit, full width.  One CTA owns one band: it
+//           stages rows [r0-2, r0+R+2) in shared memory (one TMA bulk copy when the
+//           row size allows), runs both colour passes on chip and writes the band
+//           back once.  Two halo rows on each side let the CTA recompute, locally,
+//           the colour-0 result of the rows next to the band that its colour-1
+//           pixels predict from -- no second trip through global memory;
+//   strip = 128 columns of a band; a warp walks a strip downwards, 4 pixels per lane
+//           (one 64-bit / 32-bit shared load per row), so N/S neighbours are the
+//           previous / next loads and W/E neighbours come from the lane's own word or
+//           one shuffle.
+//
+// Payload bit index of a carrier = exclusive prefix count of carriers in raster order.
+//   - per (row, strip) counts come from warp ballots, a block scan orders them;
+//   - across bands: pass 0 uses the per-band counts of pee_count_kernel (which also
+//     yields cap0, the base of pass 1); pass 1 uses a decoupled look-back over the
+//     earlier bands of the same unit.  Bands are handed out by an atomic ticket, so a
+//     band only ever waits on bands that are already running.
+// Extraction needs no inter-band ordering for the pixels; every band writes its
+// carrier bits to a staging area and pee_gather_kernel concatenates them.
+#include <algorithm>
+
+#include "peeb_common.cuh"
+
+namespace peeb {
+
+constexpr int STRIP = 128;  // columns per warp work item (4 per lane)
+
+struct PeeGeom {
+    int h, w, itemsize;
+    int R;         // band height (rows written per CTA)
+    int nb;        // bands per unit
+    int S;         // strips per row
+    int pitch;     // shared-memory row pitch (bytes)
+    int rowbytes;  // w * itemsize
+    int lmw;       // ceil(w/8): global location-map row bytes
+    int lmpitch;   // shared location-map row pitch (bytes, multiple of 4)
+    int bulk;      // TMA bulk copies usable (rowbytes % 16 == 0)
+    int maxval;
+    int bandwords; // extract staging: 32-bit words per (unit, pass, band)
+};
+
+struct PeeBatch {
+    const unsigned char* src; long long src_stride;    // bytes
+    unsigned char* dst; long long dst_stride;          // may be null
+    unsigned char* lm; long long lm_stride;            // may be null (embed) / const (extract)
+    const unsigned char* payload; long long payload_stride;
+    unsigned char* payload_out;                        // extract
+    const int* T;                                      // device, per unit
+    const unsigned* n_bits;                            // device, per unit
+    long long* info;                                   // device, per unit x 8
+    int n_units;
+};
+
+// ------------------------------------------------------------------ pixels
+template <typename PixT> struct Px;
+template <> struct Px<unsigned short> {
+    static constexpr int ITEM = 2;
+    __device__ static __forceinline__ void load4(const unsigned char* row, int c0, int (&m)[4]) {
+        const uint2 v = *reinterpret_cast<const uint2*>(row + 2 * c0);
+        m[0] = v.x & 0xffff; m[1] = v.x >> 16; m[2] = v.y & 0xffff; m[3] = v.y >> 16;
+    }
+    __device__ static __forceinline__ void store4(unsigned char* row, int c0, const int (&m)[4]) {
+        uint2 v;
+        v.x = (unsigned)m[0] | ((unsigned)m[1] << 16);
+        v.y = (unsigned)m[2] | ((unsigned)m[3] << 16);
+        *reinterpret_cast<uint2*>(row + 2 * c0) = v;
+    }
+    __device__ static __forceinline__ int load1(const unsigned char* row, int c) {
+        return *reinterpret_cast<const unsigned short*>(row + 2 * c);
+    }
+};
+template <> struct Px<unsigned char> {
+    static constexpr int ITEM = 1;
+    __device__ static __forceinline__ void load4(const unsigned char* row, int c0, int (&m)[4]) {
+        const unsigned v = *reinterpret_cast<const unsigned*>(row + c0);
+        m[0] = v & 0xff; m[1] = (v >> 8) & 0xff; m[2] = (v >> 16) & 0xff; m[3] = v >> 24;
+    }
+    __device__ static __forceinline__ void store4(unsigned char* row, int c0, const int (&m)[4]) {
+        *reinterpret_cast<unsigned*>(row + c0) =
+            (unsigned)m[0] | ((unsigned)m[1] << 8) | ((unsigned)m[2] << 16) | ((unsigned)m[3] << 24);
+    }
+    __device__ static __forceinline__ int load1(const unsigned char* row, int c) { return row[c]; }
+};
+
+// Appendix A, embed side, for one pixel: value with a zero payload bit, whether
+// it carries a bit, whether it goes to the location map.
+__device__ __forceinline__ void classify_embed(int x, int p, int T, int maxval, int& nv0, bool& carrier,
+                                               bool& flagged) {
+    const int e = x - p;
+    const int v = x + e;                                        // p + 2e
+    const bool expd = (unsigned)(e + T) < (unsigned)(2 * T);    // -T <= e < T
+    const bool fe = (unsigned)v >= (unsigned)maxval;            // v < 0 or v + 1 > maxval
+    const int xs = x + (e >= T ? T : -T);
+    const bool fs = (unsigned)xs > (unsigned)maxval;            // x+T > maxval or x-T < 0
+    carrier = expd && !fe;
+    flagged = expd ? fe : fs;
+    nv0 = expd ? (fe ? x : v) : (fs ? x : xs);
+}
+
+// Appendix A, extract side.
+__device__ __forceinline__ void classify_extract(int x, int p, int T, bool lmflag, int& orig, bool& carrier,
+                                                 int& bit) {
+    const int ee = x - p;
+    const bool car = (unsigned)(ee + 2 * T) < (unsigned)(4 * T);  // -2T <= e' < 2T
+    const int e = car ? (ee >> 1) : (ee >= 2 * T ? ee - T : ee + T);
+    bit = ee & 1;
+    carrier = car && !lmflag;
+    orig = lmflag ? x : p + e;
+}
+
+// 64 payload bits starting at bit K0 of an MSB-first packed stream; bit K0 is the
+// MSB of `hi`.  The stream must be readable 12 bytes past the word holding K0.
+__device__ __forceinline__ void payload_window(const unsigned* __restrict__ pay, unsigned K0, unsigned& hi,
+                                               unsigned& lo) {
+    const unsigned wi = K0 >> 5, sh = K0 & 31;
+    const unsigned w0 = __byte_perm(__ldg(pay + wi), 0, 0x0123);
+    const unsigned w1 = __byte_perm(__ldg(pay + wi + 1), 0, 0x0123);
+    const unsigned w2 = __byte_perm(__ldg(pay + wi + 2), 0, 0x0123);
+    hi = __funnelshift_l(w1, w0, sh);
+    lo = __funnelshift_l(w2, w1, sh);
+}
+__device__ __forceinline__ int window_bit(unsigned hi, unsigned lo, int k) {  // 0 <= k < 64
+    return (int)(((k < 32 ? hi : lo) >> (31 - (k & 31))) & 1u);
+}
+
+// location-map bit of column j inside a 32-bit little-endian word of a packbits row
+__device__ __forceinline__ unsigned lm_bitmask(int j) { return 1u << (8 * ((j >> 3) & 3) + 7 - (j & 7)); }
+
+// ------------------------------------------------------------------ shared layout
+__host__ __device__ inline size_t band_smem_bytes(const PeeGeom& g, bool extract) {
+    size_t img = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
+    size_t lm = align_up((size_t)(g.R + 2) * g.lmpitch, 16);
+    size_t cnt = align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
+    size_t total = img + lm + cnt + 64 * sizeof(int) + 16;
+    if (extract) {
+        total += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);  // xbits, 2 passes
+        total += align_up((size_t)g.R * g.S * sizeof(int), 16);                            // second count table
+        total += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);                 // 2 streams
+    }
+    return total;
+}
+
+// Cooperative copy of image rows [lo, hi) of a unit into the band buffer.
+template <typename PixT>
+__device__ __forceinline__ void load_rows(const PeeGeom& g, const unsigned char* unit_src, unsigned char* simg,
+                                          int r_first /* image row of smem row 0 */, int lo, int hi,
+                                          uint64_t* bar) {
+    if (hi <= lo) return;
+    unsigned char* dst = simg + (size_t)(lo - r_first) * g.pitch;
+    const unsigned char* src = unit_src + (size_t)lo * g.rowbytes;
+    if (g.bulk) {
+        // rows are contiguous in both spaces (pitch == rowbytes): bulk copies of <= 64 KB
+        const unsigned total = (unsigned)(hi - lo) * (unsigned)g.rowbytes;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, total);
+            for (unsigned off = 0; off < total; off += 65536u) {
+                const unsigned n = min(65536u, total - off);
+                bulk_g2s(dst + off, src + off, n, bar);
+            }
+        }
+        mbar_wait(bar, 0);
+    } else {
+        const int n = (hi - lo);
+        for (int r = threadIdx.x >> 5; r < n; r += blockDim.x >> 5) {
+            const PixT* s = reinterpret_cast<const PixT*>(src + (size_t)r * g.rowbytes);
+            PixT* d = reinterpret_cast<PixT*>(dst + (size_t)r * g.pitch);
+            for (int c = threadIdx.x & 31; c < g.w; c += 32) d[c] = s[c];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename PixT>
+__device__ __forceinline__ void store_rows(const PeeGeom& g, unsigned char* unit_dst, const unsigned char* simg,
+                                           int r_first, int lo, int hi) {
+    if (hi <= lo) return;
+    const unsigned char* src = simg + (size_t)(lo - r_first) * g.pitch;
+    unsigned char* dst = unit_dst + (size_t)lo * g.rowbytes;
+    if (g.bulk) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned total = (unsigned)(hi - lo) * (unsigned)g.rowbytes;
+            for (unsigned off = 0; off < total; off += 65536u) bulk_s2g(dst + off, src + off, min(65536u, total - off));
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    } else {
+        __syncthreads();
+        const int n = (hi - lo);
+        for (int r = threadIdx.x >> 5; r < n; r += blockDim.x >> 5) {
+            const PixT* s = reinterpret_cast<const PixT*>(src + (size_t)r * g.pitch);
+            PixT* d = reinterpret_cast<PixT*>(dst + (size_t)r * g.rowbytes);
+            for (int c = threadIdx.x & 31; c < g.w; c += 32) d[c] = s[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ embed sweeps
+// One colour pass over rows [row_lo, row_hi) of the band buffer, split into warp
+// items (strip, chunk of rows).  APPLY=false: count carriers per (row, strip) into
+// tab[(row-row_lo)*S + strip].  APPLY=true: tab holds the payload bit index of the
+// first carrier of each (row, strip); pixels are rewritten in place.
+struct EmbedStats {
+    unsigned long long sse = 0;
+    unsigned flagged = 0;
+};
+
+template <typename PixT, bool APPLY>
+__device__ __forceinline__ void embed_sweep(const PeeGeom& g, unsigned char* simg, int r_first, int colour,
+                                            int row_lo, int row_hi, int own_lo, int own_hi, int T, int* tab,
+                                            const unsigned* __restrict__ payload, unsigned n_bits,
+                                            unsigned* slm, int lm_row0, EmbedStats& st) {
+    const int nrows = row_hi - row_lo;
+    if (nrows <= 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int G = max(1, nwarps / g.S);             // row chunks per strip
+    const int RC = (nrows + G - 1) / G;             // rows per chunk
+    const int nitems = g.S * G;
+    const unsigned lt = lanemask_lt();
+    for (int item = warp; item < nitems; item += nwarps) {
+        const int s = item % g.S, chunk = item / g.S;
+        const int ra = row_lo + chunk * RC, rb = min(ra + RC, row_hi);
+        if (ra >= rb) continue;
+        const int c0 = s * STRIP + 4 * lane;
+        int u[4], m[4], d[4];
+        const unsigned char* rowp = simg + (size_t)(ra - 1 - r_first) * g.pitch;
+        Px<PixT>::load4(rowp, c0, u);
+        Px<PixT>::load4(rowp + g.pitch, c0, m);
+        for (int i = ra; i < rb; ++i) {
+            unsigned char* mid = simg + (size_t)(i - r_first) * g.pitch;
+            Px<PixT>::load4(mid + g.pitch, c0, d);
+            const int q = (i + colour) & 1;
+            int xa, pa, xb, pb;
+            if (q == 0) {
+                int left = __shfl_up_sync(0xffffffffu, m[3], 1);
+                if (lane == 0) left = c0 > 0 ? Px<PixT>::load1(mid, c0 - 1) : 0;
+                xa = m[0]; pa = (u[0] + d[0] + left + m[1]) >> 2;
+                xb = m[2]; pb = (u[2] + d[2] + m[1] + m[3]) >> 2;
+            } else {
+                int right = __shfl_down_sync(0xffffffffu, m[0], 1);
+                if (lane == 31) right = c0 + 4 < g.w ? Px<PixT>::load1(mid, c0 + 4) : 0;
+                xa = m[1]; pa = (u[1] + d[1] + m[0] + m[2]) >> 2;
+                xb = m[3]; pb = (u[3] + d[3] + m[2] + right) >> 2;
+            }
+            const int ca = c0 + q, cb = c0 + q + 2;
+            const bool va = ca >= 1 && ca <= g.w - 2, vb = cb >= 1 && cb <= g.w - 2;
+            int na, nbv;
+            bool cara, fla, carb, flb;
+            classify_embed(xa, pa, T, g.maxval, na, cara, fla);
+            classify_embed(xb, pb, T, g.maxval, nbv, carb, flb);
+            cara = cara && va; carb = carb && vb;
+            const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
+            const int e_idx = (i - row_lo) * g.S + s;
+            if (!APPLY) {
+                if (lane == 0) tab[e_idx] = __popc(ma) + __popc(mb);
+            } else {
+                const unsigned base = (unsigned)tab[e_idx];
+                if ((ma | mb) && base < n_bits) {
+                    unsigned hi, lo;
+                    payload_window(payload, base, hi, lo);
+                    const int ka = __popc(ma & lt) + __popc(mb & lt);
+                    const int kb = ka + (cara ? 1 : 0);
+                    if (cara && base + ka < n_bits) na += window_bit(hi, lo, ka);
+                    if (carb && base + kb < n_bits) nbv += window_bit(hi, lo, kb);
+                }
+                if (!va) na = xa;
+                if (!vb) nbv = xb;
+                if (i >= own_lo && i < own_hi) {
+                    const int da = na - xa, db = nbv - xb;
+                    st.sse += (unsigned long long)(unsigned)(da * da) + (unsigned)(db * db);
+                    fla = fla && va; flb = flb && vb;
+                    if (fla | flb) {
+                        unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
+                        if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st.flagged; }
+                        if (flb) { atomicOr(lrow + (cb >> 5), lm_bitmask(cb)); ++st.flagged; }
+                    }
+                }
+                if (q == 0) { m[0] = na; m[2] = nbv; } else { m[1] = na; m[3] = nbv; }
+                if (c0 < g.w) Px<PixT>::store4(mid, c0, m);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { u[k] = m[k]; m[k] = d[k]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K_A: pass-0 band counts
+// grid = n_units * nb.  band_cnt[unit*nb + band] = pass-0 carriers in the band's own
+// rows; info[unit][3] (cap0) accumulates their sum.
+template <typename PixT>
+__global__ void __launch_bounds__(256) pee_count_kernel(PeeGeom g, PeeBatch bt, int* __restrict__ band_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
+    unsigned char* simg = smem_raw;
+    const size_t img_bytes = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
+    int* cnt = reinterpret_cast<int*>(smem_raw + img_bytes);
+    int* misc = cnt + (g.R + 2) * g.S;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + img_bytes + align_up((size_t)((g.R + 2) * g.S + 64) * sizeof(int), 16));
+    if (g.bulk && threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const int r0 = band * g.R, r_first = r0 - 2;
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    const int T = bt.T[unit];
+    EmbedStats st;
+    embed_sweep<PixT, false>(g, simg, r_first, 0, own_lo, own_hi, own_lo, own_hi, T, cnt, nullptr, 0, nullptr, 0, st);
+    __syncthreads();
+    const int n = max(own_hi - own_lo, 0) * g.S;
+    int part = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) part += cnt[k];
+    part = (int)warp_sum_i64(part);
+    if ((threadIdx.x & 31) == 0) misc[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += misc[k];
+        band_cnt[unit * g.nb + band] = tot;
+        atomicAdd(reinterpret_cast<unsigned long long*>(bt.info + (long long)unit * PEEB_INFO + 3), (unsigned long long)tot);
+    }
+}
+
+// ------------------------------------------------------------------ K_B: fused two-pass embed
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_PFX = 2ull << 62, ST_MASK = 3ull << 62;
+
+template <typename PixT>
+__global__ void __launch_bounds__(256) pee_embed_kernel(PeeGeom g, PeeBatch bt, const int* __restrict__ band_cnt,
+                                                        unsigned* __restrict__ ticket,
+                                                        unsigned long long* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* simg = smem_raw;
+    size_t off = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
+    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + off);
+    off += align_up((size_t)(g.R + 2) * g.lmpitch, 16);
+    int* tab = reinterpret_cast<int*>(smem_raw + off);
+    off += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
+    int* misc = reinterpret_cast<int*>(smem_raw + off);
+    off += 64 * sizeof(int);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off);
+
+    // in-order ticket: a band only ever waits on bands with smaller tickets
+    if (threadIdx.x == 0) {
+        misc[40] = (int)atomicAdd(ticket, 1u);
+        if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
+    }
+    __syncthreads();
+    const int tk = misc[40];
+    const int unit = tk / g.nb, band = tk % g.nb;
+    const int r0 = band * g.R, r_first = r0 - 2;
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    const int T = bt.T[unit];
+    const unsigned n_bits = bt.n_bits[unit];
+    const unsigned* payload = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
+    long long* info = bt.info + (long long)unit * PEEB_INFO;
+
+    load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 2, 0), min(r0 + g.R + 2, g.h), bar);
+    for (int k = threadIdx.x; k < (g.R * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
+
+    // pass-0 prefix of this band and cap0 of the unit from the count kernel
+    if (threadIdx.x < 32) {
+        int before = 0, all = 0;
+        for (int k = threadIdx.x; k < g.nb; k += 32) {
+            const int c = band_cnt[unit * g.nb + k];
+            all += c;
+            if (k < band) before += c;
+        }
+        before = (int)warp_sum_i64(before);
+        all = (int)warp_sum_i64(all);
+        if (threadIdx.x == 0) { misc[41] = before; misc[42] = all; }
+    }
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    EmbedStats st;
+
+    // ---- pass 0 (colour 0) over the band rows and one halo row on each side
+    const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
+    embed_sweep<PixT, false>(g, simg, r_first, 0, p0_lo, p0_hi, own_lo, own_hi, T, tab, nullptr, 0, slm, r0, st);
+    __syncthreads();
+    {
+        const int n = max(p0_hi - p0_lo, 0) * g.S;
+        // carriers of the halo row above precede this band in raster order
+        int halo_top = 0;
+        if (p0_lo < own_lo) for (int k = 0; k < g.S; ++k) halo_top += tab[k];
+        __syncthreads();
+        block_excl_scan(tab, n, misc);
+        const int base = misc[41] - halo_top;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) tab[k] += base;
+        __syncthreads();
+    }
+    embed_sweep<PixT, true>(g, simg, r_first, 0, p0_lo, p0_hi, own_lo, own_hi, T, tab, payload, n_bits, slm, r0, st);
+    __syncthreads();
+
+    // ---- pass 1 (colour 1) over the band rows
+    embed_sweep<PixT, false>(g, simg, r_first, 1, own_lo, own_hi, own_lo, own_hi, T, tab, nullptr, 0, slm, r0, st);
+    __syncthreads();
+    {
+        const int n = max(own_hi - own_lo, 0) * g.S;
+        const int total = block_excl_scan(tab, n, misc);
+        if (threadIdx.x == 0) {
+            unsigned long long* stt = status + (long long)unit * g.nb;
+            atomicExch(stt + band, ST_AGG | (unsigned)total);
+            unsigned before = 0;
+            for (int k = band - 1; k >= 0; --k) {
+                unsigned long long v;
+                do { v = *reinterpret_cast<volatile unsigned long long*>(stt + k); } while ((v & ST_MASK) == 0);
+                before += (unsigned)(v & 0xffffffffu);
+                if ((v & ST_MASK) == ST_PFX) break;
+            }
+            atomicExch(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
+            misc[43] = (int)before;
+            atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
+        }
+        __syncthreads();
+        const int base = misc[42] + misc[43];  // cap0 + carriers of pass 1 in earlier bands
+        for (int k = threadIdx.x; k < n; k += blockDim.x) tab[k] += base;
+        __syncthreads();
+    }
+    embed_sweep<PixT, true>(g, simg, r_first, 1, own_lo, own_hi, own_lo, own_hi, T, tab, payload, n_bits, slm, r0, st);
+
+    // ---- statistics
+    {
+        const unsigned long long sse = warp_sum_u64(st.sse);
+        const unsigned long long fl = warp_sum_u64(st.flagged);
+        if ((threadIdx.x & 31) == 0) {
+            if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(info + 6), sse);
+            if (fl) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), fl);
+        }
+    }
+    // ---- write back the band (image rows, location-map rows)
+    const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
+    if (bt.dst) store_rows<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, b_lo, b_hi);
+    else __syncthreads();
+    if (bt.lm) {
+        unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw;
+        const int nrows = b_hi - b_lo;
+        if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
+            const int wpr = g.lmw >> 2;
+            for (int k = threadIdx.x; k < nrows * wpr; k += blockDim.x)
+                reinterpret_cast<unsigned*>(glm)[k] = slm[(k / wpr) * (g.lmpitch >> 2) + (k % wpr)];
+        } else {
+            const unsigned char* sb = reinterpret_cast<const unsigned char*>(slm);
+            for (int k = threadIdx.x; k < nrows * g.lmw; k += blockDim.x)
+                glm[k] = sb[(k / g.lmw) * g.lmpitch + (k % g.lmw)];
+        }
+    }
+}
+
+__global__ void pee_finalize_kernel(PeeBatch bt, int extract) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= bt.n_units) return;
+    long long* info = bt.info + (long long)u * PEEB_INFO;
+    info[0] = bt.T[u];
+    info[1] = bt.n_bits[u];
+    info[2] = info[3] + info[4];
+    info[7] = ((long long)bt.n_bits[u] > info[2]) ? PEEB_E_CAPACITY : 0;
+    (void)extract;
+}
+
+// ------------------------------------------------------------------ K_X: extract
+// One sweep per colour; pixels are restored in place, carrier bits of the band's own
+// rows are compacted per (row, strip) with ballots and a warp OR-reduction.
+template <typename PixT>
+__device__ __forceinline__ void extract_sweep(const PeeGeom& g, unsigned char* simg, int r_first, int colour,
+                                              int row_lo, int row_hi, int own_lo, int own_hi, int T,
+                                              const unsigned* slm, int lm_row0, int* cnt,
+                                              unsigned long long* xbits) {
+    const int nrows = row_hi - row_lo;
+    if (nrows <= 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int G = max(1, nwarps / g.S);
+    const int RC = (nrows + G - 1) / G;
+    const int nitems = g.S * G;
+    const unsigned lt = lanemask_lt();
+    for (int item = warp; item < nitems; item += nwarps) {
+        const int s = item % g.S, chunk = item / g.S;
+        const int ra = row_lo + chunk * RC, rb = min(ra + RC, row_hi);
+        if (ra >= rb) continue;
+        const int c0 = s * STRIP + 4 * lane;
+        int u[4], m[4], d[4];
+        const unsigned char* rowp = simg + (size_t)(ra - 1 - r_first) * g.pitch;
+        Px<PixT>::load4(rowp, c0, u);
+        Px<PixT>::load4(rowp + g.pitch, c0, m);
+        for (int i = ra; i < rb; ++i) {
+            unsigned char* mid = simg + (size_t)(i - r_first) * g.pitch;
+            Px<PixT>::load4(mid + g.pitch, c0, d);
+            const int q = (i + colour) & 1;
+            // location-map nibble of this lane's 4 columns (bit 3 = column c0)
+            const unsigned lw = slm[(size_t)(i - lm_row0) * (g.lmpitch >> 2) + (c0 >> 5)];
+            const unsigned nib = (lw >> (8 * ((c0 >> 3) & 3) + ((c0 & 4) ? 0 : 4))) & 0xfu;
+            int xa, pa, xb, pb;
+            if (q == 0) {
+                int left = __shfl_up_sync(0xffffffffu, m[3], 1);
+                if (lane == 0) left = c0 > 0 ? Px<PixT>::load1(mid, c0 - 1) : 0;
+                xa = m[0]; pa = (u[0] + d[0] + left + m[1]) >> 2;
+                xb = m[2]; pb = (u[2] + d[2] + m[1] + m[3]) >> 2;
+            } else {
+                int right = __shfl_down_sync(0xffffffffu, m[0], 1);
+                if (lane == 31) right = c0 + 4 < g.w ? Px<PixT>::load1(mid, c0 + 4) : 0;
+                xa = m[1]; pa = (u[1] + d[1] + m[0] + m[2]) >> 2;
+                xb = m[3]; pb = (u[3] + d[3] + m[2] + right) >> 2;
+            }
+            const int ca = c0 + q, cb = c0 + q + 2;
+            const bool va = ca >= 1 && ca <= g.w - 2, vb = cb >= 1 && cb <= g.w - 2;
+            const bool la = (nib >> (3 - q)) & 1u, lb = (nib >> (1 - q)) & 1u;
+            int oa, ob, bita, bitb;
+            bool cara, carb;
+            classify_extract(xa, pa, T, la, oa, cara, bita);
+            classify_extract(xb, pb, T, lb, ob, carb, bitb);
+            cara = cara && va; carb = carb && vb;
+            if (!va) oa = xa;
+            if (!vb) ob = xb;
+            if (i >= own_lo && i < own_hi) {
+                const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
+                const int ka = __popc(ma & lt) + __popc(mb & lt);
+                const int kb = ka + (cara ? 1 : 0);
+                unsigned long long contrib = 0;
+                if (cara && bita) contrib |= 1ull << ka;
+                if (carb && bitb) contrib |= 1ull << kb;
+                const unsigned clo = __reduce_or_sync(0xffffffffu, (unsigned)contrib);
+                const unsigned chi = __reduce_or_sync(0xffffffffu, (unsigned)(contrib >> 32));
+                if (lane == 0) {
+                    const int e_idx = (i - own_lo) * g.S + s;
+                    cnt[e_idx] = __popc(ma) + __popc(mb);
+                    xbits[e_idx] = ((unsigned long long)chi << 32) | clo;
+                }
+            }
+            if (q == 0) { m[0] = oa; m[2] = ob; } else { m[1] = oa; m[3] = ob; }
+            if (c0 < g.w) Px<PixT>::store4(mid, c0, m);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { u[k] = m[k]; m[k] = d[k]; }
+        }
+    }
+}
+
+// grid = n_units * nb (no inter-band dependency).  stage_bits: per (unit, pass, band)
+// `bandwords` 32-bit words, carrier bit k at word k>>5, bit k&31; stage_cnt likewise.
+template <typename PixT>
+__global__ void __launch_bounds__(256) pee_extract_kernel(PeeGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits,
+                                                          int* __restrict__ stage_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* simg = smem_raw;
+    size_t off = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
+    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + off);
+    off += align_up((size_t)(g.R + 2) * g.lmpitch, 16);
+    int* cnt1 = reinterpret_cast<int*>(smem_raw + off);   // colour 1 table
+    off += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
+    int* misc = reinterpret_cast<int*>(smem_raw + off);
+    off += 64 * sizeof(int);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off);
+    off += 16;
+    unsigned long long* xb1 = reinterpret_cast<unsigned long long*>(smem_raw + off);
+    unsigned long long* xb0 = xb1 + (g.R + 2) * g.S;
+    off += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);
+    int* cnt0 = reinterpret_cast<int*>(smem_raw + off);
+    off += align_up((size_t)g.R * g.S * sizeof(int), 16);
+    unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + off);  // [2][bandwords]: pass 0, pass 1
+
+    const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
+    const int r0 = band * g.R, r_first = r0 - 2;
+    if (g.bulk && threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    const int T = bt.T[unit];
+    load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 2, 0), min(r0 + g.R + 2, g.h), bar);
+    // location-map rows [r0-1, r0+R+1) -> slm (row pitch lmpitch)
+    {
+        const int l_lo = max(r0 - 1, 0), l_hi = min(r0 + g.R + 1, g.h);
+        const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
+        unsigned char* sb = reinterpret_cast<unsigned char*>(slm);
+        if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
+            const int wpr = g.lmw >> 2;
+            const unsigned* gw = reinterpret_cast<const unsigned*>(glm + (size_t)l_lo * g.lmw);
+            for (int k = threadIdx.x; k < (l_hi - l_lo) * wpr; k += blockDim.x)
+                slm[(size_t)(l_lo - (r0 - 1) + k / wpr) * (g.lmpitch >> 2) + (k % wpr)] = gw[k];
+        } else {
+            for (int k = threadIdx.x; k < (l_hi - l_lo) * g.lmw; k += blockDim.x)
+                sb[(size_t)(l_lo - (r0 - 1) + k / g.lmw) * g.lmpitch + (k % g.lmw)] = glm[(size_t)l_lo * g.lmw + k];
+        }
+        for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
+    }
+    __syncthreads();
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
+    // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
+    extract_sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, own_lo, own_hi, T, slm, r0 - 1, cnt1, xb1);
+    __syncthreads();
+    extract_sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, own_lo, own_hi, T, slm, r0 - 1, cnt0, xb0);
+    __syncthreads();
+
+    // compact the per-(row,strip) pieces into one bit stream per pass
+    const int n = max(own_hi - own_lo, 0) * g.S;
+    for (int pass = 0; pass < 2; ++pass) {
+        int* cnt = pass == 0 ? cnt0 : cnt1;
+        const unsigned long long* xb = pass == 0 ? xb0 : xb1;
+        unsigned* out = stream + (size_t)pass * g.bandwords;
+        // the scan turns counts into bit offsets; a piece's size is the next offset minus its own
+        const int total = block_excl_scan(cnt, n, misc);
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int o = cnt[k];
+            const int c = (k + 1 < n ? cnt[k + 1] : total) - o;
+            if (c > 0) {
+                const unsigned long long v = xb[k];
+                const int wi = o >> 5, sh = o & 31;
+                atomicOr(out + wi, (unsigned)(v << sh));
+                const unsigned long long hi = sh ? (v >> (32 - sh)) : (v >> 32);
+                // bits 32-sh .. of v go to the following words
+                if (sh) {
+                    if ((unsigned)hi) atomicOr(out + wi + 1, (unsigned)hi);
+                    if ((unsigned)(hi >> 32)) atomicOr(out + wi + 2, (unsigned)(hi >> 32));
+                } else {
+                    if ((unsigned)hi) atomicOr(out + wi + 1, (unsigned)hi);
+                }
+            }
+        }
+        __syncthreads();
+        const long long slot = ((long long)unit * 2 + pass) * g.nb + band;
+        if (threadIdx.x == 0) stage_cnt[slot] = total;
+        unsigned* gout = stage_bits + slot * g.bandwords;
+        const int nw = (total + 31) >> 5;
+        for (int k = threadIdx.x; k < nw; k += blockDim.x) gout[k] = out[k];
+        __syncthreads();
+    }
+    if (bt.dst)
+        store_rows<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
+}
+
+// ------------------------------------------------------------------ K_G: payload assembly
+// grid = (2*nb, n_units).  Piece p of a unit = pass-0 band p (p < nb) or pass-1 band
+// p-nb; its global bit offset is the sum of the earlier pieces' counts.  Output is
+// MSB-first packed, truncated to n_bits; payload_out is zeroed by the caller.
+__global__ void __launch_bounds__(128) pee_gather_kernel(PeeGeom g, PeeBatch bt, const unsigned* __restrict__ stage_bits,
+                                                         const int* __restrict__ stage_cnt) {
+    const int unit = blockIdx.y, piece = blockIdx.x;
+    const int* cnts = stage_cnt + (long long)unit * 2 * g.nb;
+    long long before = 0, all = 0;
+    for (int k = threadIdx.x; k < 2 * g.nb; k += blockDim.x) {
+        const int c = cnts[k];
+        all += c;
+        if (k < piece) before += c;
+    }
+    before = warp_sum_i64(before);
+    all = warp_sum_i64(all);
+    __shared__ long long s_b[4], s_a[4];
+    if ((threadIdx.x & 31) == 0) { s_b[threadIdx.x >> 5] = before; s_a[threadIdx.x >> 5] = all; }
+    __syncthreads();
+    before = s_b[0] + s_b[1] + s_b[2] + s_b[3];
+    all = s_a[0] + s_a[1] + s_a[2] + s_a[3];
+    const long long n_bits = bt.n_bits[unit];
+    long long* info = bt.info + (long long)unit * PEEB_INFO;
+    if (piece == 0 && threadIdx.x == 0) {
+        long long c0 = 0;
+        for (int k = 0; k < g.nb; ++k) c0 += cnts[k];
+        info[0] = bt.T[unit]; info[1] = n_bits; info[2] = all; info[3] = c0; info[4] = all - c0;
+        info[5] = 0; info[6] = 0; info[7] = n_bits > all ? PEEB_E_CAPACITY : 0;
+    }
+    const int cnt = cnts[piece];
+    if (cnt == 0 || before >= n_bits) return;
+    const unsigned* src = stage_bits + ((long long)unit * 2 * g.nb + piece) * g.bandwords;
+    unsigned* out = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
+    const int nsrc = (cnt + 31) >> 5;
+    const long long first = before >> 5, last = (before + cnt - 1) >> 5;
+    const int sh = (int)(before & 31);
+    for (long long mw = first + threadIdx.x; mw <= last; mw += blockDim.x) {
+        const int i = (int)(mw - first);
+        const unsigned cur = i < nsrc ? src[i] : 0u;
+        const unsigned prev = (i >= 1 && i - 1 < nsrc) ? src[i - 1] : 0u;
+        unsigned val = sh ? ((cur << sh) | (prev >> (32 - sh))) : cur;
+        // drop bits at or past n_bits
+        const long long bit0 = mw << 5;
+        if (bit0 + 32 > n_bits) {
+            const int keep = (int)(n_bits - bit0);
+            val = keep <= 0 ? 0u : (val & (0xffffffffu >> (32 - keep)));
+        }
+        if (val == 0) continue;
+        const unsigned packed = __byte_perm(__brev(val), 0, 0x0123);  // LSB-first word -> MSB-first bytes
+        if (mw == first || mw == last) atomicOr(out + mw, packed);
+        else out[mw] = packed;
+    }
+}
+
+// ------------------------------------------------------------------ prediction-error histogram
+// Appendix A threshold selection: hist[u][c][e + tmax] over interior pixels not flagged
+// for expansion.  One pixel per thread; |e| < 512 goes through warp-aggregated
+// shared-memory atomics, the rare rest straight to global memory.
+constexpr int HWIN = 512;
+template <typename PixT>
+__global__ void __launch_bounds__(256) pee_hist_kernel(const unsigned char* __restrict__ src, long long src_stride,
+                                                       int h, int w, int maxval, int tmax,
+                                                       unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[2][2 * HWIN];
+    for (int k = threadIdx.x; k < 4 * HWIN; k += blockDim.x) (&sh[0][0])[k] = 0;
+    __syncthreads();
+    const int unit = blockIdx.y;
+    const PixT* img = reinterpret_cast<const PixT*>(src + (long long)unit * src_stride);
+    unsigned* uh = hist + (long long)unit * 4 * tmax;
+    const long long npx = (long long)(h - 2) * (w - 2);
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long base = warp0 * 32; base < npx; base += nwarps * 32) {  // warp-uniform trip count
+        const long long t = base + lane;
+        bool ok = t < npx;
+        int e = 0, c = 0;
+        if (ok) {
+            const int i = 1 + (int)(t / (w - 2)), j = 1 + (int)(t % (w - 2));
+            const long long at = (long long)i * w + j;
+            const int x = img[at];
+            const int p = ((int)img[at - w] + (int)img[at + w] + (int)img[at - 1] + (int)img[at + 1]) >> 2;
+            e = x - p;
+            const int v = x + e;
+            c = (i + j) & 1;
+            ok = !((unsigned)v >= (unsigned)maxval) && e >= -tmax && e < tmax;
+        }
+        const bool in_win = ok && e >= -HWIN && e < HWIN;
+        const unsigned active = __ballot_sync(0xffffffffu, in_win);
+        if (in_win) {
+            const int key = c * 2 * HWIN + e + HWIN;
+            const unsigned peers = __match_any_sync(active, key);
+            if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&sh[0][0] + key, __popc(peers));
+        } else if (ok) {
+            atomicAdd(uh + (long long)c * 2 * tmax + e + tmax, 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * HWIN; k += blockDim.x) {
+        const unsigned v = (&sh[0][0])[k];
+        if (v) {
+            const int c = k / (2 * HWIN), e = k % (2 * HWIN) - HWIN;
+            if (e >= -tmax && e < tmax) atomicAdd(uh + (long long)c * 2 * tmax + e + tmax, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, bool extract, PeeGeom& g) {
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "pee: itemsize must be 1 or 2");
+    PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "pee: bit_depth %d out of range for itemsize %d", bit_depth, itemsize);
+    PEEB_REQUIRE(h >= 1 && w >= 1 && (long long)h * w < (1ll << 31), "pee: image size %dx%d unsupported", h, w);
+    g.h = h; g.w = w; g.itemsize = itemsize;
+    g.rowbytes = w * itemsize;
+    g.bulk = ws->use_bulk && (g.rowbytes % 16 == 0);
+    g.pitch = g.bulk ? g.rowbytes : (int)align_up((size_t)g.rowbytes, 16);
+    g.S = (w + STRIP - 1) / STRIP;
+    g.lmw = (w + 7) / 8;
+    g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 4;  // +4: partial strips may peek one word past the row
+    g.maxval = (1 << bit_depth) - 1;
+    // band height: as tall as fits a ~72 KB stage (three CTAs per SM), capped at 64 rows;
+    // wide images fall back to fewer rows and, if needed, one CTA per SM
+    int R = 64;
+    const size_t budget_small = 72 * 1024, budget_max = (size_t)ws->max_smem_optin - 2048;
+    auto fits = [&](int r, size_t budget) {
+        g.R = r; g.bandwords = (r * ((w + 1) / 2) + 31) / 32 + 2;
+        return band_smem_bytes(g, extract) <= budget;
+    };
+    while (R > 8 && !fits(R, budget_small)) R -= 8;
+    if (!fits(R, budget_small)) {
+        while (R > 2 && !fits(R, budget_max)) R -= 2;
+        if (!fits(R, budget_max)) {
+            set_error("pee: image width %d needs more shared memory than one SM has", w);
+            return PEEB_E_UNSUPPORTED;
+        }
+    }
+    if (R > h) { R = h < 1 ? 1 : h; }
+    fits(R, budget_max);
+    g.nb = (h + g.R - 1) / g.R;
+    return PEEB_OK;
+}
+
+// upload T / n_bits (host arrays) into the workspace tables; returns device pointers
+static int upload_unit_tables(peeb_ws* ws, int n_units, const int32_t* T, const int64_t* n_bits, int bit_depth,
+                              size_t extra_bytes, cudaStream_t st, int** dT, unsigned** dN, char** extra) {
+    const size_t head = align_up((size_t)n_units * 8, 256);
+    int rc = scratch_reserve(ws->tables, head + extra_bytes + 256);
+    if (rc) return rc;
+    rc = scratch_reserve(ws->tables_h, head, true);
+    if (rc) return rc;
+    int* hT = (int*)ws->tables_h.ptr;
+    unsigned* hN = (unsigned*)(hT + n_units);
+    const int tmax = 1 << (bit_depth - 1);
+    for (int u = 0; u < n_units; ++u) {
+        PEEB_REQUIRE(T[u] >= 1 && T[u] <= tmax, "pee: T[%d]=%d outside 1..%d", u, T[u], tmax);
+        PEEB_REQUIRE(n_bits[u] >= 0 && n_bits[u] < (1ll << 31), "pee: n_bits[%d] out of range", u);
+        hT[u] = T[u];
+        hN[u] = (unsigned)n_bits[u];
+    }
+    // the pinned mirror is reused by the next call: wait until the previous upload has been consumed
+    PEEB_CUDA(cudaEventSynchronize(ws->ev[3]));
+    PEEB_CUDA(cudaMemcpyAsync(ws->tables.ptr, hT, (size_t)n_units * 8, cudaMemcpyHostToDevice, st));
+    PEEB_CUDA(cudaEventRecord(ws->ev[3], st));
+    *dT = (int*)ws->tables.ptr;
+    *dN = (unsigned*)((int*)ws->tables.ptr + n_units);
+    *extra = (char*)ws->tables.ptr + head;
+    return PEEB_OK;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    PEEB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PEEB_OK;
+}
+
+static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                            int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
+                            int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm,
+                            int64_t lm_stride, int64_t* info, cudaStream_t st) {
+    PEEB_REQUIRE(ws && src && T && n_bits && payload && info, "peeb_pee_embed_batch: null pointer");
+    PEEB_REQUIRE(n_units >= 1, "peeb_pee_embed_batch: n_units must be >= 1");
+    PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_embed_batch: payload must be 4-byte aligned");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    PeeGeom g;
+    int rc = make_geom(ws, h, w, itemsize, bit_depth, false, g);
+    if (rc) return rc;
+    if (g.bulk && ((((uintptr_t)src) | (uintptr_t)marked | (uint64_t)src_stride | (uint64_t)marked_stride) & 15)) {
+        g.bulk = 0;  // unaligned user buffers: plain copies
+        g.pitch = (int)align_up((size_t)g.rowbytes, 16);
+    }
+    const long long nbands = (long long)n_units * g.nb;
+    PEEB_REQUIRE(nbands < (1ll << 30), "peeb_pee_embed_batch: too many bands");
+    int* dT; unsigned* dN; char* extra;
+    const size_t cnt_bytes = align_up((size_t)nbands * sizeof(int), 256);
+    const size_t st_bytes = align_up((size_t)nbands * sizeof(unsigned long long), 256);
+    rc = upload_unit_tables(ws, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256, st, &dT, &dN, &extra);
+    if (rc) return rc;
+    int* band_cnt = (int*)extra;
+    unsigned long long* status = (unsigned long long*)(extra + cnt_bytes);
+    unsigned* ticket = (unsigned*)(extra + cnt_bytes + st_bytes);
+    PEEB_CUDA(cudaMemsetAsync(status, 0, st_bytes + 256, st));
+    PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
+    PeeBatch bt{};
+    bt.src = (const unsigned char*)src; bt.src_stride = src_stride;
+    bt.dst = (unsigned char*)marked; bt.dst_stride = marked_stride;
+    bt.lm = lm; bt.lm_stride = lm_stride;
+    bt.payload = payload; bt.payload_stride = payload_stride;
+    bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    const size_t smem = band_smem_bytes(g, false);
+    if (h >= 3 && w >= 3) {
+        if (itemsize == 2) {
+            rc = set_smem(pee_count_kernel<unsigned short>, smem); if (rc) return rc;
+            rc = set_smem(pee_embed_kernel<unsigned short>, smem); if (rc) return rc;
+            { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
+              pee_count_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt); }
+            { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+              pee_embed_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, ticket, status); }
+        } else {
+            rc = set_smem(pee_count_kernel<unsigned char>, smem); if (rc) return rc;
+            rc = set_smem(pee_embed_kernel<unsigned char>, smem); if (rc) return rc;
+            { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
+              pee_count_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt); }
+            { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+              pee_embed_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, ticket, status); }
+        }
+        PEEB_CUDA(cudaGetLastError());
+    } else {
+        // no interior: nothing can be embedded, marked == source, empty location map
+        for (int u = 0; u < n_units; ++u) {
+            if (marked) PEEB_CUDA(cudaMemcpyAsync((char*)marked + u * marked_stride, (const char*)src + u * src_stride,
+                                                  (size_t)h * w * itemsize, cudaMemcpyDeviceToDevice, st));
+            if (lm) PEEB_CUDA(cudaMemsetAsync(lm + u * lm_stride, 0, (size_t)h * g.lmw, st));
+        }
+    }
+    { ProfScope p(ws, PEEB_K_PEE_FINAL, st);
+      pee_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt, 0); }
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
+                              int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
+                              const uint8_t* lm, int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride,
+                              void* recovered, int64_t recovered_stride, int64_t* info, cudaStream_t st) {
+    PEEB_REQUIRE(ws && marked && T && n_bits && lm && payload_out && info, "peeb_pee_extract_batch: null pointer");
+    PEEB_REQUIRE(n_units >= 1 && n_units <= 65535, "peeb_pee_extract_batch: n_units must be 1..65535");
+    PEEB_REQUIRE(((uintptr_t)payload_out & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_extract_batch: payload_out must be 4-byte aligned");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    PeeGeom g;
+    int rc = make_geom(ws, h, w, itemsize, bit_depth, true, g);
+    if (rc) return rc;
+    if (g.bulk && ((((uintptr_t)marked) | (uintptr_t)recovered | (uint64_t)marked_stride | (uint64_t)recovered_stride) & 15)) {
+        g.bulk = 0;
+        g.pitch = (int)align_up((size_t)g.rowbytes, 16);
+    }
+    const long long nbands = (long long)n_units * g.nb;
+    int* dT; unsigned* dN; char* extra;
+    const size_t cnt_bytes = align_up((size_t)nbands * 2 * sizeof(int), 256);
+    rc = upload_unit_tables(ws, n_units, T, n_bits, bit_depth, cnt_bytes, st, &dT, &dN, &extra);
+    if (rc) return rc;
+    int* stage_cnt = (int*)extra;
+    rc = scratch_reserve(ws->bits, (size_t)nbands * 2 * g.bandwords * sizeof(unsigned) + 256);
+    if (rc) return rc;
+    unsigned* stage_bits = (unsigned*)ws->bits.ptr;
+    PeeBatch bt{};
+    bt.src = (const unsigned char*)marked; bt.src_stride = marked_stride;
+    bt.dst = (unsigned char*)recovered; bt.dst_stride = recovered_stride;
+    bt.lm = const_cast<uint8_t*>(lm); bt.lm_stride = lm_stride;
+    bt.payload = nullptr; bt.payload_stride = payload_stride; bt.payload_out = payload_out;
+    bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    for (int u = 0; u < n_units; ++u) {
+        const size_t pb = peeb_payload_bytes(n_bits[u]);
+        PEEB_REQUIRE(n_units == 1 || (int64_t)pb <= payload_stride, "peeb_pee_extract_batch: payload_stride too small for unit %d", u);
+    }
+    if (n_units > 1 || true) {
+        // zero every unit's output words (gather ORs the boundary words in)
+        if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
+        else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
+    }
+    if (h >= 3 && w >= 3) {
+        const size_t smem = band_smem_bytes(g, true);
+        if (itemsize == 2) {
+            rc = set_smem(pee_extract_kernel<unsigned short>, smem); if (rc) return rc;
+            ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
+            pee_extract_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, stage_bits, stage_cnt);
+        } else {
+            rc = set_smem(pee_extract_kernel<unsigned char>, smem); if (rc) return rc;
+            ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
+            pee_extract_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, stage_bits, stage_cnt);
+        }
+        PEEB_CUDA(cudaGetLastError());
+    } else {
+        PEEB_CUDA(cudaMemsetAsync(stage_cnt, 0, cnt_bytes, st));
+        for (int u = 0; u < n_units; ++u)
+            if (recovered) PEEB_CUDA(cudaMemcpyAsync((char*)recovered + u * recovered_stride, (const char*)marked + u * marked_stride,
+                                                     (size_t)h * w * itemsize, cudaMemcpyDeviceToDevice, st));
+    }
+    {
+        ProfScope p(ws, PEEB_K_PEE_GATHER, st);
+        dim3 grid((unsigned)(2 * g.nb), (unsigned)n_units);
+        pee_gather_kernel<<<grid, 128, 0, st>>>(g, bt, stage_bits, stage_cnt);
+    }
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+static int hist_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                           int bit_depth, uint32_t* hist, cudaStream_t st) {
+    PEEB_REQUIRE(ws && src && hist, "peeb_pee_hist_batch: null pointer");
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_pee_hist_batch: itemsize must be 1 or 2");
+    PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "peeb_pee_hist_batch: bad bit_depth");
+    PEEB_REQUIRE(n_units >= 1 && n_units <= 65535 && h >= 1 && w >= 1, "peeb_pee_hist_batch: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    const int tmax = 1 << (bit_depth - 1);
+    PEEB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 4 * (size_t)tmax * n_units, st));
+    if (h < 3 || w < 3) return PEEB_OK;
+    const long long npx = (long long)(h - 2) * (w - 2);
+    long long blocks = (npx + 256 * 8 - 1) / (256 * 8);
+    long long cap = (long long)ws->sm_count * 8 / n_units;
+    if (cap < 1) cap = 1;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)n_units);
+    ProfScope p(ws, PEEB_K_PEE_HIST, st);
+    if (itemsize == 2)
+        pee_hist_kernel<unsigned short><<<grid, 256, 0, st>>>((const unsigned char*)src, src_stride, h, w, (1 << bit_depth) - 1, tmax, hist);
+    else
+        pee_hist_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)src, src_stride, h, w, (1 << bit_depth) - 1, tmax, hist);
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+}  // namespace peeb
+
+using namespace peeb;
+
+extern "C" {
+
+size_t peeb_payload_bytes(int64_t n_bits) {
+    if (n_bits < 0) n_bits = 0;
+    return align_up((size_t)((n_bits + 7) / 8), 4) + 8;
+}
+
+int peeb_pee_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                         int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
+                         int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
+                         int64_t* info, void* stream) {
+    return embed_batch_impl(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, T, n_bits, payload, payload_stride,
+                            marked, marked_stride, lm, lm_stride, info, (cudaStream_t)stream);
+}
+
+int peeb_pee_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
+                           int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm,
+                           int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,
+                           int64_t recovered_stride, int64_t* info, void* stream) {
+    return extract_batch_impl(ws, marked, marked_stride, n_units, h, w, itemsize, bit_depth, T, n_bits, lm, lm_stride,
+                              payload_out, payload_stride, recovered, recovered_stride, info, (cudaStream_t)stream);
+}
+
+int peeb_pee_hist_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                        int bit_depth, uint32_t* hist, void* stream) {
+    return hist_batch_impl(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, hist, (cudaStream_t)stream);
+}
+
+// ---- host-buffer variants: staging + copies on the workspace stream, synchronous ----
+static int64_t max_payload_bytes(int n_units, const int64_t* n_bits) {
+    int64_t m = 0;
+    for (int u = 0; u < n_units; ++u) {
+        const int64_t b = (int64_t)peeb_payload_bytes(n_bits[u]);
+        if (b > m) m = b;
+    }
+    return m;
+}
+
+int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_units, int h, int w, int itemsize,
+                     int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
+                     int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
+    PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_embed_h: null pointer");
+    PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_embed_h: bad sizes");
+    PEEB_REQUIRE(payload_stride >= 0, "peeb_pee_embed_h: negative payload stride");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256);
+    const size_t lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
+    for (int u = 0; u < n_units; ++u)
+        PEEB_REQUIRE(n_bits[u] >= 0 && (n_bits[u] + 7) / 8 <= payload_stride, "peeb_pee_embed_h: payload %d shorter than n_bits", u);
+    const size_t pstride = align_up((size_t)std::max<int64_t>(payload_stride, max_payload_bytes(n_units, n_bits)), 16);
+    const size_t n_src = shared_src ? 1 : (size_t)n_units;
+    const size_t o_marked = n_src * img_al;
+    int rc = scratch_reserve(ws->stage, o_marked + (marked_host ? (size_t)n_units * img_al : 0) + 256); if (rc) return rc;
+    const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
+    rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
+    char* d1 = (char*)ws->stage.ptr;
+    char* d2 = (char*)ws->stage2.ptr;
+    PEEB_CUDA(cudaMemcpy2DAsync(d1, img_al, src_host, img, img, n_src, cudaMemcpyHostToDevice, st));
+    if (payload_stride > 0 && payload_host)
+        PEEB_CUDA(cudaMemcpy2DAsync(d2, pstride, payload_host, (size_t)payload_stride, (size_t)payload_stride, n_units,
+                                    cudaMemcpyHostToDevice, st));
+    rc = embed_batch_impl(ws, d1, shared_src ? 0 : (int64_t)img_al, n_units, h, w, itemsize, bit_depth, T, n_bits,
+                          (const uint8_t*)d2, (int64_t)pstride, marked_host ? d1 + o_marked : nullptr, (int64_t)img_al,
+                          lm_host ? (uint8_t*)(d2 + o_lm) : nullptr, (int64_t)lm_al, (int64_t*)(d2 + o_info), st);
+    if (rc) return rc;
+    if (marked_host) PEEB_CUDA(cudaMemcpy2DAsync(marked_host, img, d1 + o_marked, img_al, img, n_units, cudaMemcpyDeviceToHost, st));
+    if (lm_host) PEEB_CUDA(cudaMemcpy2DAsync(lm_host, lmb, d2 + o_lm, lm_al, lmb, n_units, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaMemcpyAsync(info_host, d2 + o_info, (size_t)n_units * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaStreamSynchronize(st));
+    return PEEB_OK;
+}
+
+int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                       const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host, uint8_t* payload_out_host,
+                       int64_t payload_stride, void* recovered_host, int64_t* info_host) {
+    PEEB_REQUIRE(ws && marked_host && T && n_bits && lm_host && payload_out_host && info_host, "peeb_pee_extract_h: null pointer");
+    PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_extract_h: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256);
+    const size_t lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
+    for (int u = 0; u < n_units; ++u)
+        PEEB_REQUIRE(n_bits[u] >= 0 && (n_bits[u] + 7) / 8 <= payload_stride, "peeb_pee_extract_h: payload_out %d shorter than n_bits", u);
+    const size_t pstride = align_up((size_t)std::max<int64_t>(payload_stride, max_payload_bytes(n_units, n_bits)), 16);
+    const size_t o_rec = (size_t)n_units * img_al;
+    int rc = scratch_reserve(ws->stage, o_rec + (recovered_host ? (size_t)n_units * img_al : 0) + 256); if (rc) return rc;
+    const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
+    rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
+    char* d1 = (char*)ws->stage.ptr;
+    char* d2 = (char*)ws->stage2.ptr;
+    PEEB_CUDA(cudaMemcpy2DAsync(d1, img_al, marked_host, img, img, n_units, cudaMemcpyHostToDevice, st));
+    PEEB_CUDA(cudaMemcpy2DAsync(d2 + o_lm, lm_al, lm_host, lmb, lmb, n_units, cudaMemcpyHostToDevice, st));
+    rc = extract_batch_impl(ws, d1, (int64_t)img_al, n_units, h, w, itemsize, bit_depth, T, n_bits, (const uint8_t*)(d2 + o_lm),
+                            (int64_t)lm_al, (uint8_t*)d2, (int64_t)pstride, recovered_host ? d1 + o_rec : nullptr,
+                            (int64_t)img_al, (int64_t*)(d2 + o_info), st);
+    if (rc) return rc;
+    if (recovered_host) PEEB_CUDA(cudaMemcpy2DAsync(recovered_host, img, d1 + o_rec, img_al, img, n_units, cudaMemcpyDeviceToHost, st));
+    if (payload_stride > 0)
+        PEEB_CUDA(cudaMemcpy2DAsync(payload_out_host, (size_t)payload_stride, d2, pstride, (size_t)payload_stride, n_units,
+                                    cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaMemcpyAsync(info_host, d2 + o_info, (size_t)n_units * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaStreamSynchronize(st));
+    return PEEB_OK;
+}
+
+int peeb_pee_hist_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                    uint32_t* hist_host) {
+    PEEB_REQUIRE(ws && src_host && hist_host, "peeb_pee_hist_h: null pointer");
+    PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_hist_h: bad sizes");
+    PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "peeb_pee_hist_h: bad bit_depth");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    const size_t img = (size_t)h * w * itemsize;
+    const size_t hb = (size_t)4 * (1u << (bit_depth - 1)) * sizeof(uint32_t) * n_units;
+    int rc = scratch_reserve(ws->stage, img * n_units + 256); if (rc) return rc;
+    rc = scratch_reserve(ws->stage2, hb + 256); if (rc) return rc;
+    PEEB_CUDA(cudaMemcpyAsync(ws->stage.ptr, src_host, img * n_units, cudaMemcpyHostToDevice, st));
+    rc = hist_batch_impl(ws, ws->stage.ptr, (int64_t)img, n_units, h, w, itemsize, bit_depth, (uint32_t*)ws->stage2.ptr, st);
+    if (rc) return rc;
+    PEEB_CUDA(cudaMemcpyAsync(hist_host, ws->stage2.ptr, hb, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaStreamSynchronize(st));
+    return PEEB_OK;
+}
+
+}  // extern "C"

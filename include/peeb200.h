@@ -1,0 +1,216 @@
+/* libpeeb200 -- B200 (sm_100a) kernels for the pixel-array hot path of
+ * wesleyfn/codec-tcc, behind a flat C ABI.
+ *
+ * The reference has no FFI of its own: its boundary is a set of Python
+ * callables on numpy arrays.  Each entry point below
+ * names the reference callable (file:line under the reference root) whose
+ * arithmetic it carries out; the Python package `codec_tcc_b200` binds them
+ * with ctypes and keeps the reference's names, argument meaning and error
+ * behaviour (see INTEGRATION.md for the binding a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 (PEEB_OK) or a negative PEEB_E_* code;
+ *     peeb_last_error() gives the message (thread local).  No exceptions cross
+ *     the ABI.
+ *   - `*_h` entry points take HOST pointers, do their own host<->device copies
+ *     on the workspace's stream and return after synchronising it.
+ *     All other data pointers are DEVICE pointers on the workspace's device and
+ *     the call only enqueues work on `stream` (a cudaStream_t, may be 0).
+ *   - images are C-contiguous, row-major, itemsize 1 (uint8) or 2 (uint16).
+ *   - bit strings (payloads, location maps) are packed most-significant-bit
+ *     first within each byte (numpy.packbits default; same bit order as
+ *     message_to_bits, src/codec.py:239-240).
+ *   - the library owns no user buffer.  A workspace is thread compatible, not
+ *     thread safe: one per (device, calling thread).
+ */
+#ifndef PEEB200_H
+#define PEEB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the library is built with -fvisibility=hidden: only this header is exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define PEEB_OK 0
+#define PEEB_E_CUDA (-1)     /* a CUDA runtime call failed                       */
+#define PEEB_E_CAPACITY (-2) /* PEE: payload larger than capacity / carriers     */
+#define PEEB_E_INVALID (-3)  /* bad argument                                     */
+#define PEEB_E_UNSUPPORTED (-4)
+
+#define PEEB_ABI_VERSION 1
+
+typedef struct peeb_ws peeb_ws; /* opaque workspace */
+
+/* ---- lifecycle -------------------------------------------------------- */
+int peeb_abi_version(void);
+const char* peeb_last_error(void);
+int peeb_device_count(int* n);
+int peeb_ws_create(int device, peeb_ws** ws);
+int peeb_ws_destroy(peeb_ws* ws);
+int peeb_ws_sync(peeb_ws* ws);                 /* synchronise the workspace streams  */
+void* peeb_ws_stream(peeb_ws* ws);             /* the workspace's own cudaStream_t   */
+/* tuning / debugging switches: PEEB_OPT_BULK (TMA bulk copies for band staging, default 1),
+ * PEEB_OPT_CLUSTER (cluster-resident path for small images, default 1) */
+#define PEEB_OPT_BULK 0
+#define PEEB_OPT_CLUSTER 1
+int peeb_ws_set_option(peeb_ws* ws, int option, int value);
+/* pinned host memory for callers that want full-speed PCIe copies */
+int peeb_host_alloc(size_t bytes, void** ptr);
+int peeb_host_free(void* ptr);
+/* plain device memory (callers without torch) */
+int peeb_dev_alloc(peeb_ws* ws, size_t bytes, void** ptr);
+int peeb_dev_free(peeb_ws* ws, void* ptr);
+int peeb_memcpy_h2d(peeb_ws* ws, void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int peeb_memcpy_d2h(peeb_ws* ws, void* dst_host, const void* src_dev, size_t bytes, void* stream);
+
+/* per-kernel device time accounting (CUDA events around each launch; adds a
+ * sync per launch -- for bench.py's roofline leg, never for a timed `value`) */
+#define PEEB_PROF_SLOTS 16
+enum {
+    PEEB_K_MOMENTS = 0, PEEB_K_HIST_PLANES = 1, PEEB_K_TILE_MOMENTS = 2, PEEB_K_LSB_EMBED = 3,
+    PEEB_K_PLANES_PACK = 4, PEEB_K_PLANES_UNPACK = 5, PEEB_K_COMPACT = 6,
+    PEEB_K_PEE_COUNT = 7, PEEB_K_PEE_EMBED = 8, PEEB_K_PEE_EXTRACT = 9, PEEB_K_PEE_GATHER = 10,
+    PEEB_K_PEE_HIST = 11, PEEB_K_PEE_FINAL = 12
+};
+int peeb_prof_enable(peeb_ws* ws, int on);  /* also resets the counters */
+int peeb_prof_get(peeb_ws* ws, int slot, double* total_ms, long long* launches);
+const char* peeb_prof_name(int slot);
+
+/* ---- a1-a4: distortion moments ---------------------------------------- *
+ * One pass over two images gives every integer the metrics need
+ * (AnalisadorMSE.calcular_mse src/mse.py:74-116, calcular_ssim_simples
+ * :135-179, difference statistics :202-209):
+ *   out[0]=sum (a-b)^2   out[1]=sum |a-b|   out[2]=max |a-b|   out[3]=#(a!=b)
+ *   out[4]=sum a         out[5]=sum b       out[6]=sum a^2     out[7]=sum b^2
+ *   out[8]=sum a*b       out[9]=max a       out[10]=max b      out[11]=n
+ * `out` : n_images x 12 int64 (device for the plain call, host for _h).
+ * stride_a/stride_b are in elements between consecutive images.            */
+#define PEEB_MOMENTS 12
+int peeb_moments_batch(peeb_ws* ws, const void* a, const void* b, int64_t n_per_image, int itemsize,
+                       int n_images, int64_t stride_a, int64_t stride_b, int64_t* out, void* stream);
+int peeb_moments_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
+                   int64_t* out_host);
+
+/* ---- a5: histogram + bit-plane population counts ---------------------- *
+ * Everything adaptive_modalities_decomposition / calculate_entropy /
+ * calculate_mutual_information (src/codec.py:561-599, 489-502, 504-559) need
+ * from the pixels: hist[65536] uint32 (256 used for itemsize 1) and the number
+ * of set bits in each of the 16 bit-planes.  The float64 entropy sums stay on
+ * the host so that numpy's summation order is reproduced exactly.           */
+int peeb_hist_planes(peeb_ws* ws, const void* img, int64_t n, int itemsize, uint32_t* hist,
+                     uint64_t* plane_ones, void* stream);
+int peeb_hist_planes_h(peeb_ws* ws, const void* img_host, int64_t n, int itemsize,
+                       uint32_t* hist_host, uint64_t* plane_ones_host);
+
+/* ---- a8: bit-plane pack / unpack -------------------------------------- *
+ * extract_local_planes (src/codec.py:789-793) and the plane split of
+ * adaptive_modalities_decomposition (:571): planes[k][i] = (img[i] >> (first+k)) & 1,
+ * itemsize preserved.  merge_modalities (:215-237): out = OR_k (trunc(planes[k]) << k),
+ * out_itemsize = 2 when n_planes > 8 else 1.                                */
+int peeb_planes_unpack(peeb_ws* ws, const void* img, int64_t n, int itemsize, int first_plane,
+                       int n_planes, void* planes_out, void* stream);
+int peeb_planes_unpack_h(peeb_ws* ws, const void* img_host, int64_t n, int itemsize, int first_plane,
+                         int n_planes, void* planes_out_host);
+int peeb_planes_pack(peeb_ws* ws, const void* planes, int64_t n, int in_itemsize, int n_planes,
+                     void* img_out, void* stream);
+/* planes given as n_planes separate host arrays (the reference passes a list) */
+int peeb_planes_pack_h(peeb_ws* ws, const void* const* plane_ptrs_host, int64_t n, int in_itemsize,
+                       int n_planes, void* img_out_host);
+
+/* ---- a6: tile statistics for the hybrid embedder ---------------------- *
+ * lsb_embed_block_then_multiplane scans sbs x sbs tiles (edge tiles clipped) of
+ * local plane 0 for the largest float(np.var(tile)) (src/codec.py:441-450).
+ * The variance of a tile of n values is (n*sum(v^2) - sum(v)^2) / n^2, an exact
+ * rational; the device returns sum(v) and sum(v^2) per tile (row-major over
+ * tiles, 2 x int64 each) and the host does the exact comparison (and settles
+ * float ties on the few candidate tiles, see codec.py in the package).       */
+int peeb_tile_moments(peeb_ws* ws, const void* plane, int h, int w, int itemsize, int sbs,
+                      int64_t* sums_out, void* stream);
+int peeb_tile_moments_h(peeb_ws* ws, const void* plane_host, int h, int w, int itemsize, int sbs,
+                        int64_t* sums_out_host);
+
+/* ---- a6/a7: LSB embed with XOR side bitmaps --------------------------- *
+ * lsb_embed_multi_plane (src/codec.py:276-318) and the embedding loop of
+ * lsb_embed_block_then_multiplane (:456-485).  For plane p (0 <= p < s) the
+ * raster positions (start[p] + k) mod n, 0 <= k < len[p], receive
+ * (v & 0xFE) | bit where bit = payload bit (bit_off[p] + k); every other
+ * position is copied.  bitmaps[p][i] = uint8(v ^ new) (0 where untouched).
+ * planes_in/planes_out: s x n elements of `itemsize`; bitmaps: s x n uint8.  */
+int peeb_lsb_embed(peeb_ws* ws, const void* planes_in, int64_t n, int itemsize, int s,
+                   const int64_t* start, const int64_t* len, const int64_t* bit_off,
+                   const uint8_t* payload, int64_t payload_bits, void* planes_out, uint8_t* bitmaps,
+                   void* stream);
+int peeb_lsb_embed_h(peeb_ws* ws, const void* const* plane_ptrs_host, int64_t n, int itemsize, int s,
+                     const int64_t* start, const int64_t* len, const int64_t* bit_off,
+                     const uint8_t* payload_host, int64_t payload_bits, void* planes_out_host,
+                     uint8_t* bitmaps_out_host);
+
+/* ---- a9: decode_message's gather -------------------------------------- *
+ * src/codec.py:767-771: the least significant bits of `plane` at the first
+ * `limit` positions where `bitmap` is non-zero, packed MSB first into
+ * bits_out (ceil(limit/8) bytes rounded up to a multiple of 4, 4-byte aligned, zero padded); *count_out = how many were
+ * found (<= limit).                                                         */
+int peeb_compact_bits(peeb_ws* ws, const void* plane, const uint8_t* bitmap, int64_t n, int itemsize,
+                      int64_t limit, uint8_t* bits_out, int64_t* count_out, void* stream);
+int peeb_compact_bits_h(peeb_ws* ws, const void* plane_host, const uint8_t* bitmap_host, int64_t n,
+                        int itemsize, int64_t limit, uint8_t* bits_out_host, int64_t* count_out_host);
+
+/* ---- a10: Prediction-Error Expansion ---------------------------------- *
+ * Not in the reference; specified in SURVEY.md Appendix A.
+ * Units (images) are independent; a batch is n_units images of h x w with byte
+ * strides between them.  src_stride may be 0 (every unit embeds into the same
+ * cover -- the threshold sweep).  T[u], n_bits[u] are HOST arrays.
+ * info: n_units x 8 int64 = {T, n_bits, capacity, cap0, cap1, n_flagged, sse, status}
+ * with status 0 or PEEB_E_CAPACITY (the embed is still the zero-padded embed of
+ * the first `capacity` bits, which is what a sweep wants).  The function's own
+ * return value reports only launch problems.
+ * payload: per unit, at least peeb_payload_bytes(n_bits[u]) readable bytes at
+ * payload + u*payload_stride, 4-byte aligned.  marked / lm may be NULL (sweep:
+ * statistics only).  lm: h x ceil(w/8) bytes per unit, np.packbits(axis=1).  */
+#define PEEB_INFO 8
+size_t peeb_payload_bytes(int64_t n_bits); /* round_up(ceil(n_bits/8),4)+8 */
+int peeb_pee_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w,
+                         int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
+                         const uint8_t* payload, int64_t payload_stride, void* marked,
+                         int64_t marked_stride, uint8_t* lm, int64_t lm_stride, int64_t* info,
+                         void* stream);
+/* payload_out: per unit peeb_payload_bytes(n_bits[u]) writable bytes, 4-byte aligned */
+int peeb_pee_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h,
+                           int w, int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
+                           const uint8_t* lm, int64_t lm_stride, uint8_t* payload_out,
+                           int64_t payload_stride, void* recovered, int64_t recovered_stride,
+                           int64_t* info, void* stream);
+/* hist: n_units x 2 x (2*tmax) uint32, hist[u][c][e+tmax], tmax = 2^(bit_depth-1):
+ * prediction errors of the original image per colour over interior pixels not
+ * flagged for expansion (Appendix A, threshold selection). */
+int peeb_pee_hist_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w,
+                        int itemsize, int bit_depth, uint32_t* hist, void* stream);
+
+/* host-buffer variants: contiguous batches, copies inside, synchronous.
+ * payload_stride as above (host bytes); lm_stride = h*ceil(w/8). */
+int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_units, int h, int w,
+                     int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
+                     const uint8_t* payload_host, int64_t payload_stride, void* marked_host,
+                     uint8_t* lm_host, int64_t* info_host);
+int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize,
+                       int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host,
+                       uint8_t* payload_out_host, int64_t payload_stride, void* recovered_host,
+                       int64_t* info_host);
+int peeb_pee_hist_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize,
+                    int bit_depth, uint32_t* hist_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEEB200_H */

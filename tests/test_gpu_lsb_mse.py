@@ -1,0 +1,150 @@
+"""GPU parity: the reference's bit-plane LSB path and distortion metrics
+(rows a1-a9), CUDA through the C ABI, against the golden vectors produced by
+the unmodified reference and against the numpy restatement on random inputs."""
+import numpy as np
+import pytest
+
+from codec_tcc_b200 import codec, mse
+from codec_tcc_b200.synth import synth_image, synth_saturated
+
+from oracle import codec_numpy as OC
+from oracle import mse_numpy as OM
+
+import _golden_checks as GC
+
+pytestmark = pytest.mark.gpu
+
+IMAGES = ["pe", "torax", "synth16_257x301", "synth12_300x200", "synth8_129x70", "sat12_96x160"]
+
+
+class _Metrics(mse.AnalisadorMSE):
+    pass
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_entropy_mi_split(golden, golden_images, name):
+    GC.check_entropy_and_split(codec, golden_images[name], golden["images"][name])
+
+
+@pytest.mark.parametrize("name", IMAGES)
+@pytest.mark.parametrize("case_idx", range(6))
+def test_lsb_golden_cases(golden, golden_images, name, case_idx):
+    GC.check_lsb_case(codec, _Metrics(), golden_images[name], golden["images"][name]["lsb_cases"][case_idx])
+
+
+def _bits(n, seed):
+    rng = np.random.default_rng(seed)
+    return "".join("1" if b else "0" for b in rng.integers(0, 2, n).tolist())
+
+
+@pytest.mark.parametrize("idx", range(7))
+def test_lsb_random_vs_restatement(idx):
+    img, beta, sbs = [
+        (synth_image(67, 45, 255, 1), 0.5, 8),
+        (synth_image(50, 130, 4095, 2), 0.7, 16),
+        (synth_image(33, 33, 65535, 3), 0.9, 7),
+        (synth_saturated(40, 56, 255, 4), 0.3, 4),
+        (np.zeros((20, 24), np.uint16), 0.8, 8),
+        (np.full((9, 9), 255, np.uint8), 0.8, 16),
+        (synth_image(400, 1000, 4095, 8), 0.8, 16),
+    ][idx]
+    g0, l0 = OC.adaptive_modalities_decomposition(img, beta=beta)
+    g1, l1 = codec.adaptive_modalities_decomposition(img, beta=beta)
+    assert len(l0) == len(l1) and all(np.array_equal(a, b) and a.dtype == b.dtype for a, b in zip(l0 + g0, l1 + g1))
+    for n_payload in (0, 1, 5, 1000, img.size * 3):
+        bits = _bits(n_payload, idx)
+        for align in (False, True):
+            r = OC.lsb_embed_block_then_multiplane(l0, bits, search_block_size=sbs, align_across_planes=align)
+            o = codec.lsb_embed_block_then_multiplane(l1, bits, search_block_size=sbs, align_across_planes=align)
+            _same(r, o)
+        r = OC.lsb_embed_multi_plane(l0, bits)
+        o = codec.lsb_embed_multi_plane(l1, bits)
+        _same(r, o)
+        meta = {"s": len(l0), "segments_indices": r[4], "segments_lengths": r[3]}
+        assert OC.decode_message(r[0], [b.ravel() for b in r[1]], meta) == \
+            codec.decode_message(o[0], [b.ravel() for b in o[1]], meta)
+        st0, st1 = OC.merge_modalities(g0, r[0]), codec.merge_modalities(g1, o[0])
+        assert st0.dtype == st1.dtype and np.array_equal(st0, st1)
+        for a, b in zip(OC.extract_local_planes(st0, len(l0)), codec.extract_local_planes(st1, len(l0))):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def _same(r, o):
+    assert r[2] == o[2] and list(r[3]) == list(o[3]) and list(r[4]) == list(o[4])
+    for a, b in zip(r[0], o[0]):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    for a, b in zip(r[1], o[1]):
+        assert a.dtype == b.dtype == np.uint8 and np.array_equal(a, b)
+
+
+def test_metrics_scalars(golden):
+    an = mse.AnalisadorMSE()
+    sc = golden["scalars"]
+    m, r = an.calcular_mse([[10, 20], [30, 40]], [[10, 20], [30, 41]])
+    assert abs(float(m) - sc["mse_norm_small"][0]) <= 1e-12 and float(r) == 41.0
+    a = synth_image(120, 90, 4095, 21)
+    b = a.copy(); b[5, 7] += 900; b[60:70, 10:50] ^= 3
+    m, r = an.calcular_mse(a, b)
+    assert abs(float(m) - sc["mse_norm_synth"][0]) <= 1e-9 * sc["mse_norm_synth"][0] and float(r) == sc["mse_norm_synth"][1]
+    assert abs(float(an.calcular_ssim_simples(a, b)) - sc["ssim_norm_synth"]) <= 1e-9
+    m, r = an.calcular_mse(a, a)
+    assert [float(m), float(r)] == sc["mse_same"] and an.calcular_psnr(m, r) == float("inf")
+    assert float(an.calcular_ssim_simples(a, a)) == 1.0
+    with pytest.raises(ValueError):
+        an.calcular_mse(np.zeros((2, 3), np.uint8), np.zeros((3, 2), np.uint8))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 13), (512, 512), (1000, 1003), (3000, 3000)])
+@pytest.mark.parametrize("maxval", [255, 4095, 65535])
+def test_moments_exact(shape, maxval):
+    """int64 moments against numpy; MSE exact, PSNR/SSIM within 1e-9 relative
+    of the float64 element-wise restatement (BASELINE.json tolerance)."""
+    a = synth_image(shape[0], shape[1], maxval, 5)
+    rng = np.random.default_rng(shape[0])
+    b = a.copy()
+    k = max(1, a.size // 7)
+    ys, xs = rng.integers(0, shape[0], k), rng.integers(0, shape[1], k)
+    b[ys, xs] = rng.integers(0, maxval + 1, k).astype(a.dtype)
+    b.flat[0] = a.max()  # keep equal maxima: the exact (non-normalised) branch
+    if b.max() != a.max():
+        b[b > a.max()] = a.max()
+    mm = mse.image_moments(a, b)
+    ai, bi = a.astype(np.int64), b.astype(np.int64)
+    d = ai - bi
+    assert mm["sse"] == int((d * d).sum()) and mm["sad"] == int(np.abs(d).sum())
+    assert mm["max_abs"] == int(np.abs(d).max()) and mm["changed"] == int((d != 0).sum())
+    assert mm["sum_a"] == int(ai.sum()) and mm["sum_b"] == int(bi.sum()) and mm["sum_ab"] == int((ai * bi).sum())
+    assert mm["sum_aa"] == int((ai * ai).sum()) and mm["sum_bb"] == int((bi * bi).sum())
+    assert mm["max_a"] == int(a.max()) and mm["max_b"] == int(b.max()) and mm["n"] == a.size
+    an = mse.AnalisadorMSE()
+    m1, r1 = an.calcular_mse(a, b)
+    m0, r0 = OM.calcular_mse(a, b)
+    assert float(m1) == float(m0) and float(r1) == float(r0)  # bit-exact MSE
+    p1, p0 = an.calcular_psnr(m1, r1), OM.calcular_psnr(m0, r0)
+    assert p1 == p0 or abs(p1 - p0) <= 1e-9 * abs(p0)
+    s1, s0 = float(an.calcular_ssim_simples(a, b)), float(OM.calcular_ssim_simples(a, b))
+    assert abs(s1 - s0) <= 1e-9
+    st1, st0 = an.difference_stats(a, b), OM.difference_stats(a, b)
+    assert float(st1[0]) == float(st0[0]) and float(st1[1]) == float(st0[1]) and int(st1[2]) == int(st0[2])
+    assert abs(float(st1[3]) - float(st0[3])) <= 1e-12
+
+
+def test_normalisation_branch_and_mixed_inputs():
+    an = mse.AnalisadorMSE()
+    a = synth_image(200, 300, 4095, 2)
+    b = a.copy(); b[0, 0] = 4095 if a.max() < 4095 else a.max() - 5; b[50:60] ^= 1
+    m1, r1 = an.calcular_mse(a, b)
+    m0, r0 = OM.calcular_mse(a, b)
+    assert abs(float(m1) - float(m0)) <= 1e-9 * float(m0) and float(r1) == float(r0)
+    assert abs(float(an.calcular_ssim_simples(a, b)) - float(OM.calcular_ssim_simples(a, b))) <= 1e-9
+    # list / int64 / uint8-vs-uint16 inputs
+    m1, _ = an.calcular_mse(a.astype(np.int64), b.tolist())
+    assert abs(float(m1) - float(m0)) <= 1e-9 * float(m0)
+    c = synth_image(64, 64, 255, 3)
+    m1, r1 = an.calcular_mse(c, c.astype(np.uint16) + 1)
+    m0, r0 = OM.calcular_mse(c, c.astype(np.uint16) + 1)
+    assert abs(float(m1) - float(m0)) <= 1e-9 * float(m0) and float(r1) == float(r0)
+    res = an.analisar_par_arrays(a, b, "par")
+    assert set(res) >= {"mse", "psnr", "ssim", "diferenca_media", "diferenca_max", "percentual_mudanca"}
+    with pytest.raises(TypeError):
+        an.calcular_mse(a.astype(np.float64) + 0.5, b)
