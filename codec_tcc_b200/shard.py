@@ -1,0 +1,66 @@
+"""Image-wise sharding of slice batches / series over the GPUs of one box
+(SURVEY.md section 8e).  Images are independent units, so ranks take contiguous
+blocks and there is NO collective on the data path; the only exchange is an
+optional final gather of the per-image statistics (a few int64 per image)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def rank_world():
+    """(rank, world) from torch.distributed if initialised, else the launcher env."""
+    try:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def partition(n_units: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of rank ``rank``: sizes differ by at most one,
+    earlier ranks take the larger blocks."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_units, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def partition_grid(n_images: int, n_params: int, world: int, rank: int):
+    """The threshold sweep's unit is the (image, T) pair:
+    flat index u = image * n_params + param, contiguous blocks of it."""
+    lo, hi = partition(n_images * n_params, world, rank)
+    u = np.arange(lo, hi)
+    return u // max(n_params, 1), u % max(n_params, 1)
+
+
+def gather_stats(local_stats, n_total: int | None = None):
+    """all_gather of per-image int64 statistics (rows) -> (n_total, k) on every
+    rank.  Works on the NCCL backend (CUDA tensors) and on gloo (CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    t = local_stats if isinstance(local_stats, torch.Tensor) else torch.as_tensor(np.asarray(local_stats))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t
+    world = dist.get_world_size()
+    if dist.get_backend() == "nccl" and not t.is_cuda:
+        t = t.cuda()
+    counts = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
+    counts = [int(c.item()) for c in counts]
+    width = t.shape[1] if t.dim() > 1 else 1
+    pad = max(counts)
+    buf = torch.zeros((pad, width), dtype=t.dtype, device=t.device)
+    buf[: t.shape[0]] = t.reshape(t.shape[0], width)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    out = torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+    if n_total is not None and out.shape[0] != n_total:
+        raise RuntimeError(f"gathered {out.shape[0]} rows, expected {n_total}")
+    return out

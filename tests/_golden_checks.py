@@ -62,7 +62,10 @@ def check_lsb_case(impl, metrics, img, case, quiet=None):
     assert np.array_equal(back, img if back.dtype == img.dtype else img.astype(back.dtype))
     if metrics is not None:
         m, rng_ = metrics.calcular_mse(img, stego)
-        assert float(m) == case["mse"], (float(m), case["mse"])  # exact: int64 SSE / N
+        if int(img.max()) == int(stego.max()):
+            assert float(m) == case["mse"], (float(m), case["mse"])  # exact: int64 SSE / N
+        else:  # the reference rescales both images in floating point (src/mse.py:101-106)
+            assert abs(float(m) - case["mse"]) <= 1e-9 * case["mse"], (float(m), case["mse"])
         assert float(rng_) == case["max_range"]
         psnr = metrics.calcular_psnr(m, rng_)
         assert abs(float(psnr) - case["psnr"]) <= 1e-9 * abs(case["psnr"])
