@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Headline benchmark: PEE embed + extract round trip, Mpixel/s (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" = one max-capacity embed followed by one extract + recovery over one
+batch of synthetic DICOM-shaped images.  Workloads (BASELINE.json configs):
+  ct512   512 slices of 512x512, 16-bit  (configs[2]; the default; PER GPU -> weak scaling)
+  dx3000  64 radiographs of 3000x3000, 12-bit in uint16  (configs[3])
+  slice   one 512x512 16-bit slice  (configs[1]; latency case, L2 resident)
+Printed: ONE JSON line (rank 0).  `value` is device-resident throughput (inputs
+in HBM when the clock starts), `e2e` the same metric through the numpy API with
+pinned host buffers and both PCIe copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_images per GPU, h, w, maxval, bit_depth, T)
+    "ct512": (512, 512, 512, 65535, 16, 96),
+    "dx3000": (64, 3000, 3000, 4095, 12, 12),
+    "slice": (1, 512, 512, 65535, 16, 96),
+}
+METRIC = "pee_embed_extract_roundtrip_throughput"
+UNIT = "Mpixel/s"
+
+# ------------------------------------------------------------------ CPU legs (oracle port of the numpy path)
+_CPU = {}
+
+
+def _cpu_roundtrip(k):
+    """One image through the numpy oracle: embed at its capacity, extract, recover."""
+    from oracle import pee_numpy as PN
+
+    img, pay, T, bd = _CPU["imgs"][k], _CPU["pays"][k], _CPU["T"], _CPU["bd"]
+    bits = PN.payload_to_bits(pay, None)
+    maxval = (1 << bd) - 1
+    cur, lm, cap0, cap1 = PN.embed_fixed_T(img, bits, T, maxval)  # zero-padded: every carrier is expanded
+    cap = cap0 + cap1
+    marked = cur.astype(img.dtype)
+    out, rec = PN.pee_extract(marked, np.packbits(lm, axis=1), T, cap, bd)
+    ok = bool(np.array_equal(rec, img)) and bool(np.array_equal(np.unpackbits(out)[:cap], bits[:cap]))
+    return img.size, ok
+
+
+def cpu_port_throughput(name, n_sample, repeats=1):
+    """Mpixel/s of the numpy oracle over `n_sample` images of the workload, image
+    parallel over every host core this process may use (fork pool)."""
+    import multiprocessing as mp
+
+    from codec_tcc_b200.synth import synth_image
+
+    n, h, w, maxval, bd, T = WORKLOADS[name]
+    rng = np.random.default_rng(99)
+    _CPU.update(T=T, bd=bd)
+    _CPU["imgs"] = [synth_image(h, w, maxval, 1000 + k) for k in range(n_sample)]
+    _CPU["pays"] = [rng.integers(0, 256, (h * w + 7) // 8, dtype=np.uint8) for _ in range(n_sample)]
+    cores = len(os.sched_getaffinity(0))
+    procs = max(1, min(cores, n_sample))
+    times = []
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_cpu_roundtrip, range(min(procs, n_sample)))  # warm the workers
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_roundtrip, range(n_sample), chunksize=1)
+            times.append(time.perf_counter() - t0)
+    assert all(ok for _, ok in res), "CPU oracle round trip failed"
+    px = sum(p for p, _ in res)
+    return px, times, procs
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference is pure numpy and ships no PEE code
+    (SURVEY.md F2), so the CPU arm is the numpy oracle port of the same path on
+    the host cores, a bounded sample of the workload per step."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    n, h, w, maxval, bd, T = WORKLOADS[args.workload]
+    per_step = max(1, min(n, 4 * cores if h * w <= 1 << 20 else max(1, cores // 2)))
+    px, times, procs = cpu_port_throughput(args.workload, per_step, repeats=args.steps + args.warmup)
+    timed = times[args.warmup:]
+    sec = sum(timed) / len(timed)
+    value = px / sec / 1e6
+    sample = f"{per_step} of {n} images of workload {args.workload} per step, numpy oracle, fork pool of {procs}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16" if maxval > 255 else "u8", "data": "synthetic",
+        "config": workload_config(args.workload, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, world):
+    n, h, w, maxval, bd, T = WORKLOADS[name]
+    return {
+        "workload": f"{name}: {n} images/GPU of {h}x{w}, {bd}-bit in uint{16 if maxval > 255 else 8}, "
+                    f"PEE T={T}, payload = capacity (max-capacity embed + extract + recovery)",
+        "images_per_gpu": n, "height": h, "width": w, "bit_depth": bd, "T": T,
+        "parallelism": f"image-sharded x{world}, no data-path collective",
+        "l2": "inputs larger than L2 (no flush needed)" if n * h * w * 2 > 130e6 else "L2 flushed between steps",
+    }
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ the GPU arm
+def run_gpu_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    name = args.workload
+    n, h, w, maxval, bd, T = WORKLOADS[name]
+    npx = n * h * w
+
+    # CPU baseline first (fork pool before CUDA is initialised in this process)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        big = h * w > 1 << 20
+        n_sample = 12 if big else 192
+        px, times, procs = cpu_port_throughput(name, n_sample)
+        cpu_baseline = {"value": px / times[0] / 1e6, "unit": UNIT, "cores": procs, "kind": "port",
+                        "sample": f"{n_sample} images of {h}x{w} from the same generator, numpy oracle "
+                                  f"(oracle/pee_numpy.py) embed+extract, fork pool of {procs}, {times[0]:.1f} s wall"}
+
+    import torch
+    import torch.distributed as dist
+
+    from codec_tcc_b200 import _cabi, device as D, pee, shard
+    from codec_tcc_b200.synth import synth_batch
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["PEEB_DEVICE"] = str(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- synthetic inputs (host, pinned) and device copies
+    t0 = time.perf_counter()
+    imgs_h = _cabi.pinned_empty((n, h, w), np.uint16 if maxval > 255 else np.uint8)
+    imgs_h[...] = synth_batch(n, h, w, maxval, 2 + rank * n)
+    stride = D.payload_stride(h * w)
+    pays_h = _cabi.pinned_empty((n, stride), np.uint8)
+    pays_h[...] = np.random.default_rng(7 + rank).integers(0, 256, (n, stride), dtype=np.uint8)
+    tdt = torch.int16 if imgs_h.dtype == np.uint16 else torch.uint8
+    d_imgs = torch.from_numpy(imgs_h.view(np.int16) if imgs_h.dtype == np.uint16 else imgs_h).to(dev)
+    d_pays = torch.from_numpy(pays_h).to(dev)
+    gen_s = time.perf_counter() - t0
+
+    # ---- capacity of every image with this payload stream (one untimed embed, nothing written)
+    big = np.full(n, h * w, np.int64)
+    _, _, d_info = D.pee_embed_device(d_imgs, d_pays, big, T, bd, marked=False, lm=False)
+    cap = d_info[:, 2].cpu().numpy().astype(np.int64)
+    assert (cap > 0).all()
+
+    d_marked = torch.empty_like(d_imgs)
+    d_lm = torch.empty((n, h, (w + 7) // 8), dtype=torch.uint8, device=dev)
+    d_rec = torch.empty_like(d_imgs)
+    d_out = torch.empty((n, stride), dtype=torch.uint8, device=dev)
+    d_info_e = torch.empty((n, 8), dtype=torch.int64, device=dev)
+    d_info_x = torch.empty((n, 8), dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if npx * 2 <= 130e6 else None
+
+    def step():
+        D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm, info=d_info_e)
+        D.pee_extract_device(d_marked, d_lm, T, cap, bd, payload_out=d_out, recovered=d_rec, info=d_info_x)
+
+    def timed_steps(k):
+        """K steps, CUDA events on the launching stream; with a small workload the
+        L2 is flushed between steps and only the steps are timed."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        for a, b in ev:
+            if flush is not None:
+                flush.fill_(1)
+            a.record()
+            step()
+            b.record()
+        torch.cuda.synchronize(dev)
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ms_total = timed_steps(args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = npx * world / (ms_step * 1e-3) / 1e6
+
+    # ---- correctness of what was just timed: identity round trip + oracle on a bounded sample
+    assert torch.equal(d_rec, d_imgs), "recovered images differ from the originals"
+    xi = d_info_x.cpu().numpy()
+    ei = d_info_e.cpu().numpy()
+    assert (xi[:, 7] == 0).all() and (ei[:, 7] == 0).all() and np.array_equal(xi[:, 2], cap) and np.array_equal(ei[:, 2], cap)
+    out_h = d_out.cpu().numpy()
+    for u in range(0, n, max(1, n // 16)):
+        nb_, rem = int(cap[u]) // 8, int(cap[u]) % 8
+        assert np.array_equal(out_h[u, :nb_], pays_h[u, :nb_]), "extracted payload differs"
+        if rem:
+            assert int(out_h[u, nb_]) == int(pays_h[u, nb_]) & ((0xFF00 >> rem) & 0xFF)
+    if rank == 0:
+        from oracle import pee_c
+        marked_h = d_marked[:2].cpu().numpy().view(imgs_h.dtype)
+        lm_h = d_lm[:2].cpu().numpy()
+        for u in range(min(2, n)):
+            m0, lm0, i0 = pee_c.embed(imgs_h[u], pays_h[u], int(cap[u]), T, bd)
+            assert np.array_equal(marked_h[u], m0) and np.array_equal(lm_h[u], lm0) and i0["sse"] == int(ei[u, 6]), \
+                "GPU embed differs from the CPU oracle"
+
+    # ---- per-kernel device time (events around every launch; separate pass, not the timed one)
+    ws = _cabi.workspace(local)
+    ws.prof_enable(True)
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+        step()
+    torch.cuda.synchronize(dev)
+    prof = ws.prof_report()
+    ws.prof_enable(False)
+    item = imgs_h.dtype.itemsize
+    alg = {"pee_embed": 2 * item + 0.25, "pee_extract": 2 * item + 0.25, "pee_count": float(item),
+           "pee_gather": 0.25, "pee_finalize": 0.0}
+    kernels = {}
+    for kname, (ms, calls) in prof.items():
+        avg = ms / calls
+        kernels[kname] = {"avg_ms": avg, "launches_per_step": calls / args.steps,
+                          "algorithmic_gb_per_s": (alg.get(kname, 0.0) * npx / 1e9) / (avg * 1e-3) if avg > 0 else None}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(name, {}).get(dom)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_gb_per_s"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["algorithmic_gb_per_s"] / peak, "traffic": traffic,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_pixel": alg[dom],
+                "step_algorithmic_gb_per_s": (4 * item + 0.5) * npx / 1e9 / (ms_step * 1e-3),
+                "step_frac": (4 * item + 0.5) * npx / 1e9 / (ms_step * 1e-3) / peak}
+
+    # ---- end to end through the numpy API: pinned host buffers, both copies inside the clock
+    marked_p = _cabi.pinned_empty((n, h, w), imgs_h.dtype)
+    lm_p = _cabi.pinned_empty((n, h, (w + 7) // 8), np.uint8)
+    rec_p = _cabi.pinned_empty((n, h, w), imgs_h.dtype)
+    out_p = _cabi.pinned_empty((n, (h * w + 7) // 8), np.uint8)
+    pay_p = _cabi.pinned_empty((n, (h * w + 7) // 8), np.uint8)
+    pay_p[...] = pays_h[:, :pay_p.shape[1]]
+
+    def e2e_step():
+        _, _, ie = pee.pee_embed_batch(imgs_h, pay_p, cap, T, bd, out_marked=marked_p, out_lm=lm_p, device=local)
+        _, _, ix = pee.pee_extract_batch(marked_p, lm_p, T, cap, bd, out_recovered=rec_p, out_payload=out_p, device=local)
+        return ie, ix
+
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ie, ix = e2e_step()
+    sec = time.perf_counter() - t0
+    barrier()
+    t = torch.tensor([sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps * 1e3
+    assert np.array_equal(rec_p, imgs_h) and (ie[:, 7] == 0).all() and (ix[:, 7] == 0).all()
+    lmb = lm_p.nbytes
+    h2d = imgs_h.nbytes + pay_p.nbytes + marked_p.nbytes + lmb
+    d2h = marked_p.nbytes + lmb + rec_p.nbytes + out_p.nbytes + 2 * n * 64
+    e2e = {"value": npx * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "codec_tcc_b200.pee.pee_embed_batch + pee_extract_batch (numpy in / numpy out, pinned host buffers)"}
+
+    stats = shard.gather_stats(d_info_e[:, :7]) if world > 1 else d_info_e
+    if rank == 0:
+        launches_per_step = sum(v["launches_per_step"] for v in kernels.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16" if item == 2 else "u8", "data": "synthetic",
+            "config": workload_config(name, world), "roofline": roofline, "kernels": kernels, "e2e": e2e,
+            "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
+            "capacity_bpp": float(cap.mean() / (h * w)), "images_total": int(stats.shape[0]),
+            "bit_exact": "round trip identity on all images; first 2 images == CPU oracle (oracle/pee_ref.c)",
+            "setup_s": gen_s,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="ct512", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
