@@ -56,32 +56,37 @@ struct PeeBatch {
 };
 
 // ------------------------------------------------------------------ pixels
-template <typename PixT> struct Px;
-template <> struct Px<unsigned short> {
+// Four neighbouring pixels of one lane, kept packed in registers (one 64-bit / 32-bit
+// shared-memory word); fields are extracted on demand.
+template <typename PixT> struct Row4;
+template <> struct Row4<unsigned short> {
+    uint2 v;
     static constexpr int ITEM = 2;
-    __device__ static __forceinline__ void load4(const unsigned char* row, int c0, int (&m)[4]) {
-        const uint2 v = *reinterpret_cast<const uint2*>(row + 2 * c0);
-        m[0] = v.x & 0xffff; m[1] = v.x >> 16; m[2] = v.y & 0xffff; m[3] = v.y >> 16;
+    __device__ __forceinline__ void load(const unsigned char* p) { v = *reinterpret_cast<const uint2*>(p); }
+    __device__ __forceinline__ void store(unsigned char* p) const { *reinterpret_cast<uint2*>(p) = v; }
+    template <int K> __device__ __forceinline__ int f() const {
+        return K == 0 ? (int)(v.x & 0xffffu) : K == 1 ? (int)(v.x >> 16) : K == 2 ? (int)(v.y & 0xffffu) : (int)(v.y >> 16);
     }
-    __device__ static __forceinline__ void store4(unsigned char* row, int c0, const int (&m)[4]) {
-        uint2 v;
-        v.x = (unsigned)m[0] | ((unsigned)m[1] << 16);
-        v.y = (unsigned)m[2] | ((unsigned)m[3] << 16);
-        *reinterpret_cast<uint2*>(row + 2 * c0) = v;
+    template <int K> __device__ __forceinline__ void set(int a) {
+        if (K == 0) v.x = __byte_perm(v.x, (unsigned)a, 0x3254);
+        else if (K == 1) v.x = __byte_perm(v.x, (unsigned)a, 0x5410);
+        else if (K == 2) v.y = __byte_perm(v.y, (unsigned)a, 0x3254);
+        else v.y = __byte_perm(v.y, (unsigned)a, 0x5410);
     }
     __device__ static __forceinline__ int load1(const unsigned char* row, int c) {
         return *reinterpret_cast<const unsigned short*>(row + 2 * c);
     }
 };
-template <> struct Px<unsigned char> {
+template <> struct Row4<unsigned char> {
+    unsigned v;
     static constexpr int ITEM = 1;
-    __device__ static __forceinline__ void load4(const unsigned char* row, int c0, int (&m)[4]) {
-        const unsigned v = *reinterpret_cast<const unsigned*>(row + c0);
-        m[0] = v & 0xff; m[1] = (v >> 8) & 0xff; m[2] = (v >> 16) & 0xff; m[3] = v >> 24;
-    }
-    __device__ static __forceinline__ void store4(unsigned char* row, int c0, const int (&m)[4]) {
-        *reinterpret_cast<unsigned*>(row + c0) =
-            (unsigned)m[0] | ((unsigned)m[1] << 8) | ((unsigned)m[2] << 16) | ((unsigned)m[3] << 24);
+    __device__ __forceinline__ void load(const unsigned char* p) { v = *reinterpret_cast<const unsigned*>(p); }
+    __device__ __forceinline__ void store(unsigned char* p) const { *reinterpret_cast<unsigned*>(p) = v; }
+    template <int K> __device__ __forceinline__ int f() const { return (int)((v >> (8 * K)) & 0xffu); }
+    template <int K> __device__ __forceinline__ void set(int a) {
+        // byte K <- a (a <= 255)
+        constexpr unsigned sel = K == 0 ? 0x3214u : K == 1 ? 0x3240u : K == 2 ? 0x3410u : 0x4210u;
+        v = __byte_perm(v, (unsigned)a, sel);
     }
     __device__ static __forceinline__ int load1(const unsigned char* row, int c) { return row[c]; }
 };
@@ -131,17 +136,28 @@ __device__ __forceinline__ int window_bit(unsigned hi, unsigned lo, int k) {  //
 __device__ __forceinline__ unsigned lm_bitmask(int j) { return 1u << (8 * ((j >> 3) & 3) + 7 - (j & 7)); }
 
 // ------------------------------------------------------------------ shared layout
-__host__ __device__ inline size_t band_smem_bytes(const PeeGeom& g, bool extract) {
-    size_t img = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
-    size_t lm = align_up((size_t)(g.R + 2) * g.lmpitch, 16);
-    size_t cnt = align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
-    size_t total = img + lm + cnt + 64 * sizeof(int) + 16;
-    if (extract) {
-        total += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);  // xbits, 2 passes
-        total += align_up((size_t)g.R * g.S * sizeof(int), 16);                            // second count table
-        total += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);                 // 2 streams
+struct SmemLayout {
+    size_t img, lm, tab, side, ball, misc, bar, xb, tab0, stream, total;
+};
+__host__ __device__ inline SmemLayout band_layout(const PeeGeom& g, int kind /*0 count, 1 embed, 2 extract*/) {
+    SmemLayout L{};
+    size_t o = 0;
+    L.img = o; o += align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
+    L.lm = o; o += align_up((size_t)(g.R + 2) * g.lmpitch, 16);
+    L.tab = o; o += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
+    L.misc = o; o += 64 * sizeof(int);
+    L.bar = o; o += 16;
+    L.side = L.ball = L.xb = L.tab0 = L.stream = o;
+    if (kind == 1) {
+        L.side = o; o += align_up((size_t)g.R * g.S * 32 * sizeof(unsigned), 16);   // pass-1 values with a zero bit
+        L.ball = o; o += align_up((size_t)g.R * g.S * sizeof(uint2), 16);           // pass-1 carrier ballots
+    } else if (kind == 2) {
+        L.xb = o; o += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);
+        L.tab0 = o; o += align_up((size_t)g.R * g.S * sizeof(int), 16);
+        L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
     }
-    return total;
+    L.total = o;
+    return L;
 }
 
 // Cooperative copy of image rows [lo, hi) of a unit into the band buffer.
@@ -200,128 +216,273 @@ __device__ __forceinline__ void store_rows(const PeeGeom& g, unsigned char* unit
     }
 }
 
-// ------------------------------------------------------------------ embed sweeps
-// One colour pass over rows [row_lo, row_hi) of the band buffer, split into warp
-// items (strip, chunk of rows).  APPLY=false: count carriers per (row, strip) into
-// tab[(row-row_lo)*S + strip].  APPLY=true: tab holds the payload bit index of the
-// first carrier of each (row, strip); pixels are rewritten in place.
+// ------------------------------------------------------------------ the row walk
+// A warp item = (strip, chunk of rows).  The warp walks its strip downwards keeping
+// three packed rows in registers; the body sees row i as (up, mid, down) and the
+// compile-time column parity Q of the colour being processed (colour pixels sit at
+// lane columns Q and Q+2).  Rows are taken two at a time so that the parity and the
+// register roles are static inside the loop body.
+struct ItemCtx {
+    int s;        // strip
+    int c0;       // first column of this lane
+    int lane;
+    unsigned lt;  // lanemask_lt
+    bool va[2], vb[2];  // validity (interior column) of pixel A / B for Q = 0 / 1
+};
+
+// rhombus predictions for the two colour pixels of this lane in row `mid`
+template <typename PixT, int Q>
+__device__ __forceinline__ void predict_pair(const ItemCtx& c, const Row4<PixT>& U, const Row4<PixT>& M,
+                                             const Row4<PixT>& D, const unsigned char* midp, int w, int& xa,
+                                             int& pa, int& xb, int& pb) {
+    if (Q == 0) {
+        int left = __shfl_up_sync(0xffffffffu, M.template f<3>(), 1);
+        if (c.lane == 0) left = c.c0 > 0 ? Row4<PixT>::load1(midp, -1) : 0;
+        const int m1 = M.template f<1>();
+        xa = M.template f<0>(); pa = (U.template f<0>() + D.template f<0>() + left + m1) >> 2;
+        xb = M.template f<2>(); pb = (U.template f<2>() + D.template f<2>() + m1 + M.template f<3>()) >> 2;
+    } else {
+        int right = __shfl_down_sync(0xffffffffu, M.template f<0>(), 1);
+        if (c.lane == 31) right = c.c0 + 4 < w ? Row4<PixT>::load1(midp, 4) : 0;
+        const int m2 = M.template f<2>();
+        xa = M.template f<1>(); pa = (U.template f<1>() + D.template f<1>() + M.template f<0>() + m2) >> 2;
+        xb = M.template f<3>(); pb = (U.template f<3>() + D.template f<3>() + m2 + right) >> 2;
+    }
+}
+
+template <typename PixT, class Body>
+__device__ __forceinline__ void walk_rows(const PeeGeom& g, unsigned char* simg, int r_first, int colour, int ra,
+                                          int rb, const ItemCtx& c, Body& body) {
+    if (ra >= rb) return;
+    unsigned char* p = simg + (size_t)(ra - 1 - r_first) * g.pitch + (size_t)c.c0 * Row4<PixT>::ITEM;  // row ra-1
+    const int pitch = g.pitch;
+    Row4<PixT> U, M, D0, D1;
+    U.load(p);
+    M.load(p + pitch);
+    p += pitch;  // p -> row `i` (mid) at this lane's columns
+    int i = ra;
+    if ((i + colour) & 1) {  // peel one row so that the loop starts on parity 0
+        D0.load(p + pitch);
+        body.template step<1>(i, U, M, D0, p);
+        U = M; M = D0; p += pitch; ++i;
+    }
+    for (; i + 1 < rb; i += 2) {
+        D0.load(p + pitch);
+        body.template step<0>(i, U, M, D0, p);
+        D1.load(p + 2 * pitch);
+        body.template step<1>(i + 1, M, D0, D1, p + pitch);
+        U = D0; M = D1; p += 2 * pitch;
+    }
+    if (i < rb) {
+        D0.load(p + pitch);
+        body.template step<0>(i, U, M, D0, p);
+    }
+}
+
+// Splits rows [row_lo, row_hi) x strips into warp items and walks them.
+template <typename PixT, class Body>
+__device__ __forceinline__ void sweep(const PeeGeom& g, unsigned char* simg, int r_first, int colour, int row_lo,
+                                      int row_hi, Body& body) {
+    const int nrows = row_hi - row_lo;
+    if (nrows <= 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int G = max(1, nwarps / g.S);  // row chunks per strip
+    const int RC = (nrows + G - 1) / G;  // rows per chunk
+    const int nitems = g.S * G;
+    ItemCtx c;
+    c.lane = lane;
+    c.lt = lanemask_lt();
+    for (int item = warp; item < nitems; item += nwarps) {
+        const int chunk = item / g.S;
+        c.s = item - chunk * g.S;
+        c.c0 = c.s * STRIP + 4 * lane;
+        const int ra = row_lo + chunk * RC, rb = min(ra + RC, row_hi);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            c.va[q] = c.c0 + q >= 1 && c.c0 + q <= g.w - 2;
+            c.vb[q] = c.c0 + q + 2 <= g.w - 2;
+        }
+        body.begin_item(c);
+        walk_rows<PixT>(g, simg, r_first, colour, ra, rb, c, body);
+    }
+}
+
 struct EmbedStats {
     unsigned long long sse = 0;
     unsigned flagged = 0;
 };
 
-template <typename PixT, bool APPLY>
-__device__ __forceinline__ void embed_sweep(const PeeGeom& g, unsigned char* simg, int r_first, int colour,
-                                            int row_lo, int row_hi, int own_lo, int own_hi, int T, int* tab,
-                                            const unsigned* __restrict__ payload, unsigned n_bits,
-                                            unsigned* slm, int lm_row0, EmbedStats& st) {
+// ---- body: count carriers of one colour per (row, strip) ---------------------------------
+// GLOBAL=true  (pee_count_kernel): byte counts to rowcnt[row*S + strip] in global memory;
+// GLOBAL=false (pass 1 of the embed kernel): counts to the shared table, plus the values with a
+//              zero payload bit (side) and the carrier ballots (ball) for the light apply; flags
+//              go to the location map here because they do not depend on the payload.
+template <typename PixT, bool GLOBAL>
+struct CountBody {
+    const PeeGeom& g;
+    const ItemCtx* c;
+    int T, row0;                 // row0: image row of table row 0
+    unsigned char* rowcnt;       // GLOBAL
+    int* tab; unsigned* side; uint2* ball; unsigned* slm; int lm_row0; EmbedStats* st;  // !GLOBAL
+    int total;                   // carriers seen by this warp (lane 0)
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx) { c = &ctx; }
+    template <int Q>
+    __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
+                                         unsigned char* midp) {
+        int xa, pa, xb, pb, na, nb;
+        bool cara, carb, fla, flb;
+        predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
+        classify_embed(xa, pa, T, g.maxval, na, cara, fla);
+        classify_embed(xb, pb, T, g.maxval, nb, carb, flb);
+        cara = cara && c->va[Q]; carb = carb && c->vb[Q];
+        const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
+        const int idx = (i - row0) * g.S + c->s;
+        if (GLOBAL) {
+            if (c->lane == 0) {
+                const int n = __popc(ma) + __popc(mb);
+                rowcnt[idx] = (unsigned char)n;
+                total += n;
+            }
+        } else {
+            if (!c->va[Q]) na = xa;
+            if (!c->vb[Q]) nb = xb;
+            side[idx * 32 + c->lane] = (unsigned)na | ((unsigned)nb << 16);
+            if (c->lane == 0) {
+                tab[idx] = __popc(ma) + __popc(mb);
+                ball[idx] = make_uint2(ma, mb);
+            }
+            fla = fla && c->va[Q]; flb = flb && c->vb[Q];
+            if (fla | flb) {
+                unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
+                const int ca = c->c0 + Q, cb = ca + 2;
+                if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st->flagged; }
+                if (flb) { atomicOr(lrow + (cb >> 5), lm_bitmask(cb)); ++st->flagged; }
+            }
+        }
+    }
+};
+
+// ---- body: full apply of one colour (pass 0 of the embed kernel) --------------------------
+// tab[(i-row0)*S + strip] = payload bit index of the first carrier of that (row, strip).
+template <typename PixT>
+struct ApplyBody {
+    const PeeGeom& g;
+    const ItemCtx* c;
+    int T, row0, own_lo, own_hi;
+    const int* tab;
+    const unsigned* __restrict__ payload;
+    unsigned n_bits;
+    unsigned* slm; int lm_row0;
+    EmbedStats* st;
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx) { c = &ctx; }
+    template <int Q>
+    __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
+                                         unsigned char* midp) {
+        int xa, pa, xb, pb, na, nb;
+        bool cara, carb, fla, flb;
+        predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
+        classify_embed(xa, pa, T, g.maxval, na, cara, fla);
+        classify_embed(xb, pb, T, g.maxval, nb, carb, flb);
+        cara = cara && c->va[Q]; carb = carb && c->vb[Q];
+        const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
+        const unsigned base = (unsigned)tab[(i - row0) * g.S + c->s];
+        if ((ma | mb) && base < n_bits) {
+            unsigned hi, lo;
+            payload_window(payload, base, hi, lo);
+            const int ka = __popc(ma & c->lt) + __popc(mb & c->lt);
+            const int kb = ka + (cara ? 1 : 0);
+            if (cara && base + ka < n_bits) na += window_bit(hi, lo, ka);
+            if (carb && base + kb < n_bits) nb += window_bit(hi, lo, kb);
+        }
+        if (!c->va[Q]) na = xa;
+        if (!c->vb[Q]) nb = xb;
+        if (i >= own_lo && i < own_hi) {
+            const int da = na - xa, db = nb - xb;
+            st->sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
+            fla = fla && c->va[Q]; flb = flb && c->vb[Q];
+            if (fla | flb) {
+                unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
+                const int ca = c->c0 + Q, cb = ca + 2;
+                if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st->flagged; }
+                if (flb) { atomicOr(lrow + (cb >> 5), lm_bitmask(cb)); ++st->flagged; }
+            }
+        }
+        M.template set<Q>(na);
+        M.template set<Q + 2>(nb);
+        if (c->c0 < g.w) M.store(midp);
+    }
+};
+
+// ---- light apply of pass 1: no neighbourhood, everything was prepared by CountBody<false> ----
+template <typename PixT>
+__device__ __forceinline__ void apply_light(const PeeGeom& g, unsigned char* simg, int r_first, int row_lo,
+                                            int row_hi, const int* tab, const unsigned* side, const uint2* ball,
+                                            const unsigned* __restrict__ payload, unsigned n_bits, EmbedStats& st) {
     const int nrows = row_hi - row_lo;
     if (nrows <= 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int G = max(1, nwarps / g.S);             // row chunks per strip
-    const int RC = (nrows + G - 1) / G;             // rows per chunk
-    const int nitems = g.S * G;
     const unsigned lt = lanemask_lt();
-    for (int item = warp; item < nitems; item += nwarps) {
-        const int s = item % g.S, chunk = item / g.S;
-        const int ra = row_lo + chunk * RC, rb = min(ra + RC, row_hi);
-        if (ra >= rb) continue;
+    const int nitems = nrows * g.S;
+    for (int idx = warp; idx < nitems; idx += nwarps) {
+        const int r = idx / g.S, s = idx - r * g.S;
+        const int i = row_lo + r;
         const int c0 = s * STRIP + 4 * lane;
-        int u[4], m[4], d[4];
-        const unsigned char* rowp = simg + (size_t)(ra - 1 - r_first) * g.pitch;
-        Px<PixT>::load4(rowp, c0, u);
-        Px<PixT>::load4(rowp + g.pitch, c0, m);
-        for (int i = ra; i < rb; ++i) {
-            unsigned char* mid = simg + (size_t)(i - r_first) * g.pitch;
-            Px<PixT>::load4(mid + g.pitch, c0, d);
-            const int q = (i + colour) & 1;
-            int xa, pa, xb, pb;
-            if (q == 0) {
-                int left = __shfl_up_sync(0xffffffffu, m[3], 1);
-                if (lane == 0) left = c0 > 0 ? Px<PixT>::load1(mid, c0 - 1) : 0;
-                xa = m[0]; pa = (u[0] + d[0] + left + m[1]) >> 2;
-                xb = m[2]; pb = (u[2] + d[2] + m[1] + m[3]) >> 2;
-            } else {
-                int right = __shfl_down_sync(0xffffffffu, m[0], 1);
-                if (lane == 31) right = c0 + 4 < g.w ? Px<PixT>::load1(mid, c0 + 4) : 0;
-                xa = m[1]; pa = (u[1] + d[1] + m[0] + m[2]) >> 2;
-                xb = m[3]; pb = (u[3] + d[3] + m[2] + right) >> 2;
-            }
-            const int ca = c0 + q, cb = c0 + q + 2;
-            const bool va = ca >= 1 && ca <= g.w - 2, vb = cb >= 1 && cb <= g.w - 2;
-            int na, nbv;
-            bool cara, fla, carb, flb;
-            classify_embed(xa, pa, T, g.maxval, na, cara, fla);
-            classify_embed(xb, pb, T, g.maxval, nbv, carb, flb);
-            cara = cara && va; carb = carb && vb;
-            const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
-            const int e_idx = (i - row_lo) * g.S + s;
-            if (!APPLY) {
-                if (lane == 0) tab[e_idx] = __popc(ma) + __popc(mb);
-            } else {
-                const unsigned base = (unsigned)tab[e_idx];
-                if ((ma | mb) && base < n_bits) {
-                    unsigned hi, lo;
-                    payload_window(payload, base, hi, lo);
-                    const int ka = __popc(ma & lt) + __popc(mb & lt);
-                    const int kb = ka + (cara ? 1 : 0);
-                    if (cara && base + ka < n_bits) na += window_bit(hi, lo, ka);
-                    if (carb && base + kb < n_bits) nbv += window_bit(hi, lo, kb);
-                }
-                if (!va) na = xa;
-                if (!vb) nbv = xb;
-                if (i >= own_lo && i < own_hi) {
-                    const int da = na - xa, db = nbv - xb;
-                    st.sse += (unsigned long long)(unsigned)(da * da) + (unsigned)(db * db);
-                    fla = fla && va; flb = flb && vb;
-                    if (fla | flb) {
-                        unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
-                        if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st.flagged; }
-                        if (flb) { atomicOr(lrow + (cb >> 5), lm_bitmask(cb)); ++st.flagged; }
-                    }
-                }
-                if (q == 0) { m[0] = na; m[2] = nbv; } else { m[1] = na; m[3] = nbv; }
-                if (c0 < g.w) Px<PixT>::store4(mid, c0, m);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { u[k] = m[k]; m[k] = d[k]; }
+        const uint2 mm = ball[idx];
+        const unsigned sd = side[idx * 32 + lane];
+        int na = (int)(sd & 0xffffu), nb = (int)(sd >> 16);
+        const unsigned base = (unsigned)tab[idx];
+        if ((mm.x | mm.y) && base < n_bits) {
+            unsigned hi, lo;
+            payload_window(payload, base, hi, lo);
+            const bool cara = (mm.x >> lane) & 1u, carb = (mm.y >> lane) & 1u;
+            const int ka = __popc(mm.x & lt) + __popc(mm.y & lt);
+            const int kb = ka + (cara ? 1 : 0);
+            if (cara && base + ka < n_bits) na += window_bit(hi, lo, ka);
+            if (carb && base + kb < n_bits) nb += window_bit(hi, lo, kb);
         }
+        unsigned char* midp = simg + (size_t)(i - r_first) * g.pitch + (size_t)c0 * Row4<PixT>::ITEM;
+        Row4<PixT> M;
+        M.load(midp);
+        int xa, xb;
+        if (((i + 1) & 1) == 0) { xa = M.template f<0>(); xb = M.template f<2>(); M.template set<0>(na); M.template set<2>(nb); }
+        else { xa = M.template f<1>(); xb = M.template f<3>(); M.template set<1>(na); M.template set<3>(nb); }
+        // columns outside the interior were parked in `side` with whatever the buffer held then
+        const int q = (i + 1) & 1;
+        const int da = (c0 + q >= 1 && c0 + q <= g.w - 2) ? na - xa : 0;
+        const int db = (c0 + q + 2 <= g.w - 2) ? nb - xb : 0;
+        st.sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
+        if (c0 < g.w) M.store(midp);
     }
 }
 
-// ------------------------------------------------------------------ K_A: pass-0 band counts
-// grid = n_units * nb.  band_cnt[unit*nb + band] = pass-0 carriers in the band's own
-// rows; info[unit][3] (cap0) accumulates their sum.
+// ------------------------------------------------------------------ K_A: pass-0 counts
+// grid = n_units * nb.  rowcnt[(unit*h + row)*S + strip] = pass-0 carriers of that row
+// segment (<= 64, one byte); band_cnt[unit*nb + band] = their sum over the band's own rows;
+// info[unit][3] (cap0) accumulates the unit total.
 template <typename PixT>
-__global__ void __launch_bounds__(256) pee_count_kernel(PeeGeom g, PeeBatch bt, int* __restrict__ band_cnt) {
+__global__ void __launch_bounds__(256, 4) pee_count_kernel(PeeGeom g, PeeBatch bt, int* __restrict__ band_cnt,
+                                                          unsigned char* __restrict__ rowcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SmemLayout L = band_layout(g, 0);
+    unsigned char* simg = smem_raw + L.img;
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
-    unsigned char* simg = smem_raw;
-    const size_t img_bytes = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
-    int* cnt = reinterpret_cast<int*>(smem_raw + img_bytes);
-    int* misc = cnt + (g.R + 2) * g.S;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + img_bytes + align_up((size_t)((g.R + 2) * g.S + 64) * sizeof(int), 16));
-    if (g.bulk && threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    if (threadIdx.x == 0) { misc[0] = 0; if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); } }
     __syncthreads();
     const int r0 = band * g.R, r_first = r0 - 2;
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
-    const int T = bt.T[unit];
-    EmbedStats st;
-    embed_sweep<PixT, false>(g, simg, r_first, 0, own_lo, own_hi, own_lo, own_hi, T, cnt, nullptr, 0, nullptr, 0, st);
-    __syncthreads();
-    const int n = max(own_hi - own_lo, 0) * g.S;
-    int part = 0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) part += cnt[k];
-    part = (int)warp_sum_i64(part);
-    if ((threadIdx.x & 31) == 0) misc[threadIdx.x >> 5] = part;
+    CountBody<PixT, true> body{g, nullptr, bt.T[unit], 0, rowcnt + (long long)unit * g.h * g.S,
+                               nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0};
+    sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, body);
+    if ((threadIdx.x & 31) == 0 && body.total) atomicAdd(misc, body.total);
     __syncthreads();
     if (threadIdx.x == 0) {
-        int tot = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += misc[k];
+        const int tot = misc[0];
         band_cnt[unit * g.nb + band] = tot;
-        atomicAdd(reinterpret_cast<unsigned long long*>(bt.info + (long long)unit * PEEB_INFO + 3), (unsigned long long)tot);
+        if (tot) atomicAdd(reinterpret_cast<unsigned long long*>(bt.info + (long long)unit * PEEB_INFO + 3), (unsigned long long)tot);
     }
 }
 
@@ -329,19 +490,19 @@ __global__ void __launch_bounds__(256) pee_count_kernel(PeeGeom g, PeeBatch bt, 
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PFX = 2ull << 62, ST_MASK = 3ull << 62;
 
 template <typename PixT>
-__global__ void __launch_bounds__(256) pee_embed_kernel(PeeGeom g, PeeBatch bt, const int* __restrict__ band_cnt,
-                                                        unsigned* __restrict__ ticket,
-                                                        unsigned long long* __restrict__ status) {
+__global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch bt, const int* __restrict__ band_cnt,
+                                                          const unsigned char* __restrict__ rowcnt,
+                                                          unsigned* __restrict__ ticket,
+                                                          unsigned long long* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* simg = smem_raw;
-    size_t off = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
-    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + off);
-    off += align_up((size_t)(g.R + 2) * g.lmpitch, 16);
-    int* tab = reinterpret_cast<int*>(smem_raw + off);
-    off += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
-    int* misc = reinterpret_cast<int*>(smem_raw + off);
-    off += 64 * sizeof(int);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off);
+    const SmemLayout L = band_layout(g, 1);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + L.lm);
+    int* tab = reinterpret_cast<int*>(smem_raw + L.tab);
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    unsigned* side = reinterpret_cast<unsigned*>(smem_raw + L.side);
+    uint2* ball = reinterpret_cast<uint2*>(smem_raw + L.ball);
 
     // in-order ticket: a band only ever waits on bands with smaller tickets
     if (threadIdx.x == 0) {
@@ -350,56 +511,62 @@ __global__ void __launch_bounds__(256) pee_embed_kernel(PeeGeom g, PeeBatch bt, 
     }
     __syncthreads();
     const int tk = misc[40];
-    const int unit = tk / g.nb, band = tk % g.nb;
+    const int unit = tk / g.nb, band = tk - unit * g.nb;
     const int r0 = band * g.R, r_first = r0 - 2;
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     const int T = bt.T[unit];
     const unsigned n_bits = bt.n_bits[unit];
     const unsigned* payload = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
     long long* info = bt.info + (long long)unit * PEEB_INFO;
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
+    const int n0 = max(p0_hi - p0_lo, 0) * g.S, n1 = max(own_hi - own_lo, 0) * g.S;
 
     load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 2, 0), min(r0 + g.R + 2, g.h), bar);
     for (int k = threadIdx.x; k < (g.R * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
-
+    // pass-0 counts of the rows this band touches (own rows + one halo row each side)
+    {
+        const unsigned char* rc = rowcnt + ((long long)unit * g.h + p0_lo) * g.S;
+        for (int k = threadIdx.x; k < n0; k += blockDim.x) tab[k] = rc[k];
+    }
     // pass-0 prefix of this band and cap0 of the unit from the count kernel
     if (threadIdx.x < 32) {
         int before = 0, all = 0;
         for (int k = threadIdx.x; k < g.nb; k += 32) {
-            const int c = band_cnt[unit * g.nb + k];
-            all += c;
-            if (k < band) before += c;
+            const int cc = band_cnt[unit * g.nb + k];
+            all += cc;
+            if (k < band) before += cc;
         }
         before = (int)warp_sum_i64(before);
         all = (int)warp_sum_i64(all);
         if (threadIdx.x == 0) { misc[41] = before; misc[42] = all; }
     }
-    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    __syncthreads();
     EmbedStats st;
 
-    // ---- pass 0 (colour 0) over the band rows and one halo row on each side
-    const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
-    embed_sweep<PixT, false>(g, simg, r_first, 0, p0_lo, p0_hi, own_lo, own_hi, T, tab, nullptr, 0, slm, r0, st);
-    __syncthreads();
+    // ---- pass 0 (colour 0): band rows and one halo row on each side, one full sweep
     {
-        const int n = max(p0_hi - p0_lo, 0) * g.S;
         // carriers of the halo row above precede this band in raster order
         int halo_top = 0;
         if (p0_lo < own_lo) for (int k = 0; k < g.S; ++k) halo_top += tab[k];
         __syncthreads();
-        block_excl_scan(tab, n, misc);
+        block_excl_scan(tab, n0, misc);
         const int base = misc[41] - halo_top;
-        for (int k = threadIdx.x; k < n; k += blockDim.x) tab[k] += base;
+        for (int k = threadIdx.x; k < n0; k += blockDim.x) tab[k] += base;
         __syncthreads();
+        ApplyBody<PixT> body{g, nullptr, T, p0_lo, own_lo, own_hi, tab, payload, n_bits, slm, r0, &st};
+        sweep<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, body);
     }
-    embed_sweep<PixT, true>(g, simg, r_first, 0, p0_lo, p0_hi, own_lo, own_hi, T, tab, payload, n_bits, slm, r0, st);
     __syncthreads();
 
-    // ---- pass 1 (colour 1) over the band rows
-    embed_sweep<PixT, false>(g, simg, r_first, 1, own_lo, own_hi, own_lo, own_hi, T, tab, nullptr, 0, slm, r0, st);
+    // ---- pass 1 (colour 1) over the band rows: classify once, then a light apply
+    {
+        CountBody<PixT, false> body{g, nullptr, T, own_lo, nullptr, tab, side, ball, slm, r0, &st, 0};
+        sweep<PixT>(g, simg, r_first, 1, own_lo, own_hi, body);
+    }
     __syncthreads();
     {
-        const int n = max(own_hi - own_lo, 0) * g.S;
-        const int total = block_excl_scan(tab, n, misc);
+        const int total = block_excl_scan(tab, n1, misc);
         if (threadIdx.x == 0) {
             unsigned long long* stt = status + (long long)unit * g.nb;
             atomicExch(stt + band, ST_AGG | (unsigned)total);
@@ -412,14 +579,14 @@ __global__ void __launch_bounds__(256) pee_embed_kernel(PeeGeom g, PeeBatch bt, 
             }
             atomicExch(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
             misc[43] = (int)before;
-            atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
+            if (total) atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
         }
         __syncthreads();
         const int base = misc[42] + misc[43];  // cap0 + carriers of pass 1 in earlier bands
-        for (int k = threadIdx.x; k < n; k += blockDim.x) tab[k] += base;
+        for (int k = threadIdx.x; k < n1; k += blockDim.x) tab[k] += base;
         __syncthreads();
     }
-    embed_sweep<PixT, true>(g, simg, r_first, 1, own_lo, own_hi, own_lo, own_hi, T, tab, payload, n_bits, slm, r0, st);
+    apply_light<PixT>(g, simg, r_first, own_lo, own_hi, tab, side, ball, payload, n_bits, st);
 
     // ---- statistics
     {
@@ -464,100 +631,69 @@ __global__ void pee_finalize_kernel(PeeBatch bt, int extract) {
 // One sweep per colour; pixels are restored in place, carrier bits of the band's own
 // rows are compacted per (row, strip) with ballots and a warp OR-reduction.
 template <typename PixT>
-__device__ __forceinline__ void extract_sweep(const PeeGeom& g, unsigned char* simg, int r_first, int colour,
-                                              int row_lo, int row_hi, int own_lo, int own_hi, int T,
-                                              const unsigned* slm, int lm_row0, int* cnt,
-                                              unsigned long long* xbits) {
-    const int nrows = row_hi - row_lo;
-    if (nrows <= 0) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int G = max(1, nwarps / g.S);
-    const int RC = (nrows + G - 1) / G;
-    const int nitems = g.S * G;
-    const unsigned lt = lanemask_lt();
-    for (int item = warp; item < nitems; item += nwarps) {
-        const int s = item % g.S, chunk = item / g.S;
-        const int ra = row_lo + chunk * RC, rb = min(ra + RC, row_hi);
-        if (ra >= rb) continue;
-        const int c0 = s * STRIP + 4 * lane;
-        int u[4], m[4], d[4];
-        const unsigned char* rowp = simg + (size_t)(ra - 1 - r_first) * g.pitch;
-        Px<PixT>::load4(rowp, c0, u);
-        Px<PixT>::load4(rowp + g.pitch, c0, m);
-        for (int i = ra; i < rb; ++i) {
-            unsigned char* mid = simg + (size_t)(i - r_first) * g.pitch;
-            Px<PixT>::load4(mid + g.pitch, c0, d);
-            const int q = (i + colour) & 1;
-            // location-map nibble of this lane's 4 columns (bit 3 = column c0)
-            const unsigned lw = slm[(size_t)(i - lm_row0) * (g.lmpitch >> 2) + (c0 >> 5)];
-            const unsigned nib = (lw >> (8 * ((c0 >> 3) & 3) + ((c0 & 4) ? 0 : 4))) & 0xfu;
-            int xa, pa, xb, pb;
-            if (q == 0) {
-                int left = __shfl_up_sync(0xffffffffu, m[3], 1);
-                if (lane == 0) left = c0 > 0 ? Px<PixT>::load1(mid, c0 - 1) : 0;
-                xa = m[0]; pa = (u[0] + d[0] + left + m[1]) >> 2;
-                xb = m[2]; pb = (u[2] + d[2] + m[1] + m[3]) >> 2;
-            } else {
-                int right = __shfl_down_sync(0xffffffffu, m[0], 1);
-                if (lane == 31) right = c0 + 4 < g.w ? Px<PixT>::load1(mid, c0 + 4) : 0;
-                xa = m[1]; pa = (u[1] + d[1] + m[0] + m[2]) >> 2;
-                xb = m[3]; pb = (u[3] + d[3] + m[2] + right) >> 2;
-            }
-            const int ca = c0 + q, cb = c0 + q + 2;
-            const bool va = ca >= 1 && ca <= g.w - 2, vb = cb >= 1 && cb <= g.w - 2;
-            const bool la = (nib >> (3 - q)) & 1u, lb = (nib >> (1 - q)) & 1u;
-            int oa, ob, bita, bitb;
-            bool cara, carb;
-            classify_extract(xa, pa, T, la, oa, cara, bita);
-            classify_extract(xb, pb, T, lb, ob, carb, bitb);
-            cara = cara && va; carb = carb && vb;
-            if (!va) oa = xa;
-            if (!vb) ob = xb;
-            if (i >= own_lo && i < own_hi) {
-                const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
-                const int ka = __popc(ma & lt) + __popc(mb & lt);
-                const int kb = ka + (cara ? 1 : 0);
-                unsigned long long contrib = 0;
-                if (cara && bita) contrib |= 1ull << ka;
-                if (carb && bitb) contrib |= 1ull << kb;
-                const unsigned clo = __reduce_or_sync(0xffffffffu, (unsigned)contrib);
-                const unsigned chi = __reduce_or_sync(0xffffffffu, (unsigned)(contrib >> 32));
-                if (lane == 0) {
-                    const int e_idx = (i - own_lo) * g.S + s;
-                    cnt[e_idx] = __popc(ma) + __popc(mb);
-                    xbits[e_idx] = ((unsigned long long)chi << 32) | clo;
-                }
-            }
-            if (q == 0) { m[0] = oa; m[2] = ob; } else { m[1] = oa; m[3] = ob; }
-            if (c0 < g.w) Px<PixT>::store4(mid, c0, m);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { u[k] = m[k]; m[k] = d[k]; }
-        }
+struct ExtractBody {
+    const PeeGeom& g;
+    const ItemCtx* c;
+    int T, own_lo, own_hi;
+    const unsigned* slm; int lm_row0;
+    int* cnt; unsigned long long* xbits;
+    int lmword, lmshift;  // this lane's location-map word within a row and nibble position
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx) {
+        c = &ctx;
+        lmword = ctx.c0 >> 5;
+        lmshift = 8 * ((ctx.c0 >> 3) & 3) + ((ctx.c0 & 4) ? 0 : 4);
     }
-}
+    template <int Q>
+    __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
+                                         unsigned char* midp) {
+        int xa, pa, xb, pb, oa, ob, bita, bitb;
+        bool cara, carb;
+        predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
+        // location-map nibble of this lane's 4 columns (bit 3 = column c0)
+        const unsigned nib = slm[(size_t)(i - lm_row0) * (g.lmpitch >> 2) + lmword] >> lmshift;
+        const bool la = (nib >> (3 - Q)) & 1u, lb = (nib >> (1 - Q)) & 1u;
+        classify_extract(xa, pa, T, la, oa, cara, bita);
+        classify_extract(xb, pb, T, lb, ob, carb, bitb);
+        cara = cara && c->va[Q]; carb = carb && c->vb[Q];
+        if (!c->va[Q]) oa = xa;
+        if (!c->vb[Q]) ob = xb;
+        if (i >= own_lo && i < own_hi) {
+            const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
+            const int ka = __popc(ma & c->lt) + __popc(mb & c->lt);
+            const int kb = ka + (cara ? 1 : 0);
+            unsigned long long contrib = 0;
+            if (cara && bita) contrib |= 1ull << ka;
+            if (carb && bitb) contrib |= 1ull << kb;
+            const unsigned clo = __reduce_or_sync(0xffffffffu, (unsigned)contrib);
+            const unsigned chi = __reduce_or_sync(0xffffffffu, (unsigned)(contrib >> 32));
+            if (c->lane == 0) {
+                const int e_idx = (i - own_lo) * g.S + c->s;
+                cnt[e_idx] = __popc(ma) + __popc(mb);
+                xbits[e_idx] = ((unsigned long long)chi << 32) | clo;
+            }
+        }
+        M.template set<Q>(oa);
+        M.template set<Q + 2>(ob);
+        if (c->c0 < g.w) M.store(midp);
+    }
+};
 
 // grid = n_units * nb (no inter-band dependency).  stage_bits: per (unit, pass, band)
 // `bandwords` 32-bit words, carrier bit k at word k>>5, bit k&31; stage_cnt likewise.
 template <typename PixT>
-__global__ void __launch_bounds__(256) pee_extract_kernel(PeeGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits,
-                                                          int* __restrict__ stage_cnt) {
+__global__ void __launch_bounds__(256, 4) pee_extract_kernel(PeeGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits,
+                                                            int* __restrict__ stage_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned char* simg = smem_raw;
-    size_t off = align_up((size_t)(g.R + 4) * g.pitch + 512, 16);
-    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + off);
-    off += align_up((size_t)(g.R + 2) * g.lmpitch, 16);
-    int* cnt1 = reinterpret_cast<int*>(smem_raw + off);   // colour 1 table
-    off += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
-    int* misc = reinterpret_cast<int*>(smem_raw + off);
-    off += 64 * sizeof(int);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + off);
-    off += 16;
-    unsigned long long* xb1 = reinterpret_cast<unsigned long long*>(smem_raw + off);
+    const SmemLayout L = band_layout(g, 2);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + L.lm);
+    int* cnt1 = reinterpret_cast<int*>(smem_raw + L.tab);   // colour 1 table
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    unsigned long long* xb1 = reinterpret_cast<unsigned long long*>(smem_raw + L.xb);
     unsigned long long* xb0 = xb1 + (g.R + 2) * g.S;
-    off += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);
-    int* cnt0 = reinterpret_cast<int*>(smem_raw + off);
-    off += align_up((size_t)g.R * g.S * sizeof(int), 16);
-    unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + off);  // [2][bandwords]: pass 0, pass 1
+    int* cnt0 = reinterpret_cast<int*>(smem_raw + L.tab0);
+    unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + L.stream);  // [2][bandwords]: pass 0, pass 1
 
     const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
     const int r0 = band * g.R, r_first = r0 - 2;
@@ -586,9 +722,15 @@ __global__ void __launch_bounds__(256) pee_extract_kernel(PeeGeom g, PeeBatch bt
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
     // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
-    extract_sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, own_lo, own_hi, T, slm, r0 - 1, cnt1, xb1);
+    {
+        ExtractBody<PixT> body{g, nullptr, T, own_lo, own_hi, slm, r0 - 1, cnt1, xb1, 0, 0};
+        sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, body);
+    }
     __syncthreads();
-    extract_sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, own_lo, own_hi, T, slm, r0 - 1, cnt0, xb0);
+    {
+        ExtractBody<PixT> body{g, nullptr, T, own_lo, own_hi, slm, r0 - 1, cnt0, xb0, 0, 0};
+        sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, body);
+    }
     __syncthreads();
 
     // compact the per-(row,strip) pieces into one bit stream per pass
@@ -601,19 +743,14 @@ __global__ void __launch_bounds__(256) pee_extract_kernel(PeeGeom g, PeeBatch bt
         const int total = block_excl_scan(cnt, n, misc);
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
             const int o = cnt[k];
-            const int c = (k + 1 < n ? cnt[k + 1] : total) - o;
-            if (c > 0) {
+            const int cc = (k + 1 < n ? cnt[k + 1] : total) - o;
+            if (cc > 0) {
                 const unsigned long long v = xb[k];
                 const int wi = o >> 5, sh = o & 31;
                 atomicOr(out + wi, (unsigned)(v << sh));
                 const unsigned long long hi = sh ? (v >> (32 - sh)) : (v >> 32);
-                // bits 32-sh .. of v go to the following words
-                if (sh) {
-                    if ((unsigned)hi) atomicOr(out + wi + 1, (unsigned)hi);
-                    if ((unsigned)(hi >> 32)) atomicOr(out + wi + 2, (unsigned)(hi >> 32));
-                } else {
-                    if ((unsigned)hi) atomicOr(out + wi + 1, (unsigned)hi);
-                }
+                if ((unsigned)hi) atomicOr(out + wi + 1, (unsigned)hi);
+                if (sh && (unsigned)(hi >> 32)) atomicOr(out + wi + 2, (unsigned)(hi >> 32));
             }
         }
         __syncthreads();
@@ -736,7 +873,7 @@ __global__ void __launch_bounds__(256) pee_hist_kernel(const unsigned char* __re
 }
 
 // ------------------------------------------------------------------ host side
-static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, bool extract, PeeGeom& g) {
+static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int kind, PeeGeom& g) {
     PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "pee: itemsize must be 1 or 2");
     PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "pee: bit_depth %d out of range for itemsize %d", bit_depth, itemsize);
     PEEB_REQUIRE(h >= 1 && w >= 1 && (long long)h * w < (1ll << 31), "pee: image size %dx%d unsupported", h, w);
@@ -748,23 +885,26 @@ static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, boo
     g.lmw = (w + 7) / 8;
     g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 4;  // +4: partial strips may peek one word past the row
     g.maxval = (1 << bit_depth) - 1;
-    // band height: as tall as fits a ~72 KB stage (three CTAs per SM), capped at 64 rows;
-    // wide images fall back to fewer rows and, if needed, one CTA per SM
-    int R = 64;
-    const size_t budget_small = 72 * 1024, budget_max = (size_t)ws->max_smem_optin - 2048;
+    // Band height: as tall as fits a quarter of an SM's shared memory (four CTAs per SM), capped at
+    // 64 rows; wide images fall back to fewer rows and, if needed, one CTA per SM.  The rows are then
+    // spread evenly over the bands.
+    const size_t budget_small = 55 * 1024, budget_max = (size_t)ws->max_smem_optin - 2048;
     auto fits = [&](int r, size_t budget) {
         g.R = r; g.bandwords = (r * ((w + 1) / 2) + 31) / 32 + 2;
-        return band_smem_bytes(g, extract) <= budget;
+        return band_layout(g, kind).total <= budget;
     };
-    while (R > 8 && !fits(R, budget_small)) R -= 8;
+    int R = 64;
+    while (R > 8 && !fits(R, budget_small)) R -= 4;
     if (!fits(R, budget_small)) {
-        while (R > 2 && !fits(R, budget_max)) R -= 2;
+        while (R > 1 && !fits(R, budget_max)) R -= 1;
         if (!fits(R, budget_max)) {
             set_error("pee: image width %d needs more shared memory than one SM has", w);
             return PEEB_E_UNSUPPORTED;
         }
     }
-    if (R > h) { R = h < 1 ? 1 : h; }
+    if (R > h) R = h;
+    const int nb = (h + R - 1) / R;
+    R = (h + nb - 1) / nb;
     fits(R, budget_max);
     g.nb = (h + g.R - 1) / g.R;
     return PEEB_OK;
@@ -812,7 +952,7 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_embed_batch: payload must be 4-byte aligned");
     PEEB_CUDA(cudaSetDevice(ws->device));
     PeeGeom g;
-    int rc = make_geom(ws, h, w, itemsize, bit_depth, false, g);
+    int rc = make_geom(ws, h, w, itemsize, bit_depth, 1, g);
     if (rc) return rc;
     if (g.bulk && ((((uintptr_t)src) | (uintptr_t)marked | (uint64_t)src_stride | (uint64_t)marked_stride) & 15)) {
         g.bulk = 0;  // unaligned user buffers: plain copies
@@ -823,11 +963,13 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     int* dT; unsigned* dN; char* extra;
     const size_t cnt_bytes = align_up((size_t)nbands * sizeof(int), 256);
     const size_t st_bytes = align_up((size_t)nbands * sizeof(unsigned long long), 256);
-    rc = upload_unit_tables(ws, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256, st, &dT, &dN, &extra);
+    const size_t rc_bytes = align_up((size_t)n_units * h * g.S, 256);
+    rc = upload_unit_tables(ws, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256 + rc_bytes, st, &dT, &dN, &extra);
     if (rc) return rc;
     int* band_cnt = (int*)extra;
     unsigned long long* status = (unsigned long long*)(extra + cnt_bytes);
     unsigned* ticket = (unsigned*)(extra + cnt_bytes + st_bytes);
+    unsigned char* rowcnt = (unsigned char*)(extra + cnt_bytes + st_bytes + 256);
     PEEB_CUDA(cudaMemsetAsync(status, 0, st_bytes + 256, st));
     PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
     PeeBatch bt{};
@@ -836,22 +978,22 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     bt.lm = lm; bt.lm_stride = lm_stride;
     bt.payload = payload; bt.payload_stride = payload_stride;
     bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
-    const size_t smem = band_smem_bytes(g, false);
+    const size_t smem = band_layout(g, 1).total;
     if (h >= 3 && w >= 3) {
         if (itemsize == 2) {
             rc = set_smem(pee_count_kernel<unsigned short>, smem); if (rc) return rc;
             rc = set_smem(pee_embed_kernel<unsigned short>, smem); if (rc) return rc;
             { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-              pee_count_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt); }
+              pee_count_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt); }
             { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
-              pee_embed_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, ticket, status); }
+              pee_embed_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
         } else {
             rc = set_smem(pee_count_kernel<unsigned char>, smem); if (rc) return rc;
             rc = set_smem(pee_embed_kernel<unsigned char>, smem); if (rc) return rc;
             { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-              pee_count_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt); }
+              pee_count_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt); }
             { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
-              pee_embed_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, ticket, status); }
+              pee_embed_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
         }
         PEEB_CUDA(cudaGetLastError());
     } else {
@@ -877,7 +1019,7 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
     PEEB_REQUIRE(((uintptr_t)payload_out & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_extract_batch: payload_out must be 4-byte aligned");
     PEEB_CUDA(cudaSetDevice(ws->device));
     PeeGeom g;
-    int rc = make_geom(ws, h, w, itemsize, bit_depth, true, g);
+    int rc = make_geom(ws, h, w, itemsize, bit_depth, 2, g);
     if (rc) return rc;
     if (g.bulk && ((((uintptr_t)marked) | (uintptr_t)recovered | (uint64_t)marked_stride | (uint64_t)recovered_stride) & 15)) {
         g.bulk = 0;
@@ -908,7 +1050,7 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
         else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
     }
     if (h >= 3 && w >= 3) {
-        const size_t smem = band_smem_bytes(g, true);
+        const size_t smem = band_layout(g, 2).total;
         if (itemsize == 2) {
             rc = set_smem(pee_extract_kernel<unsigned short>, smem); if (rc) return rc;
             ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
