@@ -96,14 +96,14 @@ template <> struct Row4<unsigned char> {
 __device__ __forceinline__ void classify_embed(int x, int p, int T, int maxval, int& nv0, bool& carrier,
                                                bool& flagged) {
     const int e = x - p;
-    const int v = x + e;                                        // p + 2e
-    const bool expd = (unsigned)(e + T) < (unsigned)(2 * T);    // -T <= e < T
-    const bool fe = (unsigned)v >= (unsigned)maxval;            // v < 0 or v + 1 > maxval
-    const int xs = x + (e >= T ? T : -T);
-    const bool fs = (unsigned)xs > (unsigned)maxval;            // x+T > maxval or x-T < 0
-    carrier = expd && !fe;
-    flagged = expd ? fe : fs;
-    nv0 = expd ? (fe ? x : v) : (fs ? x : xs);
+    const int t = e + T;
+    const int v = x + e;                                            // p + 2e
+    const bool expd = (unsigned)t < (unsigned)(2 * T);              // -T <= e < T
+    carrier = expd && (unsigned)v < (unsigned)maxval;               // 0 <= v and v + 1 <= maxval
+    const int xs = x + (t < 0 ? -T : T);                            // e < -T : e >= T (when not expandable)
+    const bool shifted = !expd && (unsigned)xs <= (unsigned)maxval; // x-T >= 0 / x+T <= maxval
+    nv0 = carrier ? v : (shifted ? xs : x);
+    flagged = !(carrier || shifted);
 }
 
 // Appendix A, extract side.
@@ -137,7 +137,7 @@ __device__ __forceinline__ unsigned lm_bitmask(int j) { return 1u << (8 * ((j >>
 
 // ------------------------------------------------------------------ shared layout
 struct SmemLayout {
-    size_t img, lm, tab, side, ball, misc, bar, xb, tab0, stream, total;
+    size_t img, lm, tab, side, ball, bits, misc, bar, xb, tab0, stream, total;
 };
 __host__ __device__ inline SmemLayout band_layout(const PeeGeom& g, int kind /*0 count, 1 embed, 2 extract*/) {
     SmemLayout L{};
@@ -147,8 +147,9 @@ __host__ __device__ inline SmemLayout band_layout(const PeeGeom& g, int kind /*0
     L.tab = o; o += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
     L.misc = o; o += 64 * sizeof(int);
     L.bar = o; o += 16;
-    L.side = L.ball = L.xb = L.tab0 = L.stream = o;
+    L.side = L.ball = L.bits = L.xb = L.tab0 = L.stream = o;
     if (kind == 1) {
+        L.bits = o; o += align_up((size_t)(g.R + 2) * g.S * 64 + 64, 16);           // payload bits of the band, one byte each
         L.side = o; o += align_up((size_t)g.R * g.S * 32 * sizeof(unsigned), 16);   // pass-1 values with a zero bit
         L.ball = o; o += align_up((size_t)g.R * g.S * sizeof(uint2), 16);           // pass-1 carrier ballots
     } else if (kind == 2) {
@@ -216,6 +217,29 @@ __device__ __forceinline__ void store_rows(const PeeGeom& g, unsigned char* unit
     }
 }
 
+// Expands payload bits [first, first + count) of an MSB-first packed stream into one byte
+// per bit in shared memory (bits at or past n_bits read as 0, Appendix A's zero padding).
+// The stream must be readable 8 bytes past the word holding bit n_bits-1.
+__device__ __forceinline__ void expand_payload(const unsigned* __restrict__ pay, unsigned first, int count,
+                                               unsigned n_bits, unsigned char* out /* 4-byte aligned */) {
+    const unsigned sh = first & 31, w0 = first >> 5;
+    unsigned* out4 = reinterpret_cast<unsigned*>(out);
+    for (int j = threadIdx.x; j * 32 < count; j += blockDim.x) {
+        const unsigned start = first + 32u * (unsigned)j;  // stream index of this thread's first bit
+        unsigned win = 0;
+        if (start < n_bits) {
+            const unsigned a = __byte_perm(__ldg(pay + w0 + j), 0, 0x0123);
+            const unsigned b = __byte_perm(__ldg(pay + w0 + j + 1), 0, 0x0123);
+            win = __funnelshift_l(b, a, sh);                 // bit `start` is the MSB
+            if (n_bits - start < 32u) win &= ~(0xffffffffu >> (n_bits - start));
+        }
+        const unsigned lsb = __brev(win);                    // bit `start + k` at bit k
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+            out4[j * 8 + n] = (((lsb >> (4 * n)) & 0xfu) * 0x00204081u) & 0x01010101u;
+    }
+}
+
 // ------------------------------------------------------------------ the row walk
 // A warp item = (strip, chunk of rows).  The warp walks its strip downwards keeping
 // three packed rows in registers; the body sees row i as (up, mid, down) and the
@@ -228,6 +252,8 @@ struct ItemCtx {
     int lane;
     unsigned lt;  // lanemask_lt
     bool va[2], vb[2];  // validity (interior column) of pixel A / B for Q = 0 / 1
+    int Ta[2], Tb[2];   // the threshold for pixel A / B, 0 where the column is not interior: with T = 0
+                        // a pixel is never expandable and its shift is by 0, i.e. it is left alone
 };
 
 // rhombus predictions for the two colour pixels of this lane in row `mid`
@@ -282,7 +308,7 @@ __device__ __forceinline__ void walk_rows(const PeeGeom& g, unsigned char* simg,
 // Splits rows [row_lo, row_hi) x strips into warp items and walks them.
 template <typename PixT, class Body>
 __device__ __forceinline__ void sweep(const PeeGeom& g, unsigned char* simg, int r_first, int colour, int row_lo,
-                                      int row_hi, Body& body) {
+                                      int row_hi, int T, Body& body) {
     const int nrows = row_hi - row_lo;
     if (nrows <= 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -301,8 +327,10 @@ __device__ __forceinline__ void sweep(const PeeGeom& g, unsigned char* simg, int
         for (int q = 0; q < 2; ++q) {
             c.va[q] = c.c0 + q >= 1 && c.c0 + q <= g.w - 2;
             c.vb[q] = c.c0 + q + 2 <= g.w - 2;
+            c.Ta[q] = c.va[q] ? T : 0;
+            c.Tb[q] = c.vb[q] ? T : 0;
         }
-        body.begin_item(c);
+        body.begin_item(c, ra);
         walk_rows<PixT>(g, simg, r_first, colour, ra, rb, c, body);
     }
 }
@@ -321,22 +349,21 @@ template <typename PixT, bool GLOBAL>
 struct CountBody {
     const PeeGeom& g;
     const ItemCtx* c;
-    int T, row0;                 // row0: image row of table row 0
+    int row0;                    // image row of table row 0
     unsigned char* rowcnt;       // GLOBAL
     int* tab; unsigned* side; uint2* ball; unsigned* slm; int lm_row0; EmbedStats* st;  // !GLOBAL
     int total;                   // carriers seen by this warp (lane 0)
-    __device__ __forceinline__ void begin_item(const ItemCtx& ctx) { c = &ctx; }
+    int idx;                     // running table index of (row, strip)
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx, int ra) { c = &ctx; idx = (ra - row0) * g.S + ctx.s; }
     template <int Q>
     __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
                                          unsigned char* midp) {
         int xa, pa, xb, pb, na, nb;
         bool cara, carb, fla, flb;
         predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
-        classify_embed(xa, pa, T, g.maxval, na, cara, fla);
-        classify_embed(xb, pb, T, g.maxval, nb, carb, flb);
-        cara = cara && c->va[Q]; carb = carb && c->vb[Q];
+        classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara, fla);
+        classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb, flb);
         const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
-        const int idx = (i - row0) * g.S + c->s;
         if (GLOBAL) {
             if (c->lane == 0) {
                 const int n = __popc(ma) + __popc(mb);
@@ -344,63 +371,55 @@ struct CountBody {
                 total += n;
             }
         } else {
-            if (!c->va[Q]) na = xa;
-            if (!c->vb[Q]) nb = xb;
             side[idx * 32 + c->lane] = (unsigned)na | ((unsigned)nb << 16);
             if (c->lane == 0) {
                 tab[idx] = __popc(ma) + __popc(mb);
                 ball[idx] = make_uint2(ma, mb);
             }
-            fla = fla && c->va[Q]; flb = flb && c->vb[Q];
-            if (fla | flb) {
+            if (fla | flb) {  // rare; only interior columns may enter the map
+                fla = fla && c->va[Q]; flb = flb && c->vb[Q];
                 unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
                 const int ca = c->c0 + Q, cb = ca + 2;
                 if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st->flagged; }
                 if (flb) { atomicOr(lrow + (cb >> 5), lm_bitmask(cb)); ++st->flagged; }
             }
         }
+        idx += g.S;
     }
 };
 
 // ---- body: full apply of one colour (pass 0 of the embed kernel) --------------------------
-// tab[(i-row0)*S + strip] = payload bit index of the first carrier of that (row, strip).
+// tab[(i-row0)*S + strip] = index into `bits` (one byte per payload bit of this band, zero
+// padded) of the first carrier of that (row, strip).
 template <typename PixT>
 struct ApplyBody {
     const PeeGeom& g;
     const ItemCtx* c;
-    int T, row0, own_lo, own_hi;
+    int row0, own_lo, own_hi;
     const int* tab;
-    const unsigned* __restrict__ payload;
-    unsigned n_bits;
+    const unsigned char* bits;
     unsigned* slm; int lm_row0;
     EmbedStats* st;
-    __device__ __forceinline__ void begin_item(const ItemCtx& ctx) { c = &ctx; }
+    int idx;
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx, int ra) { c = &ctx; idx = (ra - row0) * g.S + ctx.s; }
     template <int Q>
     __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
                                          unsigned char* midp) {
         int xa, pa, xb, pb, na, nb;
         bool cara, carb, fla, flb;
         predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
-        classify_embed(xa, pa, T, g.maxval, na, cara, fla);
-        classify_embed(xb, pb, T, g.maxval, nb, carb, flb);
-        cara = cara && c->va[Q]; carb = carb && c->vb[Q];
+        classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara, fla);
+        classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb, flb);
         const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
-        const unsigned base = (unsigned)tab[(i - row0) * g.S + c->s];
-        if ((ma | mb) && base < n_bits) {
-            unsigned hi, lo;
-            payload_window(payload, base, hi, lo);
-            const int ka = __popc(ma & c->lt) + __popc(mb & c->lt);
-            const int kb = ka + (cara ? 1 : 0);
-            if (cara && base + ka < n_bits) na += window_bit(hi, lo, ka);
-            if (carb && base + kb < n_bits) nb += window_bit(hi, lo, kb);
-        }
-        if (!c->va[Q]) na = xa;
-        if (!c->vb[Q]) nb = xb;
+        const unsigned char* bp = bits + tab[idx] + __popc(ma & c->lt) + __popc(mb & c->lt);
+        idx += g.S;
+        if (cara) { na += bp[0]; ++bp; }
+        if (carb) nb += bp[0];
         if (i >= own_lo && i < own_hi) {
             const int da = na - xa, db = nb - xb;
             st->sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
-            fla = fla && c->va[Q]; flb = flb && c->vb[Q];
-            if (fla | flb) {
+            if (fla | flb) {  // rare; only interior columns may enter the map
+                fla = fla && c->va[Q]; flb = flb && c->vb[Q];
                 unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
                 const int ca = c->c0 + Q, cb = ca + 2;
                 if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st->flagged; }
@@ -417,7 +436,7 @@ struct ApplyBody {
 template <typename PixT>
 __device__ __forceinline__ void apply_light(const PeeGeom& g, unsigned char* simg, int r_first, int row_lo,
                                             int row_hi, const int* tab, const unsigned* side, const uint2* ball,
-                                            const unsigned* __restrict__ payload, unsigned n_bits, EmbedStats& st) {
+                                            const unsigned char* bits, EmbedStats& st) {
     const int nrows = row_hi - row_lo;
     if (nrows <= 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -430,24 +449,17 @@ __device__ __forceinline__ void apply_light(const PeeGeom& g, unsigned char* sim
         const uint2 mm = ball[idx];
         const unsigned sd = side[idx * 32 + lane];
         int na = (int)(sd & 0xffffu), nb = (int)(sd >> 16);
-        const unsigned base = (unsigned)tab[idx];
-        if ((mm.x | mm.y) && base < n_bits) {
-            unsigned hi, lo;
-            payload_window(payload, base, hi, lo);
-            const bool cara = (mm.x >> lane) & 1u, carb = (mm.y >> lane) & 1u;
-            const int ka = __popc(mm.x & lt) + __popc(mm.y & lt);
-            const int kb = ka + (cara ? 1 : 0);
-            if (cara && base + ka < n_bits) na += window_bit(hi, lo, ka);
-            if (carb && base + kb < n_bits) nb += window_bit(hi, lo, kb);
-        }
+        const unsigned char* bp = bits + tab[idx] + __popc(mm.x & lt) + __popc(mm.y & lt);
+        if ((mm.x >> lane) & 1u) { na += bp[0]; ++bp; }
+        if ((mm.y >> lane) & 1u) nb += bp[0];
         unsigned char* midp = simg + (size_t)(i - r_first) * g.pitch + (size_t)c0 * Row4<PixT>::ITEM;
         Row4<PixT> M;
         M.load(midp);
         int xa, xb;
-        if (((i + 1) & 1) == 0) { xa = M.template f<0>(); xb = M.template f<2>(); M.template set<0>(na); M.template set<2>(nb); }
+        const int q = (i + 1) & 1;
+        if (q == 0) { xa = M.template f<0>(); xb = M.template f<2>(); M.template set<0>(na); M.template set<2>(nb); }
         else { xa = M.template f<1>(); xb = M.template f<3>(); M.template set<1>(na); M.template set<3>(nb); }
         // columns outside the interior were parked in `side` with whatever the buffer held then
-        const int q = (i + 1) & 1;
         const int da = (c0 + q >= 1 && c0 + q <= g.w - 2) ? na - xa : 0;
         const int db = (c0 + q + 2 <= g.w - 2) ? nb - xb : 0;
         st.sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
@@ -474,9 +486,9 @@ __global__ void __launch_bounds__(256, 4) pee_count_kernel(PeeGeom g, PeeBatch b
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
-    CountBody<PixT, true> body{g, nullptr, bt.T[unit], 0, rowcnt + (long long)unit * g.h * g.S,
-                               nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0};
-    sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, body);
+    CountBody<PixT, true> body{g, nullptr, 0, rowcnt + (long long)unit * g.h * g.S,
+                               nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0};
+    sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, bt.T[unit], body);
     if ((threadIdx.x & 31) == 0 && body.total) atomicAdd(misc, body.total);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -503,6 +515,7 @@ __global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch b
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     unsigned* side = reinterpret_cast<unsigned*>(smem_raw + L.side);
     uint2* ball = reinterpret_cast<uint2*>(smem_raw + L.ball);
+    unsigned char* bits = smem_raw + L.bits;
 
     // in-order ticket: a band only ever waits on bands with smaller tickets
     if (threadIdx.x == 0) {
@@ -550,19 +563,18 @@ __global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch b
         int halo_top = 0;
         if (p0_lo < own_lo) for (int k = 0; k < g.S; ++k) halo_top += tab[k];
         __syncthreads();
-        block_excl_scan(tab, n0, misc);
-        const int base = misc[41] - halo_top;
-        for (int k = threadIdx.x; k < n0; k += blockDim.x) tab[k] += base;
+        const int total0 = block_excl_scan(tab, n0, misc);   // tab: index into `bits`
+        expand_payload(payload, (unsigned)(misc[41] - halo_top), total0, n_bits, bits);
         __syncthreads();
-        ApplyBody<PixT> body{g, nullptr, T, p0_lo, own_lo, own_hi, tab, payload, n_bits, slm, r0, &st};
-        sweep<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, body);
+        ApplyBody<PixT> body{g, nullptr, p0_lo, own_lo, own_hi, tab, bits, slm, r0, &st, 0};
+        sweep<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
     }
     __syncthreads();
 
     // ---- pass 1 (colour 1) over the band rows: classify once, then a light apply
     {
-        CountBody<PixT, false> body{g, nullptr, T, own_lo, nullptr, tab, side, ball, slm, r0, &st, 0};
-        sweep<PixT>(g, simg, r_first, 1, own_lo, own_hi, body);
+        CountBody<PixT, false> body{g, nullptr, own_lo, nullptr, tab, side, ball, slm, r0, &st, 0, 0};
+        sweep<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
     }
     __syncthreads();
     {
@@ -582,11 +594,10 @@ __global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch b
             if (total) atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
         }
         __syncthreads();
-        const int base = misc[42] + misc[43];  // cap0 + carriers of pass 1 in earlier bands
-        for (int k = threadIdx.x; k < n1; k += blockDim.x) tab[k] += base;
+        expand_payload(payload, (unsigned)(misc[42] + misc[43]), total, n_bits, bits);  // from cap0 + earlier bands' pass-1 carriers
         __syncthreads();
     }
-    apply_light<PixT>(g, simg, r_first, own_lo, own_hi, tab, side, ball, payload, n_bits, st);
+    apply_light<PixT>(g, simg, r_first, own_lo, own_hi, tab, side, ball, bits, st);
 
     // ---- statistics
     {
@@ -638,7 +649,7 @@ struct ExtractBody {
     const unsigned* slm; int lm_row0;
     int* cnt; unsigned long long* xbits;
     int lmword, lmshift;  // this lane's location-map word within a row and nibble position
-    __device__ __forceinline__ void begin_item(const ItemCtx& ctx) {
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx, int) {
         c = &ctx;
         lmword = ctx.c0 >> 5;
         lmshift = 8 * ((ctx.c0 >> 3) & 3) + ((ctx.c0 & 4) ? 0 : 4);
@@ -724,12 +735,12 @@ __global__ void __launch_bounds__(256, 4) pee_extract_kernel(PeeGeom g, PeeBatch
     // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
     {
         ExtractBody<PixT> body{g, nullptr, T, own_lo, own_hi, slm, r0 - 1, cnt1, xb1, 0, 0};
-        sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, body);
+        sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
     }
     __syncthreads();
     {
         ExtractBody<PixT> body{g, nullptr, T, own_lo, own_hi, slm, r0 - 1, cnt0, xb0, 0, 0};
-        sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, body);
+        sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
     }
     __syncthreads();
 
