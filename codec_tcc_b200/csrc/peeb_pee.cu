@@ -150,8 +150,6 @@ __host__ __device__ inline SmemLayout band_layout(const PeeGeom& g, int kind /*0
     L.side = L.ball = L.bits = L.xb = L.tab0 = L.stream = o;
     if (kind == 1) {
         L.bits = o; o += align_up((size_t)(g.R + 2) * g.S * 64 + 64, 16);           // payload bits of the band, one byte each
-        L.side = o; o += align_up((size_t)g.R * g.S * 32 * sizeof(unsigned), 16);   // pass-1 values with a zero bit
-        L.ball = o; o += align_up((size_t)g.R * g.S * sizeof(uint2), 16);           // pass-1 carrier ballots
     } else if (kind == 2) {
         L.xb = o; o += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);
         L.tab0 = o; o += align_up((size_t)g.R * g.S * sizeof(int), 16);
@@ -342,16 +340,15 @@ struct EmbedStats {
 
 // ---- body: count carriers of one colour per (row, strip) ---------------------------------
 // GLOBAL=true  (pee_count_kernel): byte counts to rowcnt[row*S + strip] in global memory;
-// GLOBAL=false (pass 1 of the embed kernel): counts to the shared table, plus the values with a
-//              zero payload bit (side) and the carrier ballots (ball) for the light apply; flags
-//              go to the location map here because they do not depend on the payload.
+// GLOBAL=false (pass 1 of the embed kernel): counts to the shared table.
+// Only the carrier predicate is live here, so the sweep is about a third of a full apply.
 template <typename PixT, bool GLOBAL>
 struct CountBody {
     const PeeGeom& g;
     const ItemCtx* c;
     int row0;                    // image row of table row 0
     unsigned char* rowcnt;       // GLOBAL
-    int* tab; unsigned* side; uint2* ball; unsigned* slm; int lm_row0; EmbedStats* st;  // !GLOBAL
+    int* tab;                    // !GLOBAL
     int total;                   // carriers seen by this warp (lane 0)
     int idx;                     // running table index of (row, strip)
     __device__ __forceinline__ void begin_item(const ItemCtx& ctx, int ra) { c = &ctx; idx = (ra - row0) * g.S + ctx.s; }
@@ -364,27 +361,13 @@ struct CountBody {
         classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara, fla);
         classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb, flb);
         const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
-        if (GLOBAL) {
-            if (c->lane == 0) {
-                const int n = __popc(ma) + __popc(mb);
-                rowcnt[idx] = (unsigned char)n;
-                total += n;
-            }
-        } else {
-            side[idx * 32 + c->lane] = (unsigned)na | ((unsigned)nb << 16);
-            if (c->lane == 0) {
-                tab[idx] = __popc(ma) + __popc(mb);
-                ball[idx] = make_uint2(ma, mb);
-            }
-            if (fla | flb) {  // rare; only interior columns may enter the map
-                fla = fla && c->va[Q]; flb = flb && c->vb[Q];
-                unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
-                const int ca = c->c0 + Q, cb = ca + 2;
-                if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st->flagged; }
-                if (flb) { atomicOr(lrow + (cb >> 5), lm_bitmask(cb)); ++st->flagged; }
-            }
+        if (c->lane == 0) {
+            const int n = __popc(ma) + __popc(mb);
+            if (GLOBAL) { rowcnt[idx] = (unsigned char)n; total += n; }
+            else tab[idx] = n;
         }
         idx += g.S;
+        (void)i;
     }
 };
 
@@ -432,41 +415,6 @@ struct ApplyBody {
     }
 };
 
-// ---- light apply of pass 1: no neighbourhood, everything was prepared by CountBody<false> ----
-template <typename PixT>
-__device__ __forceinline__ void apply_light(const PeeGeom& g, unsigned char* simg, int r_first, int row_lo,
-                                            int row_hi, const int* tab, const unsigned* side, const uint2* ball,
-                                            const unsigned char* bits, EmbedStats& st) {
-    const int nrows = row_hi - row_lo;
-    if (nrows <= 0) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const unsigned lt = lanemask_lt();
-    const int nitems = nrows * g.S;
-    for (int idx = warp; idx < nitems; idx += nwarps) {
-        const int r = idx / g.S, s = idx - r * g.S;
-        const int i = row_lo + r;
-        const int c0 = s * STRIP + 4 * lane;
-        const uint2 mm = ball[idx];
-        const unsigned sd = side[idx * 32 + lane];
-        int na = (int)(sd & 0xffffu), nb = (int)(sd >> 16);
-        const unsigned char* bp = bits + tab[idx] + __popc(mm.x & lt) + __popc(mm.y & lt);
-        if ((mm.x >> lane) & 1u) { na += bp[0]; ++bp; }
-        if ((mm.y >> lane) & 1u) nb += bp[0];
-        unsigned char* midp = simg + (size_t)(i - r_first) * g.pitch + (size_t)c0 * Row4<PixT>::ITEM;
-        Row4<PixT> M;
-        M.load(midp);
-        int xa, xb;
-        const int q = (i + 1) & 1;
-        if (q == 0) { xa = M.template f<0>(); xb = M.template f<2>(); M.template set<0>(na); M.template set<2>(nb); }
-        else { xa = M.template f<1>(); xb = M.template f<3>(); M.template set<1>(na); M.template set<3>(nb); }
-        // columns outside the interior were parked in `side` with whatever the buffer held then
-        const int da = (c0 + q >= 1 && c0 + q <= g.w - 2) ? na - xa : 0;
-        const int db = (c0 + q + 2 <= g.w - 2) ? nb - xb : 0;
-        st.sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
-        if (c0 < g.w) M.store(midp);
-    }
-}
-
 // ------------------------------------------------------------------ K_A: pass-0 counts
 // grid = n_units * nb.  rowcnt[(unit*h + row)*S + strip] = pass-0 carriers of that row
 // segment (<= 64, one byte); band_cnt[unit*nb + band] = their sum over the band's own rows;
@@ -486,8 +434,7 @@ __global__ void __launch_bounds__(256, 4) pee_count_kernel(PeeGeom g, PeeBatch b
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     load_rows<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
-    CountBody<PixT, true> body{g, nullptr, 0, rowcnt + (long long)unit * g.h * g.S,
-                               nullptr, nullptr, nullptr, nullptr, 0, nullptr, 0, 0};
+    CountBody<PixT, true> body{g, nullptr, 0, rowcnt + (long long)unit * g.h * g.S, nullptr, 0, 0};
     sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, bt.T[unit], body);
     if ((threadIdx.x & 31) == 0 && body.total) atomicAdd(misc, body.total);
     __syncthreads();
@@ -513,8 +460,6 @@ __global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch b
     int* tab = reinterpret_cast<int*>(smem_raw + L.tab);
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
-    unsigned* side = reinterpret_cast<unsigned*>(smem_raw + L.side);
-    uint2* ball = reinterpret_cast<uint2*>(smem_raw + L.ball);
     unsigned char* bits = smem_raw + L.bits;
 
     // in-order ticket: a band only ever waits on bands with smaller tickets
@@ -571,9 +516,10 @@ __global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch b
     }
     __syncthreads();
 
-    // ---- pass 1 (colour 1) over the band rows: classify once, then a light apply
+    // ---- pass 1 (colour 1) over the band rows: a cheap counting sweep orders the carriers,
+    //      the same full apply as pass 0 then rewrites the pixels
     {
-        CountBody<PixT, false> body{g, nullptr, own_lo, nullptr, tab, side, ball, slm, r0, &st, 0, 0};
+        CountBody<PixT, false> body{g, nullptr, own_lo, nullptr, tab, 0, 0};
         sweep<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
     }
     __syncthreads();
@@ -596,8 +542,9 @@ __global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch b
         __syncthreads();
         expand_payload(payload, (unsigned)(misc[42] + misc[43]), total, n_bits, bits);  // from cap0 + earlier bands' pass-1 carriers
         __syncthreads();
+        ApplyBody<PixT> body{g, nullptr, own_lo, own_lo, own_hi, tab, bits, slm, r0, &st, 0};
+        sweep<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
     }
-    apply_light<PixT>(g, simg, r_first, own_lo, own_hi, tab, side, ball, bits, st);
 
     // ---- statistics
     {
@@ -672,11 +619,10 @@ struct ExtractBody {
             const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
             const int ka = __popc(ma & c->lt) + __popc(mb & c->lt);
             const int kb = ka + (cara ? 1 : 0);
-            unsigned long long contrib = 0;
-            if (cara && bita) contrib |= 1ull << ka;
-            if (carb && bitb) contrib |= 1ull << kb;
-            const unsigned clo = __reduce_or_sync(0xffffffffu, (unsigned)contrib);
-            const unsigned chi = __reduce_or_sync(0xffffffffu, (unsigned)(contrib >> 32));
+            // this lane's (at most two) carrier bits at positions ka, kb of the 64-bit piece
+            const unsigned sa = (cara && bita) ? 1u << (ka & 31) : 0u, sb = (carb && bitb) ? 1u << (kb & 31) : 0u;
+            const unsigned clo = __reduce_or_sync(0xffffffffu, (ka < 32 ? sa : 0u) | (kb < 32 ? sb : 0u));
+            const unsigned chi = __reduce_or_sync(0xffffffffu, (ka < 32 ? 0u : sa) | (kb < 32 ? 0u : sb));
             if (c->lane == 0) {
                 const int e_idx = (i - own_lo) * g.S + c->s;
                 cnt[e_idx] = __popc(ma) + __popc(mb);
