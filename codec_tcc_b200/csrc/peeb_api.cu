@@ -75,6 +75,7 @@ int peeb_ws_create(int device, peeb_ws** out) {
     PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream2, cudaStreamNonBlocking));
     for (int i = 0; i < 4; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreate(&ws->prof_ev[i]));
+    for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pev[i], cudaEventDisableTiming));
     const char* nb = getenv("PEEB_NO_BULK");
     ws->use_bulk = !(nb && nb[0] == '1');
     const char* nc = getenv("PEEB_NO_CLUSTER");
@@ -93,6 +94,13 @@ int peeb_ws_destroy(peeb_ws* ws) {
     scratch_free(ws->stage);
     scratch_free(ws->stage2);
     scratch_free(ws->bits);
+    scratch_free(ws->info_h, true);
+    for (int i = 0; i < 2; ++i) {
+        scratch_free(ws->ptables[i]);
+        scratch_free(ws->ptables_h[i], true);
+        scratch_free(ws->pbits[i]);
+        if (ws->pev[i]) cudaEventDestroy(ws->pev[i]);
+    }
     for (int i = 0; i < 4; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     for (int i = 0; i < 2; ++i) if (ws->prof_ev[i]) cudaEventDestroy(ws->prof_ev[i]);
     if (ws->stream) cudaStreamDestroy(ws->stream);

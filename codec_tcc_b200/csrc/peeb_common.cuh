@@ -46,7 +46,15 @@ struct peeb_ws {
     peeb::Scratch tables_h;          // pinned host mirror
     peeb::Scratch stage;             // device: staging for *_h entry points
     peeb::Scratch stage2;            // device: second staging area
-    peeb::Scratch bits;              // device: extract per-band bit staging
+    peeb::Scratch bits;              // device: compaction scratch (decode_message)
+    // PEE launches use one of two independent table sets, so that two chunks of a host batch
+    // can be in flight on the two streams at once
+    peeb::Scratch ptables[2];        // device: T/n_bits per unit, band counts, look-back status, tickets
+    peeb::Scratch ptables_h[2];      // pinned host mirrors of the per-unit tables
+    peeb::Scratch pbits[2];          // device: extract per-band bit staging
+    cudaEvent_t pev[2] = {nullptr, nullptr};
+    peeb::Scratch info_h;            // pinned landing zone for per-unit info rows (keeps every copy of a
+                                     // host batch asynchronous even when the caller's info array is pageable)
     int use_bulk = 1;                // TMA bulk copies (PEEB_NO_BULK=1 disables)
     int use_cluster = 1;             // cluster-resident path for small images (PEEB_NO_CLUSTER=1 disables)
     // profiling: accumulate per-kernel device time with events when enabled

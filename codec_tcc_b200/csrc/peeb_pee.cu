@@ -867,15 +867,18 @@ static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int
     return PEEB_OK;
 }
 
-// upload T / n_bits (host arrays) into the workspace tables; returns device pointers
-static int upload_unit_tables(peeb_ws* ws, int n_units, const int32_t* T, const int64_t* n_bits, int bit_depth,
-                              size_t extra_bytes, cudaStream_t st, int** dT, unsigned** dN, char** extra) {
+// upload T / n_bits (host arrays) into table set `slot` of the workspace; returns device pointers
+static int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, const int64_t* n_bits,
+                              int bit_depth, size_t extra_bytes, cudaStream_t st, int** dT, unsigned** dN,
+                              char** extra) {
     const size_t head = align_up((size_t)n_units * 8, 256);
-    int rc = scratch_reserve(ws->tables, head + extra_bytes + 256);
+    int rc = scratch_reserve(ws->ptables[slot], head + extra_bytes + 256);
     if (rc) return rc;
-    rc = scratch_reserve(ws->tables_h, head, true);
+    // the pinned mirror is reused by the next call: wait until the previous upload has been consumed
+    PEEB_CUDA(cudaEventSynchronize(ws->pev[slot]));
+    rc = scratch_reserve(ws->ptables_h[slot], head, true);
     if (rc) return rc;
-    int* hT = (int*)ws->tables_h.ptr;
+    int* hT = (int*)ws->ptables_h[slot].ptr;
     unsigned* hN = (unsigned*)(hT + n_units);
     const int tmax = 1 << (bit_depth - 1);
     for (int u = 0; u < n_units; ++u) {
@@ -884,13 +887,11 @@ static int upload_unit_tables(peeb_ws* ws, int n_units, const int32_t* T, const 
         hT[u] = T[u];
         hN[u] = (unsigned)n_bits[u];
     }
-    // the pinned mirror is reused by the next call: wait until the previous upload has been consumed
-    PEEB_CUDA(cudaEventSynchronize(ws->ev[3]));
-    PEEB_CUDA(cudaMemcpyAsync(ws->tables.ptr, hT, (size_t)n_units * 8, cudaMemcpyHostToDevice, st));
-    PEEB_CUDA(cudaEventRecord(ws->ev[3], st));
-    *dT = (int*)ws->tables.ptr;
-    *dN = (unsigned*)((int*)ws->tables.ptr + n_units);
-    *extra = (char*)ws->tables.ptr + head;
+    PEEB_CUDA(cudaMemcpyAsync(ws->ptables[slot].ptr, hT, (size_t)n_units * 8, cudaMemcpyHostToDevice, st));
+    PEEB_CUDA(cudaEventRecord(ws->pev[slot], st));
+    *dT = (int*)ws->ptables[slot].ptr;
+    *dN = (unsigned*)((int*)ws->ptables[slot].ptr + n_units);
+    *extra = (char*)ws->ptables[slot].ptr + head;
     return PEEB_OK;
 }
 
@@ -903,7 +904,7 @@ static int set_smem(K kernel, size_t bytes) {
 static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
                             int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
                             int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm,
-                            int64_t lm_stride, int64_t* info, cudaStream_t st) {
+                            int64_t lm_stride, int64_t* info, cudaStream_t st, int slot = 0) {
     PEEB_REQUIRE(ws && src && T && n_bits && payload && info, "peeb_pee_embed_batch: null pointer");
     PEEB_REQUIRE(n_units >= 1, "peeb_pee_embed_batch: n_units must be >= 1");
     PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_embed_batch: payload must be 4-byte aligned");
@@ -921,7 +922,7 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     const size_t cnt_bytes = align_up((size_t)nbands * sizeof(int), 256);
     const size_t st_bytes = align_up((size_t)nbands * sizeof(unsigned long long), 256);
     const size_t rc_bytes = align_up((size_t)n_units * h * g.S, 256);
-    rc = upload_unit_tables(ws, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256 + rc_bytes, st, &dT, &dN, &extra);
+    rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256 + rc_bytes, st, &dT, &dN, &extra);
     if (rc) return rc;
     int* band_cnt = (int*)extra;
     unsigned long long* status = (unsigned long long*)(extra + cnt_bytes);
@@ -970,7 +971,8 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
 static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
                               int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
                               const uint8_t* lm, int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride,
-                              void* recovered, int64_t recovered_stride, int64_t* info, cudaStream_t st) {
+                              void* recovered, int64_t recovered_stride, int64_t* info, cudaStream_t st,
+                              int slot = 0) {
     PEEB_REQUIRE(ws && marked && T && n_bits && lm && payload_out && info, "peeb_pee_extract_batch: null pointer");
     PEEB_REQUIRE(n_units >= 1 && n_units <= 65535, "peeb_pee_extract_batch: n_units must be 1..65535");
     PEEB_REQUIRE(((uintptr_t)payload_out & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_extract_batch: payload_out must be 4-byte aligned");
@@ -985,12 +987,12 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
     const long long nbands = (long long)n_units * g.nb;
     int* dT; unsigned* dN; char* extra;
     const size_t cnt_bytes = align_up((size_t)nbands * 2 * sizeof(int), 256);
-    rc = upload_unit_tables(ws, n_units, T, n_bits, bit_depth, cnt_bytes, st, &dT, &dN, &extra);
+    rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, cnt_bytes, st, &dT, &dN, &extra);
     if (rc) return rc;
     int* stage_cnt = (int*)extra;
-    rc = scratch_reserve(ws->bits, (size_t)nbands * 2 * g.bandwords * sizeof(unsigned) + 256);
+    rc = scratch_reserve(ws->pbits[slot], (size_t)nbands * 2 * g.bandwords * sizeof(unsigned) + 256);
     if (rc) return rc;
-    unsigned* stage_bits = (unsigned*)ws->bits.ptr;
+    unsigned* stage_bits = (unsigned*)ws->pbits[slot].ptr;
     PeeBatch bt{};
     bt.src = (const unsigned char*)marked; bt.src_stride = marked_stride;
     bt.dst = (unsigned char*)recovered; bt.dst_stride = recovered_stride;
@@ -1001,11 +1003,9 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
         const size_t pb = peeb_payload_bytes(n_bits[u]);
         PEEB_REQUIRE(n_units == 1 || (int64_t)pb <= payload_stride, "peeb_pee_extract_batch: payload_stride too small for unit %d", u);
     }
-    if (n_units > 1 || true) {
-        // zero every unit's output words (gather ORs the boundary words in)
-        if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
-        else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
-    }
+    // zero every unit's output words (the gather kernel ORs the boundary words in)
+    if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
+    else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
     if (h >= 3 && w >= 3) {
         const size_t smem = band_layout(g, 2).total;
         if (itemsize == 2) {
@@ -1100,6 +1100,16 @@ static int64_t max_payload_bytes(int n_units, const int64_t* n_bits) {
     return m;
 }
 
+// Units per chunk of a host batch: small enough that several chunks overlap their PCIe copies
+// with each other's kernels, large enough to fill the GPU.
+static int chunk_units(int n_units, size_t unit_bytes) {
+    const size_t target = 16u << 20;
+    long long c = (long long)((target + unit_bytes - 1) / unit_bytes);
+    if (c < 1) c = 1;
+    if (c > n_units) c = n_units;
+    return (int)c;
+}
+
 int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_units, int h, int w, int itemsize,
                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
                      int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
@@ -1107,7 +1117,6 @@ int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_un
     PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_embed_h: bad sizes");
     PEEB_REQUIRE(payload_stride >= 0, "peeb_pee_embed_h: negative payload stride");
     PEEB_CUDA(cudaSetDevice(ws->device));
-    cudaStream_t st = ws->stream;
     const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256);
     const size_t lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
     for (int u = 0; u < n_units; ++u)
@@ -1118,20 +1127,46 @@ int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_un
     int rc = scratch_reserve(ws->stage, o_marked + (marked_host ? (size_t)n_units * img_al : 0) + 256); if (rc) return rc;
     const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
     rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
+    rc = scratch_reserve(ws->info_h, (size_t)n_units * PEEB_INFO * 8, true); if (rc) return rc;
+    int64_t* info_pin = (int64_t*)ws->info_h.ptr;
     char* d1 = (char*)ws->stage.ptr;
     char* d2 = (char*)ws->stage2.ptr;
-    PEEB_CUDA(cudaMemcpy2DAsync(d1, img_al, src_host, img, img, n_src, cudaMemcpyHostToDevice, st));
-    if (payload_stride > 0 && payload_host)
-        PEEB_CUDA(cudaMemcpy2DAsync(d2, pstride, payload_host, (size_t)payload_stride, (size_t)payload_stride, n_units,
-                                    cudaMemcpyHostToDevice, st));
-    rc = embed_batch_impl(ws, d1, shared_src ? 0 : (int64_t)img_al, n_units, h, w, itemsize, bit_depth, T, n_bits,
-                          (const uint8_t*)d2, (int64_t)pstride, marked_host ? d1 + o_marked : nullptr, (int64_t)img_al,
-                          lm_host ? (uint8_t*)(d2 + o_lm) : nullptr, (int64_t)lm_al, (int64_t*)(d2 + o_info), st);
-    if (rc) return rc;
-    if (marked_host) PEEB_CUDA(cudaMemcpy2DAsync(marked_host, img, d1 + o_marked, img_al, img, n_units, cudaMemcpyDeviceToHost, st));
-    if (lm_host) PEEB_CUDA(cudaMemcpy2DAsync(lm_host, lmb, d2 + o_lm, lm_al, lmb, n_units, cudaMemcpyDeviceToHost, st));
-    PEEB_CUDA(cudaMemcpyAsync(info_host, d2 + o_info, (size_t)n_units * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
-    PEEB_CUDA(cudaStreamSynchronize(st));
+    cudaStream_t streams[2] = {ws->stream, ws->stream2};
+    if (shared_src) {
+        PEEB_CUDA(cudaMemcpyAsync(d1, src_host, img, cudaMemcpyHostToDevice, streams[0]));
+        PEEB_CUDA(cudaEventRecord(ws->ev[1], streams[0]));
+        PEEB_CUDA(cudaStreamWaitEvent(streams[1], ws->ev[1], 0));
+    }
+    // chunks alternate between the two streams: copy-in, kernels and copy-out of neighbouring
+    // chunks overlap (PCIe is full duplex, the copy engines run beside the SMs)
+    const int cu = chunk_units(n_units, img);
+    for (int u0 = 0, c = 0; u0 < n_units; u0 += cu, ++c) {
+        const int n = std::min(cu, n_units - u0), slot = c & 1;
+        cudaStream_t st = streams[slot];
+        if (!shared_src)
+            PEEB_CUDA(cudaMemcpy2DAsync(d1 + (size_t)u0 * img_al, img_al, (const char*)src_host + (size_t)u0 * img, img, img, n,
+                                        cudaMemcpyHostToDevice, st));
+        if (payload_stride > 0 && payload_host)
+            PEEB_CUDA(cudaMemcpy2DAsync(d2 + (size_t)u0 * pstride, pstride, payload_host + (size_t)u0 * payload_stride,
+                                        (size_t)payload_stride, (size_t)payload_stride, n, cudaMemcpyHostToDevice, st));
+        rc = embed_batch_impl(ws, shared_src ? d1 : d1 + (size_t)u0 * img_al, shared_src ? 0 : (int64_t)img_al, n, h, w,
+                              itemsize, bit_depth, T + u0, n_bits + u0, (const uint8_t*)(d2 + (size_t)u0 * pstride),
+                              (int64_t)pstride, marked_host ? d1 + o_marked + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
+                              lm_host ? (uint8_t*)(d2 + o_lm + (size_t)u0 * lm_al) : nullptr, (int64_t)lm_al,
+                              (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO, st, slot);
+        if (rc) return rc;
+        if (marked_host)
+            PEEB_CUDA(cudaMemcpy2DAsync((char*)marked_host + (size_t)u0 * img, img, d1 + o_marked + (size_t)u0 * img_al, img_al,
+                                        img, n, cudaMemcpyDeviceToHost, st));
+        if (lm_host)
+            PEEB_CUDA(cudaMemcpy2DAsync(lm_host + (size_t)u0 * lmb, lmb, d2 + o_lm + (size_t)u0 * lm_al, lm_al, lmb, n,
+                                        cudaMemcpyDeviceToHost, st));
+        PEEB_CUDA(cudaMemcpyAsync(info_pin + (size_t)u0 * PEEB_INFO, (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO,
+                                  (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PEEB_CUDA(cudaStreamSynchronize(streams[0]));
+    PEEB_CUDA(cudaStreamSynchronize(streams[1]));
+    memcpy(info_host, info_pin, (size_t)n_units * PEEB_INFO * 8);
     return PEEB_OK;
 }
 
@@ -1141,7 +1176,6 @@ int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h,
     PEEB_REQUIRE(ws && marked_host && T && n_bits && lm_host && payload_out_host && info_host, "peeb_pee_extract_h: null pointer");
     PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_extract_h: bad sizes");
     PEEB_CUDA(cudaSetDevice(ws->device));
-    cudaStream_t st = ws->stream;
     const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256);
     const size_t lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
     for (int u = 0; u < n_units; ++u)
@@ -1151,20 +1185,37 @@ int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h,
     int rc = scratch_reserve(ws->stage, o_rec + (recovered_host ? (size_t)n_units * img_al : 0) + 256); if (rc) return rc;
     const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
     rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
+    rc = scratch_reserve(ws->info_h, (size_t)n_units * PEEB_INFO * 8, true); if (rc) return rc;
+    int64_t* info_pin = (int64_t*)ws->info_h.ptr;
     char* d1 = (char*)ws->stage.ptr;
     char* d2 = (char*)ws->stage2.ptr;
-    PEEB_CUDA(cudaMemcpy2DAsync(d1, img_al, marked_host, img, img, n_units, cudaMemcpyHostToDevice, st));
-    PEEB_CUDA(cudaMemcpy2DAsync(d2 + o_lm, lm_al, lm_host, lmb, lmb, n_units, cudaMemcpyHostToDevice, st));
-    rc = extract_batch_impl(ws, d1, (int64_t)img_al, n_units, h, w, itemsize, bit_depth, T, n_bits, (const uint8_t*)(d2 + o_lm),
-                            (int64_t)lm_al, (uint8_t*)d2, (int64_t)pstride, recovered_host ? d1 + o_rec : nullptr,
-                            (int64_t)img_al, (int64_t*)(d2 + o_info), st);
-    if (rc) return rc;
-    if (recovered_host) PEEB_CUDA(cudaMemcpy2DAsync(recovered_host, img, d1 + o_rec, img_al, img, n_units, cudaMemcpyDeviceToHost, st));
-    if (payload_stride > 0)
-        PEEB_CUDA(cudaMemcpy2DAsync(payload_out_host, (size_t)payload_stride, d2, pstride, (size_t)payload_stride, n_units,
-                                    cudaMemcpyDeviceToHost, st));
-    PEEB_CUDA(cudaMemcpyAsync(info_host, d2 + o_info, (size_t)n_units * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
-    PEEB_CUDA(cudaStreamSynchronize(st));
+    cudaStream_t streams[2] = {ws->stream, ws->stream2};
+    const int cu = std::min(chunk_units(n_units, img), 65535);
+    for (int u0 = 0, c = 0; u0 < n_units; u0 += cu, ++c) {
+        const int n = std::min(cu, n_units - u0), slot = c & 1;
+        cudaStream_t st = streams[slot];
+        PEEB_CUDA(cudaMemcpy2DAsync(d1 + (size_t)u0 * img_al, img_al, (const char*)marked_host + (size_t)u0 * img, img, img, n,
+                                    cudaMemcpyHostToDevice, st));
+        PEEB_CUDA(cudaMemcpy2DAsync(d2 + o_lm + (size_t)u0 * lm_al, lm_al, lm_host + (size_t)u0 * lmb, lmb, lmb, n,
+                                    cudaMemcpyHostToDevice, st));
+        rc = extract_batch_impl(ws, d1 + (size_t)u0 * img_al, (int64_t)img_al, n, h, w, itemsize, bit_depth, T + u0, n_bits + u0,
+                                (const uint8_t*)(d2 + o_lm + (size_t)u0 * lm_al), (int64_t)lm_al,
+                                (uint8_t*)(d2 + (size_t)u0 * pstride), (int64_t)pstride,
+                                recovered_host ? d1 + o_rec + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
+                                (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO, st, slot);
+        if (rc) return rc;
+        if (recovered_host)
+            PEEB_CUDA(cudaMemcpy2DAsync((char*)recovered_host + (size_t)u0 * img, img, d1 + o_rec + (size_t)u0 * img_al, img_al,
+                                        img, n, cudaMemcpyDeviceToHost, st));
+        if (payload_stride > 0)
+            PEEB_CUDA(cudaMemcpy2DAsync(payload_out_host + (size_t)u0 * payload_stride, (size_t)payload_stride,
+                                        d2 + (size_t)u0 * pstride, pstride, (size_t)payload_stride, n, cudaMemcpyDeviceToHost, st));
+        PEEB_CUDA(cudaMemcpyAsync(info_pin + (size_t)u0 * PEEB_INFO, (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO,
+                                  (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PEEB_CUDA(cudaStreamSynchronize(streams[0]));
+    PEEB_CUDA(cudaStreamSynchronize(streams[1]));
+    memcpy(info_host, info_pin, (size_t)n_units * PEEB_INFO * 8);
     return PEEB_OK;
 }
 
