@@ -137,7 +137,7 @@ __device__ __forceinline__ unsigned lm_bitmask(int j) { return 1u << (8 * ((j >>
 
 // ------------------------------------------------------------------ shared layout
 struct SmemLayout {
-    size_t img, lm, tab, side, ball, bits, misc, bar, xb, tab0, stream, total;
+    size_t img, lm, tab, bits, misc, bar, xb, pk, tab0, stream, total;
 };
 __host__ __device__ inline SmemLayout band_layout(const PeeGeom& g, int kind /*0 count, 1 embed, 2 extract*/) {
     SmemLayout L{};
@@ -147,11 +147,12 @@ __host__ __device__ inline SmemLayout band_layout(const PeeGeom& g, int kind /*0
     L.tab = o; o += align_up((size_t)(g.R + 2) * g.S * sizeof(int), 16);
     L.misc = o; o += 64 * sizeof(int);
     L.bar = o; o += 16;
-    L.side = L.ball = L.bits = L.xb = L.tab0 = L.stream = o;
+    L.bits = L.xb = L.pk = L.tab0 = L.stream = o;
     if (kind == 1) {
         L.bits = o; o += align_up((size_t)(g.R + 2) * g.S * 64 + 64, 16);           // payload bits of the band, one byte each
     } else if (kind == 2) {
-        L.xb = o; o += align_up((size_t)2 * (g.R + 2) * g.S * sizeof(unsigned long long), 16);
+        L.xb = o; o += align_up((size_t)g.R * g.S * 64, 16);
+        L.pk = o; o += align_up((size_t)2 * g.R * g.S * sizeof(unsigned long long), 16);
         L.tab0 = o; o += align_up((size_t)g.R * g.S * sizeof(int), 16);
         L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
     }
@@ -592,14 +593,18 @@ template <typename PixT>
 struct ExtractBody {
     const PeeGeom& g;
     const ItemCtx* c;
-    int T, own_lo, own_hi;
+    int own_lo, own_hi;
     const unsigned* slm; int lm_row0;
-    int* cnt; unsigned long long* xbits;
-    int lmword, lmshift;  // this lane's location-map word within a row and nibble position
-    __device__ __forceinline__ void begin_item(const ItemCtx& ctx, int) {
+    int* cnt;                 // carriers per (row, strip) of the band's own rows
+    unsigned char* xbytes;    // their payload bits, one byte each, 64-byte slot per (row, strip)
+    int lmshift;              // nibble position of this lane's 4 columns inside its location-map word
+    const unsigned* lmp;      // running pointer to this lane's location-map word of row i
+    int idx;                  // running table index
+    __device__ __forceinline__ void begin_item(const ItemCtx& ctx, int ra) {
         c = &ctx;
-        lmword = ctx.c0 >> 5;
         lmshift = 8 * ((ctx.c0 >> 3) & 3) + ((ctx.c0 & 4) ? 0 : 4);
+        lmp = slm + (size_t)(ra - lm_row0) * (g.lmpitch >> 2) + (ctx.c0 >> 5);
+        idx = (ra - own_lo) * g.S + ctx.s;
     }
     template <int Q>
     __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
@@ -607,33 +612,38 @@ struct ExtractBody {
         int xa, pa, xb, pb, oa, ob, bita, bitb;
         bool cara, carb;
         predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
-        // location-map nibble of this lane's 4 columns (bit 3 = column c0)
-        const unsigned nib = slm[(size_t)(i - lm_row0) * (g.lmpitch >> 2) + lmword] >> lmshift;
-        const bool la = (nib >> (3 - Q)) & 1u, lb = (nib >> (1 - Q)) & 1u;
-        classify_extract(xa, pa, T, la, oa, cara, bita);
-        classify_extract(xb, pb, T, lb, ob, carb, bitb);
-        cara = cara && c->va[Q]; carb = carb && c->vb[Q];
-        if (!c->va[Q]) oa = xa;
-        if (!c->vb[Q]) ob = xb;
+        const unsigned nib = *lmp >> lmshift;  // bit 3 = column c0 ... bit 0 = column c0 + 3
+        lmp += g.lmpitch >> 2;
+        classify_extract(xa, pa, c->Ta[Q], (nib >> (3 - Q)) & 1u, oa, cara, bita);
+        classify_extract(xb, pb, c->Tb[Q], (nib >> (1 - Q)) & 1u, ob, carb, bitb);
         if (i >= own_lo && i < own_hi) {
             const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
-            const int ka = __popc(ma & c->lt) + __popc(mb & c->lt);
-            const int kb = ka + (cara ? 1 : 0);
-            // this lane's (at most two) carrier bits at positions ka, kb of the 64-bit piece
-            const unsigned sa = (cara && bita) ? 1u << (ka & 31) : 0u, sb = (carb && bitb) ? 1u << (kb & 31) : 0u;
-            const unsigned clo = __reduce_or_sync(0xffffffffu, (ka < 32 ? sa : 0u) | (kb < 32 ? sb : 0u));
-            const unsigned chi = __reduce_or_sync(0xffffffffu, (ka < 32 ? 0u : sa) | (kb < 32 ? 0u : sb));
-            if (c->lane == 0) {
-                const int e_idx = (i - own_lo) * g.S + c->s;
-                cnt[e_idx] = __popc(ma) + __popc(mb);
-                xbits[e_idx] = ((unsigned long long)chi << 32) | clo;
-            }
+            unsigned char* sp = xbytes + idx * 64 + __popc(ma & c->lt) + __popc(mb & c->lt);  // raster rank
+            if (cara) { sp[0] = (unsigned char)bita; ++sp; }
+            if (carb) sp[0] = (unsigned char)bitb;
+            if (c->lane == 0) cnt[idx] = __popc(ma) + __popc(mb);
         }
+        idx += g.S;
         M.template set<Q>(oa);
         M.template set<Q + 2>(ob);
         if (c->c0 < g.w) M.store(midp);
     }
 };
+
+// Packs the first `n` (<= 64) 0/1 bytes of a 64-byte slot into a 64-bit word, first byte at bit 0.
+__device__ __forceinline__ unsigned long long pack_slot(const unsigned char* slot, int n) {
+    const unsigned* w = reinterpret_cast<const unsigned*>(slot);
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // (b0 | b1<<8 | b2<<16 | b3<<24) * 0x10204080 >> 28 = b0 | b1<<1 | b2<<2 | b3<<3
+        lo |= (((w[k] & 0x01010101u) * 0x10204080u) >> 28) << (4 * k);
+        hi |= (((w[k + 8] & 0x01010101u) * 0x10204080u) >> 28) << (4 * k);
+    }
+    unsigned long long v = ((unsigned long long)hi << 32) | lo;
+    if (n < 64) v &= (1ull << n) - 1ull;  // bytes past the count are stale
+    return v;
+}
 
 // grid = n_units * nb (no inter-band dependency).  stage_bits: per (unit, pass, band)
 // `bandwords` 32-bit words, carrier bit k at word k>>5, bit k&31; stage_cnt likewise.
@@ -647,8 +657,9 @@ __global__ void __launch_bounds__(256, 4) pee_extract_kernel(PeeGeom g, PeeBatch
     int* cnt1 = reinterpret_cast<int*>(smem_raw + L.tab);   // colour 1 table
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
-    unsigned long long* xb1 = reinterpret_cast<unsigned long long*>(smem_raw + L.xb);
-    unsigned long long* xb0 = xb1 + (g.R + 2) * g.S;
+    unsigned char* xbytes = smem_raw + L.xb;                   // 64-byte slot per (row, strip), reused by both colours
+    unsigned long long* pk1 = reinterpret_cast<unsigned long long*>(smem_raw + L.pk);  // packed pieces, colour 1 then 0
+    unsigned long long* pk0 = pk1 + g.R * g.S;
     int* cnt0 = reinterpret_cast<int*>(smem_raw + L.tab0);
     unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + L.stream);  // [2][bandwords]: pass 0, pass 1
 
@@ -679,22 +690,26 @@ __global__ void __launch_bounds__(256, 4) pee_extract_kernel(PeeGeom g, PeeBatch
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
     // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
+    const int n = max(own_hi - own_lo, 0) * g.S;
     {
-        ExtractBody<PixT> body{g, nullptr, T, own_lo, own_hi, slm, r0 - 1, cnt1, xb1, 0, 0};
+        ExtractBody<PixT> body{g, nullptr, own_lo, own_hi, slm, r0 - 1, cnt1, xbytes, 0, nullptr, 0};
         sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
     }
     __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) pk1[k] = pack_slot(xbytes + k * 64, cnt1[k]);
+    __syncthreads();
     {
-        ExtractBody<PixT> body{g, nullptr, T, own_lo, own_hi, slm, r0 - 1, cnt0, xb0, 0, 0};
+        ExtractBody<PixT> body{g, nullptr, own_lo, own_hi, slm, r0 - 1, cnt0, xbytes, 0, nullptr, 0};
         sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
     }
     __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) pk0[k] = pack_slot(xbytes + k * 64, cnt0[k]);
+    __syncthreads();
 
-    // compact the per-(row,strip) pieces into one bit stream per pass
-    const int n = max(own_hi - own_lo, 0) * g.S;
+    // concatenate the per-(row,strip) pieces into one bit stream per pass
     for (int pass = 0; pass < 2; ++pass) {
         int* cnt = pass == 0 ? cnt0 : cnt1;
-        const unsigned long long* xb = pass == 0 ? xb0 : xb1;
+        const unsigned long long* pk = pass == 0 ? pk0 : pk1;
         unsigned* out = stream + (size_t)pass * g.bandwords;
         // the scan turns counts into bit offsets; a piece's size is the next offset minus its own
         const int total = block_excl_scan(cnt, n, misc);
@@ -702,7 +717,7 @@ __global__ void __launch_bounds__(256, 4) pee_extract_kernel(PeeGeom g, PeeBatch
             const int o = cnt[k];
             const int cc = (k + 1 < n ? cnt[k + 1] : total) - o;
             if (cc > 0) {
-                const unsigned long long v = xb[k];
+                const unsigned long long v = pk[k];
                 const int wi = o >> 5, sh = o & 31;
                 atomicOr(out + wi, (unsigned)(v << sh));
                 const unsigned long long hi = sh ? (v >> (32 - sh)) : (v >> 32);
