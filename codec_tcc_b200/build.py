@@ -38,13 +38,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "peeb200.h"))
     nvcc = _nvcc()
+    extra = os.environ.get("PEEB_NVCC_EXTRA", "").split()
     objs = []
     for src in SOURCES:
         spath = os.path.join(CSRC, src)
         opath = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(opath)
         if force or _stale(opath, [spath] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", spath, "-o", opath]
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", spath, "-o", opath]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

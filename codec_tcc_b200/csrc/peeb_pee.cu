@@ -22,12 +22,14 @@
 // Extraction needs no inter-band ordering for the pixels; every band writes its
 // carrier bits to a staging area and pee_gather_kernel concatenates them.
 #include <algorithm>
+#include <cstdlib>
 
 #include "peeb_common.cuh"
 
 namespace peeb {
 
 constexpr int STRIP = 128;  // columns per warp work item (4 per lane)
+
 
 struct PeeGeom {
     int h, w, itemsize;
@@ -41,6 +43,7 @@ struct PeeGeom {
     int bulk;      // TMA bulk copies usable (rowbytes % 16 == 0)
     int maxval;
     int bandwords; // extract staging: 32-bit words per (unit, pass, band)
+    int threads;   // CTA size: 256 (4 CTAs/SM), 512 (2) or 1024 (1), by how much of an SM's shared memory a band needs
 };
 
 struct PeeBatch {
@@ -420,8 +423,8 @@ struct ApplyBody {
 // grid = n_units * nb.  rowcnt[(unit*h + row)*S + strip] = pass-0 carriers of that row
 // segment (<= 64, one byte); band_cnt[unit*nb + band] = their sum over the band's own rows;
 // info[unit][3] (cap0) accumulates the unit total.
-template <typename PixT>
-__global__ void __launch_bounds__(256, 4) pee_count_kernel(PeeGeom g, PeeBatch bt, int* __restrict__ band_cnt,
+template <typename PixT, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) pee_count_kernel(PeeGeom g, PeeBatch bt, int* __restrict__ band_cnt,
                                                           unsigned char* __restrict__ rowcnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SmemLayout L = band_layout(g, 0);
@@ -449,8 +452,8 @@ __global__ void __launch_bounds__(256, 4) pee_count_kernel(PeeGeom g, PeeBatch b
 // ------------------------------------------------------------------ K_B: fused two-pass embed
 constexpr unsigned long long ST_AGG = 1ull << 62, ST_PFX = 2ull << 62, ST_MASK = 3ull << 62;
 
-template <typename PixT>
-__global__ void __launch_bounds__(256, 4) pee_embed_kernel(PeeGeom g, PeeBatch bt, const int* __restrict__ band_cnt,
+template <typename PixT, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) pee_embed_kernel(PeeGeom g, PeeBatch bt, const int* __restrict__ band_cnt,
                                                           const unsigned char* __restrict__ rowcnt,
                                                           unsigned* __restrict__ ticket,
                                                           unsigned long long* __restrict__ status) {
@@ -647,8 +650,8 @@ __device__ __forceinline__ unsigned long long pack_slot(const unsigned char* slo
 
 // grid = n_units * nb (no inter-band dependency).  stage_bits: per (unit, pass, band)
 // `bandwords` 32-bit words, carrier bit k at word k>>5, bit k&31; stage_cnt likewise.
-template <typename PixT>
-__global__ void __launch_bounds__(256, 4) pee_extract_kernel(PeeGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits,
+template <typename PixT, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) pee_extract_kernel(PeeGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits,
                                                             int* __restrict__ stage_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SmemLayout L = band_layout(g, 2);
@@ -857,27 +860,47 @@ static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int
     g.lmw = (w + 7) / 8;
     g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 4;  // +4: partial strips may peek one word past the row
     g.maxval = (1 << bit_depth) - 1;
-    // Band height: as tall as fits a quarter of an SM's shared memory (four CTAs per SM), capped at
-    // 64 rows; wide images fall back to fewer rows and, if needed, one CTA per SM.  The rows are then
-    // spread evenly over the bands.
-    const size_t budget_small = 55 * 1024, budget_max = (size_t)ws->max_smem_optin - 2048;
+    // Band height and CTA size.  Narrow images: 256-thread CTAs, four per SM, bands as tall as a
+    // quarter of the SM's shared memory allows (capped at 64 rows).  When that leaves fewer than 24
+    // rows (wide rows), the two halo rows per side cost too much: take half or all of the SM's
+    // shared memory with 512- / 1024-thread CTAs instead (same warps per SM).  Rows are then spread
+    // evenly over the bands.
+    const size_t sm_total = (size_t)ws->max_smem_optin + 1024;  // 227 KB usable + 1 KB reserved per CTA
     auto fits = [&](int r, size_t budget) {
         g.R = r; g.bandwords = (r * ((w + 1) / 2) + 31) / 32 + 2;
         return band_layout(g, kind).total <= budget;
     };
-    int R = 64;
-    while (R > 8 && !fits(R, budget_small)) R -= 4;
-    if (!fits(R, budget_small)) {
-        while (R > 1 && !fits(R, budget_max)) R -= 1;
-        if (!fits(R, budget_max)) {
-            set_error("pee: image width %d needs more shared memory than one SM has", w);
-            return PEEB_E_UNSUPPORTED;
+    auto tallest = [&](size_t budget) {
+        int r = 64;
+        while (r > 1 && !fits(r, budget)) r -= (r > 16 ? 4 : 1);
+        return fits(r, budget) ? r : 0;
+    };
+    int R = 0;
+    g.threads = 256;
+    if (const char* e = getenv("PEEB_BAND_KB")) {  // tuning experiments
+        R = tallest((size_t)atoi(e) * 1024);
+    } else {
+        const int r4 = tallest(sm_total / 4 - 1024 - 1024);
+        if (r4 >= 24) R = r4;
+        else {
+            const int r2 = tallest(sm_total / 2 - 1024 - 1024);
+            if (r2 >= 24) { R = r2; g.threads = 512; }
+            else {
+                const int r1 = tallest((size_t)ws->max_smem_optin - 1024);
+                R = r1; g.threads = 1024;
+                if (r2 >= r1 && r2 > 0) { R = r2; g.threads = 512; }
+                if (r4 >= R && r4 > 0) { R = r4; g.threads = 256; }
+            }
         }
+    }
+    if (R <= 0) {
+        set_error("pee: image width %d needs more shared memory than one SM has", w);
+        return PEEB_E_UNSUPPORTED;
     }
     if (R > h) R = h;
     const int nb = (h + R - 1) / R;
     R = (h + nb - 1) / nb;
-    fits(R, budget_max);
+    fits(R, (size_t)ws->max_smem_optin);
     g.nb = (h + g.R - 1) / g.R;
     return PEEB_OK;
 }
@@ -916,6 +939,34 @@ static int set_smem(K kernel, size_t bytes) {
     return PEEB_OK;
 }
 
+// launch dispatch over (pixel type, CTA size)
+template <typename PixT, int NT>
+static int launch_embed(peeb_ws* ws, const PeeGeom& g, const PeeBatch& bt, long long nbands, size_t smem, int* band_cnt,
+                        unsigned char* rowcnt, unsigned* ticket, unsigned long long* status, cudaStream_t st) {
+    int rc = set_smem(pee_count_kernel<PixT, NT>, smem); if (rc) return rc;
+    rc = set_smem(pee_embed_kernel<PixT, NT>, smem); if (rc) return rc;
+    { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
+      pee_count_kernel<PixT, NT><<<(unsigned)nbands, NT, smem, st>>>(g, bt, band_cnt, rowcnt); }
+    { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+      pee_embed_kernel<PixT, NT><<<(unsigned)nbands, NT, smem, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
+    return PEEB_OK;
+}
+template <typename PixT, int NT>
+static int launch_extract(peeb_ws* ws, const PeeGeom& g, const PeeBatch& bt, long long nbands, size_t smem,
+                          unsigned* stage_bits, int* stage_cnt, cudaStream_t st) {
+    int rc = set_smem(pee_extract_kernel<PixT, NT>, smem); if (rc) return rc;
+    ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
+    pee_extract_kernel<PixT, NT><<<(unsigned)nbands, NT, smem, st>>>(g, bt, stage_bits, stage_cnt);
+    return PEEB_OK;
+}
+#define PEEB_DISPATCH(FN, ...)                                                                     \
+    (g.itemsize == 2 ? (g.threads == 256 ? FN<unsigned short, 256>(__VA_ARGS__)                     \
+                        : g.threads == 512 ? FN<unsigned short, 512>(__VA_ARGS__)                   \
+                                           : FN<unsigned short, 1024>(__VA_ARGS__))                 \
+                     : (g.threads == 256 ? FN<unsigned char, 256>(__VA_ARGS__)                      \
+                        : g.threads == 512 ? FN<unsigned char, 512>(__VA_ARGS__)                    \
+                                           : FN<unsigned char, 1024>(__VA_ARGS__)))
+
 static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
                             int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
                             int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm,
@@ -953,21 +1004,8 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
     const size_t smem = band_layout(g, 1).total;
     if (h >= 3 && w >= 3) {
-        if (itemsize == 2) {
-            rc = set_smem(pee_count_kernel<unsigned short>, smem); if (rc) return rc;
-            rc = set_smem(pee_embed_kernel<unsigned short>, smem); if (rc) return rc;
-            { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-              pee_count_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt); }
-            { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
-              pee_embed_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
-        } else {
-            rc = set_smem(pee_count_kernel<unsigned char>, smem); if (rc) return rc;
-            rc = set_smem(pee_embed_kernel<unsigned char>, smem); if (rc) return rc;
-            { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-              pee_count_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt); }
-            { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
-              pee_embed_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
-        }
+        rc = PEEB_DISPATCH(launch_embed, ws, g, bt, nbands, smem, band_cnt, rowcnt, ticket, status, st);
+        if (rc) return rc;
         PEEB_CUDA(cudaGetLastError());
     } else {
         // no interior: nothing can be embedded, marked == source, empty location map
@@ -1023,15 +1061,8 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
     else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
     if (h >= 3 && w >= 3) {
         const size_t smem = band_layout(g, 2).total;
-        if (itemsize == 2) {
-            rc = set_smem(pee_extract_kernel<unsigned short>, smem); if (rc) return rc;
-            ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
-            pee_extract_kernel<unsigned short><<<(unsigned)nbands, 256, smem, st>>>(g, bt, stage_bits, stage_cnt);
-        } else {
-            rc = set_smem(pee_extract_kernel<unsigned char>, smem); if (rc) return rc;
-            ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
-            pee_extract_kernel<unsigned char><<<(unsigned)nbands, 256, smem, st>>>(g, bt, stage_bits, stage_cnt);
-        }
+        rc = PEEB_DISPATCH(launch_extract, ws, g, bt, nbands, smem, stage_bits, stage_cnt, st);
+        if (rc) return rc;
         PEEB_CUDA(cudaGetLastError());
     } else {
         PEEB_CUDA(cudaMemsetAsync(stage_cnt, 0, cnt_bytes, st));
@@ -1118,7 +1149,8 @@ static int64_t max_payload_bytes(int n_units, const int64_t* n_bits) {
 // Units per chunk of a host batch: small enough that several chunks overlap their PCIe copies
 // with each other's kernels, large enough to fill the GPU.
 static int chunk_units(int n_units, size_t unit_bytes) {
-    const size_t target = 16u << 20;
+    size_t target = 16u << 20;
+    if (const char* e = getenv("PEEB_CHUNK_MB")) target = (size_t)atoi(e) << 20;  // tuning experiments
     long long c = (long long)((target + unit_bytes - 1) / unit_bytes);
     if (c < 1) c = 1;
     if (c > n_units) c = n_units;

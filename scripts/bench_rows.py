@@ -1,0 +1,153 @@
+"""Measures the non-headline rows of SURVEY.md section 8 (a1-a9) on one B200:
+each C-ABI kernel device-resident (CUDA events, achieved algorithmic GB/s vs the
+measured copy peak) and each numpy-API call end to end, next to the CPU oracle
+(the numpy restatement of the reference) timed on the same inputs.
+
+    python scripts/bench_rows.py > gpurun_out/rows.json
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from codec_tcc_b200 import _cabi, codec, mse  # noqa: E402
+from codec_tcc_b200.synth import synth_image  # noqa: E402
+from oracle import codec_numpy as OC  # noqa: E402
+from oracle import mse_numpy as OM  # noqa: E402
+
+L = _cabi.lib()
+ws = _cabi.workspace(0)
+dev = torch.device("cuda", 0)
+peak = 6557.1
+pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+if os.path.exists(pp):
+    peak = float(json.load(open(pp))["hbm_gbs"])
+
+
+def dev_time(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
+def wall(fn, reps=3):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def stream():
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+rows = []
+h = w = 3000
+n_img = 16
+imgs = np.stack([synth_image(h, w, 4095, 50 + k) for k in range(n_img)])
+stego = imgs.copy()
+stego[:, ::3, ::5] ^= 1
+d_a = torch.from_numpy(imgs.view(np.int16)).to(dev)
+d_b = torch.from_numpy(stego.view(np.int16)).to(dev)
+npx = h * w
+
+# ---- a1-a4: moments (16 images of 3000x3000: 288 MB per operand, larger than L2)
+d_out = torch.empty((n_img, 12), dtype=torch.int64, device=dev)
+t = dev_time(lambda: _cabi.check(L.peeb_moments_batch(ws.handle, d_a.data_ptr(), d_b.data_ptr(), npx, 2, n_img, npx, npx,
+                                                      d_out.data_ptr(), stream())))
+rows.append({"row": "a1-a4", "kernel": "moments_kernel", "workload": f"{n_img} x {h}x{w} u16 pairs",
+             "device_ms": t * 1e3, "mpixel_s": n_img * npx / t / 1e6, "algorithmic_gb_s": 4 * n_img * npx / t / 1e9,
+             "frac_of_measured_peak": 4 * n_img * npx / t / 1e9 / peak})
+an = mse.AnalisadorMSE()
+t_api = wall(lambda: an.analisar_par_arrays(imgs[0], stego[0]))
+t_cpu = wall(lambda: (OM.calcular_mse(imgs[0], stego[0]), OM.calcular_ssim_simples(imgs[0], stego[0]),
+                      OM.difference_stats(imgs[0], stego[0])), reps=1)
+rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3,
+                cpu_oracle_mpixel_s=npx / t_cpu / 1e6, api="AnalisadorMSE.analisar_par_arrays (mse+psnr+ssim+stats, one image pair)")
+
+# ---- a5: histogram + plane counts, plane split
+d_hist = torch.empty(65536, dtype=torch.int32, device=dev)
+d_ones = torch.empty(16, dtype=torch.int64, device=dev)
+big = d_a.reshape(-1)
+t = dev_time(lambda: _cabi.check(L.peeb_hist_planes(ws.handle, big.data_ptr(), big.numel(), 2, d_hist.data_ptr(),
+                                                    d_ones.data_ptr(), stream())))
+rows.append({"row": "a5", "kernel": "hist_kernel+hist_to_planes", "workload": f"{n_img * npx / 1e6:.0f} Mpixel u16 (12-bit values)",
+             "device_ms": t * 1e3, "mpixel_s": big.numel() / t / 1e6, "algorithmic_gb_s": 2 * big.numel() / t / 1e9,
+             "frac_of_measured_peak": 2 * big.numel() / t / 1e9 / peak})
+t_api = wall(lambda: codec.adaptive_modalities_decomposition(imgs[0], beta=0.8))
+t_cpu = wall(lambda: OC.adaptive_modalities_decomposition(imgs[0], beta=0.8), reps=1)
+rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3,
+                cpu_oracle_mpixel_s=npx / t_cpu / 1e6, api="adaptive_modalities_decomposition (one 3000x3000 image, 16 planes returned)")
+
+d_planes = torch.empty((16, npx), dtype=torch.int16, device=dev)
+t = dev_time(lambda: _cabi.check(L.peeb_planes_unpack(ws.handle, d_a.data_ptr(), npx, 2, 0, 16, d_planes.data_ptr(), stream())))
+rows.append({"row": "a5/a8", "kernel": "planes_unpack_kernel", "workload": "3000x3000 u16 -> 16 planes", "device_ms": t * 1e3,
+             "mpixel_s": npx / t / 1e6, "algorithmic_gb_s": (2 + 32) * npx / t / 1e9, "frac_of_measured_peak": (2 + 32) * npx / t / 1e9 / peak})
+d_packed = torch.empty(npx, dtype=torch.int16, device=dev)
+t = dev_time(lambda: _cabi.check(L.peeb_planes_pack(ws.handle, d_planes.data_ptr(), npx, 2, 16, d_packed.data_ptr(), stream())))
+rows.append({"row": "a8", "kernel": "planes_pack_kernel", "workload": "16 planes -> 3000x3000 u16", "device_ms": t * 1e3,
+             "mpixel_s": npx / t / 1e6, "algorithmic_gb_s": (2 + 32) * npx / t / 1e9, "frac_of_measured_peak": (2 + 32) * npx / t / 1e9 / peak})
+g, l = codec.adaptive_modalities_decomposition(imgs[0], beta=0.8)
+t_api = wall(lambda: codec.merge_modalities(g, l))
+t_cpu = wall(lambda: OC.merge_modalities(g, l), reps=1)
+rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3, cpu_oracle_mpixel_s=npx / t_cpu / 1e6,
+                api="merge_modalities (16 planes)")
+
+# ---- a6/a7: tile moments + LSB embed (s planes in, s planes + s uint8 bitmaps out)
+s = len(l)
+d_sums = torch.empty((((h + 15) // 16) * ((w + 15) // 16), 2), dtype=torch.int64, device=dev)
+t = dev_time(lambda: _cabi.check(L.peeb_tile_moments(ws.handle, d_planes.data_ptr(), h, w, 2, 16, d_sums.data_ptr(), stream())))
+rows.append({"row": "a6", "kernel": "tile_moments_kernel", "workload": "3000x3000 plane, 16x16 tiles", "device_ms": t * 1e3,
+             "mpixel_s": npx / t / 1e6, "algorithmic_gb_s": 2 * npx / t / 1e9, "frac_of_measured_peak": 2 * npx / t / 1e9 / peak})
+pay_bits = int(npx * 2.0)
+rng = np.random.default_rng(1)
+bits = "".join("1" if b else "0" for b in rng.integers(0, 2, pay_bits).tolist())
+d_out_planes = torch.empty((s, npx), dtype=torch.int16, device=dev)
+d_bm = torch.empty((s, npx), dtype=torch.uint8, device=dev)
+d_pay = torch.from_numpy(np.packbits(rng.integers(0, 2, pay_bits, dtype=np.uint8))).to(dev)
+segs, sizes, order = codec.distribute_message_segments(l, bits)
+start = np.zeros(s, np.int64); ln = np.zeros(s, np.int64); off = np.zeros(s, np.int64)
+at = 0
+for seg, p in zip(segs, order):
+    ln[p] = min(len(seg), npx); off[p] = at; at += ln[p]
+t = dev_time(lambda: _cabi.check(L.peeb_lsb_embed(ws.handle, d_planes.data_ptr(), npx, 2, s, start.ctypes.data, ln.ctypes.data,
+                                                 off.ctypes.data, d_pay.data_ptr(), pay_bits, d_out_planes.data_ptr(),
+                                                 d_bm.data_ptr(), stream())))
+rows.append({"row": "a6/a7", "kernel": "lsb_embed_kernel", "workload": f"s={s} planes of 3000x3000 u16, {pay_bits / 1e6:.1f} Mbit payload",
+             "device_ms": t * 1e3, "mpixel_s": npx / t / 1e6, "algorithmic_gb_s": s * 5 * npx / t / 1e9,
+             "frac_of_measured_peak": s * 5 * npx / t / 1e9 / peak})
+t_api = wall(lambda: codec.lsb_embed_block_then_multiplane(l, bits, search_block_size=16), reps=1)
+t0 = time.perf_counter(); ref = OC.lsb_embed_block_then_multiplane(l, bits, search_block_size=16); t_cpu = time.perf_counter() - t0
+got = codec.lsb_embed_block_then_multiplane(l, bits, search_block_size=16)
+assert all(np.array_equal(a, b) for a, b in zip(ref[0] + ref[1], got[0] + got[1])) and ref[2:] == got[2:]
+rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3, cpu_oracle_mpixel_s=npx / t_cpu / 1e6,
+                api="lsb_embed_block_then_multiplane (numpy planes in/out, '0'/'1' string payload); outputs equal the restatement")
+
+# ---- a9: decode_message
+meta = {"s": s, "segments_indices": got[4], "segments_lengths": got[3]}
+t_api = wall(lambda: codec.decode_message(got[0], got[1], meta), reps=1)
+t0 = time.perf_counter(); r0 = OC.decode_message(ref[0], ref[1], meta); t_cpu = time.perf_counter() - t0
+assert r0 == codec.decode_message(got[0], got[1], meta)
+rows.append({"row": "a9", "kernel": "compact_{count,scan,write}", "workload": f"s={s} planes 3000x3000", "api_ms": t_api * 1e3,
+             "api_mpixel_s": npx / t_api / 1e6, "cpu_oracle_ms": t_cpu * 1e3, "cpu_oracle_mpixel_s": npx / t_cpu / 1e6,
+             "api": "decode_message (outputs equal the restatement)"})
+
+print(json.dumps({"peak_gb_s": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(pp) else "fallback",
+                  "cpu_cores_used_by_oracle": 1, "rows": rows}, indent=1))
