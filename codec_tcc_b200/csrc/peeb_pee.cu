@@ -67,8 +67,18 @@ template <> struct Row4<unsigned short> {
     static constexpr int ITEM = 2;
     __device__ __forceinline__ void load(const unsigned char* p) { v = *reinterpret_cast<const uint2*>(p); }
     __device__ __forceinline__ void store(unsigned char* p) const { *reinterpret_cast<uint2*>(p) = v; }
+    // Note (round 1 experiment): the kernels are bound by the ALU pipe (LOP3/SHF/ISETP/SEL, ncu ~70-80 %
+    // busy) while the FMA pipe idles (~20 %).  Extracting halfwords with IMAD.HI / IMAD instead
+    // (-DPEEB_FMA_EXTRACT) moves 10 ops per row step to the FMA pipe but needs two instructions
+    // for the low half and was not faster on B200 (0.394 vs 0.389 ms), so LOP3/SHF stays.
     template <int K> __device__ __forceinline__ int f() const {
+#ifndef PEEB_FMA_EXTRACT
         return K == 0 ? (int)(v.x & 0xffffu) : K == 1 ? (int)(v.x >> 16) : K == 2 ? (int)(v.y & 0xffffu) : (int)(v.y >> 16);
+#else
+        const unsigned wv = K < 2 ? v.x : v.y;
+        const unsigned hi = __umulhi(wv, 0x10000u);
+        return (K & 1) ? (int)hi : (int)(wv + hi * 0xffff0000u);
+#endif
     }
     template <int K> __device__ __forceinline__ void set(int a) {
         if (K == 0) v.x = __byte_perm(v.x, (unsigned)a, 0x3254);
@@ -254,6 +264,7 @@ struct ItemCtx {
     int lane;
     unsigned lt;  // lanemask_lt
     bool va[2], vb[2];  // validity (interior column) of pixel A / B for Q = 0 / 1
+    bool in_image;      // c0 < w: this lane's word holds image columns and may be written back
     int Ta[2], Tb[2];   // the threshold for pixel A / B, 0 where the column is not interior: with T = 0
                         // a pixel is never expandable and its shift is by 0, i.e. it is left alone
 };
@@ -324,6 +335,7 @@ __device__ __forceinline__ void sweep(const PeeGeom& g, unsigned char* simg, int
         const int chunk = item / g.S;
         c.s = item - chunk * g.S;
         c.c0 = c.s * STRIP + 4 * lane;
+        c.in_image = c.c0 < g.w;
         const int ra = row_lo + chunk * RC, rb = min(ra + RC, row_hi);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -378,7 +390,7 @@ struct CountBody {
 // ---- body: full apply of one colour (pass 0 of the embed kernel) --------------------------
 // tab[(i-row0)*S + strip] = index into `bits` (one byte per payload bit of this band, zero
 // padded) of the first carrier of that (row, strip).
-template <typename PixT>
+template <typename PixT, bool ALLOWN>
 struct ApplyBody {
     const PeeGeom& g;
     const ItemCtx* c;
@@ -402,7 +414,7 @@ struct ApplyBody {
         idx += g.S;
         if (cara) { na += bp[0]; ++bp; }
         if (carb) nb += bp[0];
-        if (i >= own_lo && i < own_hi) {
+        if (ALLOWN || (i >= own_lo && i < own_hi)) {
             const int da = na - xa, db = nb - xb;
             st->sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
             if (fla | flb) {  // rare; only interior columns may enter the map
@@ -415,7 +427,7 @@ struct ApplyBody {
         }
         M.template set<Q>(na);
         M.template set<Q + 2>(nb);
-        if (c->c0 < g.w) M.store(midp);
+        if (c->in_image) M.store(midp);
     }
 };
 
@@ -515,7 +527,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) pee_embed_kernel(PeeGeom g, Pee
         const int total0 = block_excl_scan(tab, n0, misc);   // tab: index into `bits`
         expand_payload(payload, (unsigned)(misc[41] - halo_top), total0, n_bits, bits);
         __syncthreads();
-        ApplyBody<PixT> body{g, nullptr, p0_lo, own_lo, own_hi, tab, bits, slm, r0, &st, 0};
+        ApplyBody<PixT, false> body{g, nullptr, p0_lo, own_lo, own_hi, tab, bits, slm, r0, &st, 0};
         sweep<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
     }
     __syncthreads();
@@ -546,7 +558,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) pee_embed_kernel(PeeGeom g, Pee
         __syncthreads();
         expand_payload(payload, (unsigned)(misc[42] + misc[43]), total, n_bits, bits);  // from cap0 + earlier bands' pass-1 carriers
         __syncthreads();
-        ApplyBody<PixT> body{g, nullptr, own_lo, own_lo, own_hi, tab, bits, slm, r0, &st, 0};
+        ApplyBody<PixT, true> body{g, nullptr, own_lo, own_lo, own_hi, tab, bits, slm, r0, &st, 0};
         sweep<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
     }
 
@@ -592,7 +604,7 @@ __global__ void pee_finalize_kernel(PeeBatch bt, int extract) {
 // ------------------------------------------------------------------ K_X: extract
 // One sweep per colour; pixels are restored in place, carrier bits of the band's own
 // rows are compacted per (row, strip) with ballots and a warp OR-reduction.
-template <typename PixT>
+template <typename PixT, bool ALLOWN>
 struct ExtractBody {
     const PeeGeom& g;
     const ItemCtx* c;
@@ -619,7 +631,7 @@ struct ExtractBody {
         lmp += g.lmpitch >> 2;
         classify_extract(xa, pa, c->Ta[Q], (nib >> (3 - Q)) & 1u, oa, cara, bita);
         classify_extract(xb, pb, c->Tb[Q], (nib >> (1 - Q)) & 1u, ob, carb, bitb);
-        if (i >= own_lo && i < own_hi) {
+        if (ALLOWN || (i >= own_lo && i < own_hi)) {
             const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
             unsigned char* sp = xbytes + idx * 64 + __popc(ma & c->lt) + __popc(mb & c->lt);  // raster rank
             if (cara) { sp[0] = (unsigned char)bita; ++sp; }
@@ -629,7 +641,7 @@ struct ExtractBody {
         idx += g.S;
         M.template set<Q>(oa);
         M.template set<Q + 2>(ob);
-        if (c->c0 < g.w) M.store(midp);
+        if (c->in_image) M.store(midp);
     }
 };
 
@@ -695,14 +707,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) pee_extract_kernel(PeeGeom g, P
     // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
     const int n = max(own_hi - own_lo, 0) * g.S;
     {
-        ExtractBody<PixT> body{g, nullptr, own_lo, own_hi, slm, r0 - 1, cnt1, xbytes, 0, nullptr, 0};
+        ExtractBody<PixT, false> body{g, nullptr, own_lo, own_hi, slm, r0 - 1, cnt1, xbytes, 0, nullptr, 0};
         sweep<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < n; k += blockDim.x) pk1[k] = pack_slot(xbytes + k * 64, cnt1[k]);
     __syncthreads();
     {
-        ExtractBody<PixT> body{g, nullptr, own_lo, own_hi, slm, r0 - 1, cnt0, xbytes, 0, nullptr, 0};
+        ExtractBody<PixT, true> body{g, nullptr, own_lo, own_hi, slm, r0 - 1, cnt0, xbytes, 0, nullptr, 0};
         sweep<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
     }
     __syncthreads();
