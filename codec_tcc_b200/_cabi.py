@@ -46,6 +46,8 @@ SIGNATURES = {
     "peeb_prof_name": (C.c_char_p, [_i32]),
     "peeb_moments_batch": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp]),
     "peeb_moments_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "peeb_sse_batch": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp]),
+    "peeb_sse_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "peeb_hist_planes": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "peeb_hist_planes_h": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "peeb_planes_unpack": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),

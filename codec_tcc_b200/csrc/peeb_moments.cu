@@ -8,8 +8,16 @@ namespace peeb {
 struct Acc {
     unsigned long long sse = 0, sad = 0, ne = 0, sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
     unsigned maxd = 0, maxa = 0, maxb = 0;
+    // FULL=false keeps only what calcular_mse needs when both maxima agree: SSE and the two maxima
+    template <bool FULL>
     __device__ __forceinline__ void add(unsigned a, unsigned b) {
         const int d = (int)a - (int)b;
+        if (!FULL) {
+            sse += (unsigned long long)((long long)d * d);
+            maxa = max(maxa, a);
+            maxb = max(maxb, b);
+            return;
+        }
         const unsigned ad = (unsigned)(d < 0 ? -d : d);
         sse += (unsigned long long)ad * ad;
         saa += (unsigned long long)a * a;
@@ -31,24 +39,24 @@ struct Acc {
     }
 };
 
-template <int ITEM>
+template <int ITEM, bool FULL>
 __device__ __forceinline__ void add_vec(Acc& acc, const int4& va, const int4& vb) {
     const unsigned wa[4] = {(unsigned)va.x, (unsigned)va.y, (unsigned)va.z, (unsigned)va.w};
     const unsigned wb[4] = {(unsigned)vb.x, (unsigned)vb.y, (unsigned)vb.z, (unsigned)vb.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (ITEM == 2) {
-            acc.add(wa[k] & 0xffffu, wb[k] & 0xffffu);
-            acc.add(wa[k] >> 16, wb[k] >> 16);
+            acc.template add<FULL>(wa[k] & 0xffffu, wb[k] & 0xffffu);
+            acc.template add<FULL>(wa[k] >> 16, wb[k] >> 16);
         } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc.add((wa[k] >> (8 * j)) & 0xffu, (wb[k] >> (8 * j)) & 0xffu);
+            for (int j = 0; j < 4; ++j) acc.template add<FULL>((wa[k] >> (8 * j)) & 0xffu, (wb[k] >> (8 * j)) & 0xffu);
         }
     }
 }
 
 // grid = (blocks_per_image, n_images); out zeroed by the caller.
-template <int ITEM>
+template <int ITEM, bool FULL>
 __global__ void __launch_bounds__(256) moments_kernel(const unsigned char* __restrict__ a,
                                                       const unsigned char* __restrict__ b, long long n,
                                                       long long stride_a, long long stride_b,
@@ -72,17 +80,17 @@ __global__ void __launch_bounds__(256) moments_kernel(const unsigned char* __res
 #pragma unroll
         for (int u = 0; u < 4; ++u) { va[u] = ldg_stream(qa + i + u * nthr); vb[u] = ldg_stream(qb + i + u * nthr); }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) add_vec<ITEM>(acc, va[u], vb[u]);
+        for (int u = 0; u < 4; ++u) add_vec<ITEM, FULL>(acc, va[u], vb[u]);
         if (++since_fold == 256) { acc.fold(); since_fold = 0; }
     }
-    for (; i < nvec; i += nthr) add_vec<ITEM>(acc, ldg_stream(qa + i), ldg_stream(qb + i));
+    for (; i < nvec; i += nthr) add_vec<ITEM, FULL>(acc, ldg_stream(qa + i), ldg_stream(qb + i));
     acc.fold();
     // scalar tail (or everything, when unaligned)
     for (long long e = nvec * PER_VEC + tid; e < n; e += nthr) {
         unsigned x, y;
         if (ITEM == 2) { x = reinterpret_cast<const unsigned short*>(pa)[e]; y = reinterpret_cast<const unsigned short*>(pb)[e]; }
         else { x = pa[e]; y = pb[e]; }
-        acc.add(x, y);
+        acc.template add<FULL>(x, y);
         acc.fold();
     }
 
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const unsigned char* __res
 }
 
 static int launch_moments(peeb_ws* ws, const void* a, const void* b, int64_t n, int itemsize, int n_images,
-                          int64_t stride_a, int64_t stride_b, int64_t* out, cudaStream_t st) {
+                          int64_t stride_a, int64_t stride_b, int64_t* out, cudaStream_t st, bool full = true) {
     PEEB_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * PEEB_MOMENTS * n_images, st));
     if (n <= 0) return PEEB_OK;
     // enough blocks to fill the machine (multiples of the SM count), split over the images
@@ -136,12 +144,13 @@ static int launch_moments(peeb_ws* ws, const void* a, const void* b, int64_t n, 
     if (want > cap) want = cap;
     dim3 grid((unsigned)want, (unsigned)n_images);
     ProfScope prof(ws, PEEB_K_MOMENTS, st);
-    if (itemsize == 2)
-        moments_kernel<2><<<grid, 256, 0, st>>>((const unsigned char*)a, (const unsigned char*)b, n, stride_a,
-                                                stride_b, (unsigned long long*)out);
-    else
-        moments_kernel<1><<<grid, 256, 0, st>>>((const unsigned char*)a, (const unsigned char*)b, n, stride_a,
-                                                stride_b, (unsigned long long*)out);
+    const unsigned char* pa = (const unsigned char*)a;
+    const unsigned char* pb = (const unsigned char*)b;
+    unsigned long long* po = (unsigned long long*)out;
+    if (itemsize == 2 && full) moments_kernel<2, true><<<grid, 256, 0, st>>>(pa, pb, n, stride_a, stride_b, po);
+    else if (itemsize == 2) moments_kernel<2, false><<<grid, 256, 0, st>>>(pa, pb, n, stride_a, stride_b, po);
+    else if (full) moments_kernel<1, true><<<grid, 256, 0, st>>>(pa, pb, n, stride_a, stride_b, po);
+    else moments_kernel<1, false><<<grid, 256, 0, st>>>(pa, pb, n, stride_a, stride_b, po);
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }
@@ -161,8 +170,29 @@ int peeb_moments_batch(peeb_ws* ws, const void* a, const void* b, int64_t n, int
     return launch_moments(ws, a, b, n, itemsize, n_images, stride_a, stride_b, out, (cudaStream_t)stream);
 }
 
+int peeb_sse_batch(peeb_ws* ws, const void* a, const void* b, int64_t n, int itemsize, int n_images,
+                   int64_t stride_a, int64_t stride_b, int64_t* out, void* stream) {
+    PEEB_REQUIRE(ws && a && b && out, "peeb_sse_batch: null pointer");
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_sse_batch: itemsize must be 1 or 2");
+    PEEB_REQUIRE(n >= 0 && n_images >= 1 && n_images <= 65535, "peeb_sse_batch: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    return launch_moments(ws, a, b, n, itemsize, n_images, stride_a, stride_b, out, (cudaStream_t)stream, false);
+}
+
+static int moments_host(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
+                        int64_t* out_host, bool full);
+
 int peeb_moments_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
                    int64_t* out_host) {
+    return moments_host(ws, a_host, b_host, n, itemsize, out_host, true);
+}
+
+int peeb_sse_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize, int64_t* out_host) {
+    return moments_host(ws, a_host, b_host, n, itemsize, out_host, false);
+}
+
+static int moments_host(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
+                        int64_t* out_host, bool full) {
     PEEB_REQUIRE(ws && a_host && b_host && out_host, "peeb_moments_h: null pointer");
     PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_moments_h: itemsize must be 1 or 2");
     PEEB_REQUIRE(n >= 0, "peeb_moments_h: negative size");
@@ -180,7 +210,7 @@ int peeb_moments_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t 
     PEEB_CUDA(cudaMemcpyAsync(db, b_host, (size_t)n * itemsize, cudaMemcpyHostToDevice, ws->stream2));
     PEEB_CUDA(cudaEventRecord(ws->ev[0], ws->stream2));
     PEEB_CUDA(cudaStreamWaitEvent(ws->stream, ws->ev[0], 0));
-    rc = launch_moments(ws, da, db, n, itemsize, 1, 0, 0, dout, ws->stream);
+    rc = launch_moments(ws, da, db, n, itemsize, 1, 0, 0, dout, ws->stream, full);
     if (rc) return rc;
     PEEB_CUDA(cudaMemcpyAsync(out_host, dout, sizeof(int64_t) * PEEB_MOMENTS, cudaMemcpyDeviceToHost, ws->stream));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream));

@@ -93,8 +93,9 @@ def pee_extract_device(marked, lm, T, n_bits, bit_depth, payload_out=None, recov
     return payload_out, recovered, info
 
 
-def moments_device(a, b, out=None):
-    """Per-image integer moments of two (n, ...) pixel tensors -> (n, 12) int64."""
+def moments_device(a, b, out=None, full=True):
+    """Per-image integer moments of two (n, ...) pixel tensors -> (n, 12) int64.
+    ``full=False``: the MSE-only subset (SSE, maxima, n), HBM bound."""
     dev = a.device
     item = _pixels(a, "a")
     if a.shape != b.shape or a.element_size() != b.element_size():
@@ -104,6 +105,7 @@ def moments_device(a, b, out=None):
     if out is None:
         out = torch.empty((n, MOMENTS), dtype=torch.int64, device=dev)
     ws = workspace(dev.index if dev.index is not None else torch.cuda.current_device())
-    check(lib().peeb_moments_batch(ws.handle, _raw(a, "a"), _raw(b, "b"), per, item, n, per, per, _raw(out, "out"),
-                                   _stream(dev)), "peeb_moments_batch")
+    fn = lib().peeb_moments_batch if full else lib().peeb_sse_batch
+    check(fn(ws.handle, _raw(a, "a"), _raw(b, "b"), per, item, n, per, per, _raw(out, "out"), _stream(dev)),
+          "peeb_moments_batch")
     return out

@@ -54,8 +54,9 @@ def _as_pixels(img, name):
     raise TypeError(f"{name}: unsupported dtype {a.dtype}")
 
 
-def image_moments(img1, img2, device=None) -> dict:
-    """The twelve integers (see module docstring) as Python ints."""
+def image_moments(img1, img2, device=None, full=True) -> dict:
+    """The twelve integers (see module docstring) as Python ints.  ``full=False``
+    runs the lighter SSE-only kernel: only sse, max_a, max_b and n are filled."""
     a = _as_pixels(img1, "img1")
     b = _as_pixels(img2, "img2")
     if a.shape != b.shape:
@@ -67,7 +68,8 @@ def image_moments(img1, img2, device=None) -> dict:
         b = b.astype(np.uint16)
     out = np.zeros(MOMENTS, np.int64)
     ws = workspace(device)
-    check(lib().peeb_moments_h(ws.handle, ptr(a), ptr(b), a.size, a.dtype.itemsize, ptr(out)), "peeb_moments_h")
+    fn = lib().peeb_moments_h if full else lib().peeb_sse_h
+    check(fn(ws.handle, ptr(a), ptr(b), a.size, a.dtype.itemsize, ptr(out)), "peeb_moments_h")
     return {k: int(v) for k, v in zip(_KEYS, out)}
 
 
@@ -96,7 +98,9 @@ class AnalisadorMSE:
     # -- a1 ---------------------------------------------------------------
     def calcular_mse(self, imagem1, imagem2):
         """src/mse.py:74-116 -> ``(np.float64 mse, np.float64 max_range)``."""
-        m = image_moments(imagem1, imagem2, self._device)
+        m = image_moments(imagem1, imagem2, self._device, full=False)
+        if m["max_a"] != m["max_b"]:  # the normalisation branch needs the second moments too
+            m = image_moments(imagem1, imagem2, self._device)
         return self._mse_from(m)
 
     @staticmethod

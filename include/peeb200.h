@@ -97,6 +97,13 @@ int peeb_moments_batch(peeb_ws* ws, const void* a, const void* b, int64_t n_per_
                        int n_images, int64_t stride_a, int64_t stride_b, int64_t* out, void* stream);
 int peeb_moments_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
                    int64_t* out_host);
+/* The MSE-only subset -- out[0] (SSE), out[9], out[10] (maxima), out[11] (n); the other slots are 0.
+ * It is all calcular_mse (src/mse.py:74-116) needs when both maxima agree, and it is HBM bound where
+ * the full set is bound by integer issue. */
+int peeb_sse_batch(peeb_ws* ws, const void* a, const void* b, int64_t n_per_image, int itemsize,
+                   int n_images, int64_t stride_a, int64_t stride_b, int64_t* out, void* stream);
+int peeb_sse_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
+               int64_t* out_host);
 
 /* ---- a5: histogram + bit-plane population counts ---------------------- *
  * Everything adaptive_modalities_decomposition / calculate_entropy /

@@ -75,11 +75,20 @@ t = dev_time(lambda: _cabi.check(L.peeb_moments_batch(ws.handle, d_a.data_ptr(),
 rows.append({"row": "a1-a4", "kernel": "moments_kernel", "workload": f"{n_img} x {h}x{w} u16 pairs",
              "device_ms": t * 1e3, "mpixel_s": n_img * npx / t / 1e6, "algorithmic_gb_s": 4 * n_img * npx / t / 1e9,
              "frac_of_measured_peak": 4 * n_img * npx / t / 1e9 / peak})
+t = dev_time(lambda: _cabi.check(L.peeb_sse_batch(ws.handle, d_a.data_ptr(), d_b.data_ptr(), npx, 2, n_img, npx, npx,
+                                                  d_out.data_ptr(), stream())))
+rows.append({"row": "a1", "kernel": "moments_kernel<FULL=false> (SSE + maxima: calcular_mse)", "workload": f"{n_img} x {h}x{w} u16 pairs",
+             "device_ms": t * 1e3, "mpixel_s": n_img * npx / t / 1e6, "algorithmic_gb_s": 4 * n_img * npx / t / 1e9,
+             "frac_of_measured_peak": 4 * n_img * npx / t / 1e9 / peak})
 an = mse.AnalisadorMSE()
+t_api = wall(lambda: an.calcular_mse(imgs[0], stego[0]))
+t_cpu = wall(lambda: OM.calcular_mse(imgs[0], stego[0]), reps=1)
+rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3,
+                cpu_oracle_mpixel_s=npx / t_cpu / 1e6, api="AnalisadorMSE.calcular_mse (one image pair, pageable numpy arrays)")
 t_api = wall(lambda: an.analisar_par_arrays(imgs[0], stego[0]))
 t_cpu = wall(lambda: (OM.calcular_mse(imgs[0], stego[0]), OM.calcular_ssim_simples(imgs[0], stego[0]),
                       OM.difference_stats(imgs[0], stego[0])), reps=1)
-rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3,
+rows[-2].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3,
                 cpu_oracle_mpixel_s=npx / t_cpu / 1e6, api="AnalisadorMSE.analisar_par_arrays (mse+psnr+ssim+stats, one image pair)")
 
 # ---- a5: histogram + plane counts, plane split
