@@ -190,6 +190,7 @@ def run_gpu_arm(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = shard.bind_to_gpu_numa(local) if world > 1 else []  # host buffers on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -359,6 +360,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
             "capacity_bpp": float(cap.mean() / (h * w)), "images_total": int(stats.shape[0]),
             "bit_exact": "round trip identity on all images; first 2 images == CPU oracle (oracle/pee_ref.c)",
+            "numa_cores_rank0": len(numa_cores),
             "setup_s": gen_s,
         }
         if cpu_baseline is not None:

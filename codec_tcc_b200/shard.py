@@ -39,6 +39,29 @@ def partition_grid(n_images: int, n_params: int, world: int, rank: int):
     return u // max(n_params, 1), u % max(n_params, 1)
 
 
+def bind_to_gpu_numa(device_index: int) -> list:
+    """Pins the calling process to the CPU cores that are local to GPU
+    ``device_index`` (NVML's CPU affinity mask), so that pinned host buffers are
+    allocated on the GPU's own NUMA node and several ranks of one box do not
+    push their PCIe traffic through the socket interconnect.  Returns the cores
+    (empty list when NVML or the affinity call is unavailable: then nothing is
+    changed)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cores = [64 * k + b for k, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:  # noqa: BLE001 -- best effort, never fatal
+        return []
+
+
 def gather_stats(local_stats, n_total: int | None = None):
     """all_gather of per-image int64 statistics (rows) -> (n_total, k) on every
     rank.  Works on the NCCL backend (CUDA tensors) and on gloo (CPU)."""
