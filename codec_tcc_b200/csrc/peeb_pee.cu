@@ -105,9 +105,8 @@ template <> struct Row4<unsigned char> {
 };
 
 // Appendix A, embed side, for one pixel: value with a zero payload bit, whether
-// it carries a bit, whether it goes to the location map.
-__device__ __forceinline__ void classify_embed(int x, int p, int T, int maxval, int& nv0, bool& carrier,
-                                               bool& flagged) {
+// it carries a bit.
+__device__ __forceinline__ void classify_embed(int x, int p, int T, int maxval, int& nv0, bool& carrier) {
     const int e = x - p;
     const int t = e + T;
     const int v = x + e;                                            // p + 2e
@@ -116,7 +115,13 @@ __device__ __forceinline__ void classify_embed(int x, int p, int T, int maxval, 
     const int xs = x + (t < 0 ? -T : T);                            // e < -T : e >= T (when not expandable)
     const bool shifted = !expd && (unsigned)xs <= (unsigned)maxval; // x-T >= 0 / x+T <= maxval
     nv0 = carrier ? v : (shifted ? xs : x);
-    flagged = !(carrier || shifted);
+}
+// A pixel goes to the location map when it could neither be expanded nor shifted.  Shifts move by
+// T >= 1, so "value unchanged and not a carrier" says exactly that (a carrier with e = 0 also keeps
+// its value); deriving the flag this way keeps it out of the common path.
+// (T == 0 marks a border column, which is never flagged.)
+__device__ __forceinline__ bool flagged_embed(int x, int nv0, bool carrier, int T) {
+    return nv0 == x && !carrier && T != 0;
 }
 
 // Appendix A, extract side.
@@ -343,6 +348,8 @@ __device__ __forceinline__ void sweep(const PeeGeom& g, unsigned char* simg, int
             c.vb[q] = c.c0 + q + 2 <= g.w - 2;
             c.Ta[q] = c.va[q] ? T : 0;
             c.Tb[q] = c.vb[q] ? T : 0;
+            // keep them as register values: otherwise they are re-derived from c0 and w in every row step
+            asm volatile("" : "+r"(c.Ta[q]), "+r"(c.Tb[q]));
         }
         body.begin_item(c, ra);
         walk_rows<PixT>(g, simg, r_first, colour, ra, rb, c, body);
@@ -372,10 +379,10 @@ struct CountBody {
     __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
                                          unsigned char* midp) {
         int xa, pa, xb, pb, na, nb;
-        bool cara, carb, fla, flb;
+        bool cara, carb;
         predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
-        classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara, fla);
-        classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb, flb);
+        classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara);
+        classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb);
         const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
         if (c->lane == 0) {
             const int n = __popc(ma) + __popc(mb);
@@ -405,20 +412,20 @@ struct ApplyBody {
     __device__ __forceinline__ void step(int i, const Row4<PixT>& U, Row4<PixT>& M, const Row4<PixT>& D,
                                          unsigned char* midp) {
         int xa, pa, xb, pb, na, nb;
-        bool cara, carb, fla, flb;
+        bool cara, carb;
         predict_pair<PixT, Q>(*c, U, M, D, midp, g.w, xa, pa, xb, pb);
-        classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara, fla);
-        classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb, flb);
+        classify_embed(xa, pa, c->Ta[Q], g.maxval, na, cara);
+        classify_embed(xb, pb, c->Tb[Q], g.maxval, nb, carb);
         const unsigned ma = __ballot_sync(0xffffffffu, cara), mb = __ballot_sync(0xffffffffu, carb);
         const unsigned char* bp = bits + tab[idx] + __popc(ma & c->lt) + __popc(mb & c->lt);
         idx += g.S;
+        const bool fla = flagged_embed(xa, na, cara, c->Ta[Q]), flb = flagged_embed(xb, nb, carb, c->Tb[Q]);
         if (cara) { na += bp[0]; ++bp; }
         if (carb) nb += bp[0];
         if (ALLOWN || (i >= own_lo && i < own_hi)) {
             const int da = na - xa, db = nb - xb;
             st->sse += (unsigned long long)((unsigned)(da * da) + (unsigned)(db * db));
             if (fla | flb) {  // rare; only interior columns may enter the map
-                fla = fla && c->va[Q]; flb = flb && c->vb[Q];
                 unsigned* lrow = slm + (size_t)(i - lm_row0) * (g.lmpitch >> 2);
                 const int ca = c->c0 + Q, cb = ca + 2;
                 if (fla) { atomicOr(lrow + (ca >> 5), lm_bitmask(ca)); ++st->flagged; }
