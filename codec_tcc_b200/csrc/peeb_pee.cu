@@ -1176,13 +1176,14 @@ static int chunk_units(int n_units, size_t unit_bytes) {
     return (int)c;
 }
 
-int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_units, int h, int w, int itemsize,
+int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w, int itemsize,
                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
                      int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
     PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_embed_h: null pointer");
     PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_embed_h: bad sizes");
     PEEB_REQUIRE(payload_stride >= 0, "peeb_pee_embed_h: negative payload stride");
     PEEB_CUDA(cudaSetDevice(ws->device));
+    const int shared_src = shared_flags & 1, shared_pay = (shared_flags >> 1) & 1;
     const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256);
     const size_t lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
     for (int u = 0; u < n_units; ++u)
@@ -1191,15 +1192,18 @@ int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_un
     const size_t n_src = shared_src ? 1 : (size_t)n_units;
     const size_t o_marked = n_src * img_al;
     int rc = scratch_reserve(ws->stage, o_marked + (marked_host ? (size_t)n_units * img_al : 0) + 256); if (rc) return rc;
-    const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
+    const size_t n_pay = shared_pay ? 1 : (size_t)n_units;
+    const size_t o_lm = n_pay * pstride, o_info = o_lm + (size_t)n_units * lm_al;
     rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
     rc = scratch_reserve(ws->info_h, (size_t)n_units * PEEB_INFO * 8, true); if (rc) return rc;
     int64_t* info_pin = (int64_t*)ws->info_h.ptr;
     char* d1 = (char*)ws->stage.ptr;
     char* d2 = (char*)ws->stage2.ptr;
     cudaStream_t streams[2] = {ws->stream, ws->stream2};
-    if (shared_src) {
-        PEEB_CUDA(cudaMemcpyAsync(d1, src_host, img, cudaMemcpyHostToDevice, streams[0]));
+    if (shared_src || shared_pay) {
+        if (shared_src) PEEB_CUDA(cudaMemcpyAsync(d1, src_host, img, cudaMemcpyHostToDevice, streams[0]));
+        if (shared_pay && payload_stride > 0 && payload_host)
+            PEEB_CUDA(cudaMemcpyAsync(d2, payload_host, (size_t)payload_stride, cudaMemcpyHostToDevice, streams[0]));
         PEEB_CUDA(cudaEventRecord(ws->ev[1], streams[0]));
         PEEB_CUDA(cudaStreamWaitEvent(streams[1], ws->ev[1], 0));
     }
@@ -1212,12 +1216,12 @@ int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_un
         if (!shared_src)
             PEEB_CUDA(cudaMemcpy2DAsync(d1 + (size_t)u0 * img_al, img_al, (const char*)src_host + (size_t)u0 * img, img, img, n,
                                         cudaMemcpyHostToDevice, st));
-        if (payload_stride > 0 && payload_host)
+        if (!shared_pay && payload_stride > 0 && payload_host)
             PEEB_CUDA(cudaMemcpy2DAsync(d2 + (size_t)u0 * pstride, pstride, payload_host + (size_t)u0 * payload_stride,
                                         (size_t)payload_stride, (size_t)payload_stride, n, cudaMemcpyHostToDevice, st));
         rc = embed_batch_impl(ws, shared_src ? d1 : d1 + (size_t)u0 * img_al, shared_src ? 0 : (int64_t)img_al, n, h, w,
-                              itemsize, bit_depth, T + u0, n_bits + u0, (const uint8_t*)(d2 + (size_t)u0 * pstride),
-                              (int64_t)pstride, marked_host ? d1 + o_marked + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
+                              itemsize, bit_depth, T + u0, n_bits + u0, (const uint8_t*)(shared_pay ? d2 : d2 + (size_t)u0 * pstride),
+                              shared_pay ? 0 : (int64_t)pstride, marked_host ? d1 + o_marked + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
                               lm_host ? (uint8_t*)(d2 + o_lm + (size_t)u0 * lm_al) : nullptr, (int64_t)lm_al,
                               (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO, st, slot);
         if (rc) return rc;

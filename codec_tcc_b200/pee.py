@@ -19,8 +19,8 @@ from . import _cabi
 from ._cabi import INFO, INFO_KEYS, PEEB_E_CAPACITY, check, lib, ptr, workspace
 
 __all__ = [
-    "pee_embed", "pee_extract", "pee_sweep", "pee_histogram", "pee_embed_batch", "pee_extract_batch",
-    "pack_payload", "estimate_threshold",
+    "pee_embed", "pee_extract", "pee_sweep", "pee_sweep_pairs", "pee_histogram", "pee_embed_batch",
+    "pee_extract_batch", "pack_payload", "estimate_threshold",
 ]
 
 
@@ -68,13 +68,14 @@ def _info_dict(row):
 
 
 # ---------------------------------------------------------------- batches (numpy in / numpy out)
-def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=False, want_marked=True,
-                    want_lm=True, out_marked=None, out_lm=None, device=None):
+def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=False, shared_payload=False,
+                    want_marked=True, want_lm=True, out_marked=None, out_lm=None, device=None):
     """Embed into a batch of equally shaped images.
 
     imgs      (n, h, w) uint8/uint16 -- or (h, w) with ``shared_cover=True``,
               every unit then embeds into the same cover (threshold sweep)
     payloads  (n, stride) uint8, packed MSB first; row u holds unit u's bits
+              (one row of (1, stride) or (stride,) with ``shared_payload=True``)
     n_bits    (n,) ints; T scalar or (n,) ints
     -> (marked (n,h,w) or None, lm_packed (n,h,ceil(w/8)) or None, info (n, 8) int64)
     ``info[:, 7]`` is 0 or PEEB_E_CAPACITY (-2): nothing is raised here, the
@@ -98,7 +99,9 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
     for t in np.unique(Ts):
         _check_T(t, bd)
     payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
-    if payloads.ndim != 2 or payloads.shape[0] != n:
+    if shared_payload:
+        payloads = payloads.reshape(1, -1)
+    elif payloads.ndim != 2 or payloads.shape[0] != n:
         raise ValueError("payloads must be (n, stride)")
     if n and int(((nb + 7) // 8).max()) > payloads.shape[1]:
         raise ValueError("a payload row is shorter than its n_bits")
@@ -112,7 +115,8 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
         lm = out_lm if out_lm is not None else np.empty((n, h, (w + 7) // 8), np.uint8)
     info = np.zeros((n, INFO), np.int64)
     ws = workspace(device)
-    check(lib().peeb_pee_embed_h(ws.handle, ptr(imgs), 1 if shared_cover else 0, n, h, w, imgs.dtype.itemsize, bd,
+    flags = (1 if shared_cover else 0) | (2 if shared_payload else 0)
+    check(lib().peeb_pee_embed_h(ws.handle, ptr(imgs), flags, n, h, w, imgs.dtype.itemsize, bd,
                                  ptr(Ts), ptr(nb), ptr(payloads) if payloads.size else None, payloads.shape[1],
                                  ptr(marked), ptr(lm), ptr(info)), "peeb_pee_embed_h")
     return marked, lm, info
@@ -248,11 +252,8 @@ def pee_sweep(img, payload, T_values, bit_depth=None, n_bits=None, device=None):
     n = Ts.size
     if n == 0:
         return []
-    # every unit reads the same payload: stride 0 is not expressible on the host
-    # side, so the (small) payload is tiled
-    pays = np.ascontiguousarray(np.broadcast_to(packed, (n, packed.size)))
-    _, _, info = pee_embed_batch(img, pays, [n_bits] * n, Ts, bd, shared_cover=True, want_marked=False,
-                                 want_lm=False, device=device)
+    _, _, info = pee_embed_batch(img, packed, [n_bits] * n, Ts, bd, shared_cover=True, shared_payload=True,
+                                 want_marked=False, want_lm=False, device=device)
     rows = []
     for k in range(n):
         sse = int(info[k, 6])
@@ -261,3 +262,35 @@ def pee_sweep(img, payload, T_values, bit_depth=None, n_bits=None, device=None):
         rows.append({"T": int(Ts[k]), "capacity": int(info[k, 2]), "cap0": int(info[k, 3]), "cap1": int(info[k, 4]),
                      "n_flagged": int(info[k, 5]), "sse": sse, "mse": mse, "psnr": psnr})
     return rows
+
+
+def pee_sweep_pairs(imgs, payloads, image_index, T_values, bit_depth=None, n_bits=None, device=None):
+    """Capacity / distortion of explicit (image, T) pairs -- the sharded unit of the threshold sweep
+    over a series (``shard.partition_grid`` hands each rank its pairs).
+
+    imgs (n, h, w); payloads (n, stride) packed; image_index / T_values: equal-length int sequences,
+    grouped by image (any order works, consecutive equal indices share one launch).
+    -> int64 array (len(pairs), 8): the ``info`` rows {T, n_bits, capacity, cap0, cap1, n_flagged, sse, status}.
+    """
+    imgs = _cabi.as_image(imgs, "imgs")
+    if imgs.ndim != 3:
+        raise ValueError("imgs must be (n, h, w)")
+    bd = _bit_depth(imgs, bit_depth)
+    payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+    idx = np.asarray(image_index, dtype=np.int64).reshape(-1)
+    Ts = np.asarray(T_values, dtype=np.int32).reshape(-1)
+    if idx.size != Ts.size:
+        raise ValueError("image_index and T_values must have the same length")
+    out = np.zeros((idx.size, INFO), np.int64)
+    nb_all = 8 * payloads.shape[1] if n_bits is None else int(n_bits)
+    k = 0
+    while k < idx.size:
+        j = k
+        while j < idx.size and idx[j] == idx[k]:
+            j += 1
+        u = int(idx[k])
+        _, _, info = pee_embed_batch(imgs[u], payloads[u], [nb_all] * (j - k), Ts[k:j], bd, shared_cover=True,
+                                     shared_payload=True, want_marked=False, want_lm=False, device=device)
+        out[k:j] = info
+        k = j
+    return out

@@ -87,3 +87,21 @@ def gather_stats(local_stats, n_total: int | None = None):
     if n_total is not None and out.shape[0] != n_total:
         raise RuntimeError(f"gathered {out.shape[0]} rows, expected {n_total}")
     return out
+
+
+def sweep_sharded(imgs, payloads, T_values, bit_depth=None, device=None):
+    """Threshold sweep of a whole series over the ranks of one box: the (image, T) grid is split in
+    contiguous blocks, every rank embeds its pairs on its own GPU (no data-path collective) and the
+    per-pair statistics are gathered at the end.  -> (n_images * n_T, 10) int64 on every rank:
+    columns {image, T, n_bits, capacity, cap0, cap1, n_flagged, sse, status, rank}."""
+    from . import pee
+
+    rank, world = rank_world()
+    Ts = np.asarray(list(T_values), dtype=np.int32)
+    n_images = len(imgs)
+    img_idx, t_idx = partition_grid(n_images, Ts.size, world, rank)
+    info = pee.pee_sweep_pairs(imgs, payloads, img_idx, Ts[t_idx], bit_depth, device=device) if img_idx.size else \
+        np.zeros((0, 8), np.int64)
+    local = np.concatenate([img_idx[:, None], info, np.full((img_idx.size, 1), rank, np.int64)], axis=1)
+    full = gather_stats(local, n_images * Ts.size)
+    return full.cpu().numpy() if hasattr(full, "cpu") else np.asarray(full)

@@ -201,8 +201,10 @@ int peeb_pee_hist_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_
                         int itemsize, int bit_depth, uint32_t* hist, void* stream);
 
 /* host-buffer variants: contiguous batches, copies inside, synchronous.
- * payload_stride as above (host bytes); lm_stride = h*ceil(w/8). */
-int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_src, int n_units, int h, int w,
+ * payload_stride as above (host bytes); lm_stride = h*ceil(w/8).
+ * shared_flags: bit 0 = every unit embeds into the one image at src_host, bit 1 = every unit reads
+ * the one payload row at payload_host (both: the threshold sweep of one image). */
+int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w,
                      int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
                      const uint8_t* payload_host, int64_t payload_stride, void* marked_host,
                      uint8_t* lm_host, int64_t* info_host);

@@ -158,5 +158,28 @@ rows.append({"row": "a9", "kernel": "compact_{count,scan,write}", "workload": f"
              "api_mpixel_s": npx / t_api / 1e6, "cpu_oracle_ms": t_cpu * 1e3, "cpu_oracle_mpixel_s": npx / t_cpu / 1e6,
              "api": "decode_message (outputs equal the restatement)"})
 
+# ---- a10 sweep (BASELINE configs[4]): every T = 1..64 on 2048x2048 16-bit images, (image, T) = unit
+from codec_tcc_b200 import shard  # noqa: E402
+from oracle import pee_c  # noqa: E402
+
+n_sw, hs = 8, 2048
+sw_imgs = np.stack([synth_image(hs, hs, 65535, 300 + k) for k in range(n_sw)])
+sw_pays = np.random.default_rng(3).integers(0, 256, (n_sw, hs * hs // 8), dtype=np.uint8)
+Ts = list(range(1, 65))
+t_api = wall(lambda: shard.sweep_sharded(sw_imgs, sw_pays, Ts, 16), reps=2)
+table = shard.sweep_sharded(sw_imgs, sw_pays, Ts, 16)
+t0 = time.perf_counter()
+for T in (1, 16, 64):
+    _, _, i0 = pee_c.embed(sw_imgs[0], sw_pays[0], hs * hs, T, 16)
+    row = table[T - 1]
+    assert [int(v) for v in row[3:8]] == [i0[k] for k in ("capacity", "cap0", "cap1", "n_flagged", "sse")]
+t_cpu = (time.perf_counter() - t0) / 3
+units = n_sw * len(Ts)
+rows.append({"row": "a10-sweep", "kernel": "pee_count + pee_embed (statistics only, shared cover and payload)",
+             "workload": f"{n_sw} images {hs}x{hs} u16 x T=1..64 = {units} (image,T) units", "api_ms": t_api * 1e3,
+             "api_mpixel_s": units * hs * hs / t_api / 1e6, "cpu_oracle_ms": t_cpu * 1e3 * units,
+             "cpu_oracle_mpixel_s": hs * hs / t_cpu / 1e6,
+             "api": "shard.sweep_sharded -> pee.pee_sweep_pairs (numpy in, table out); CPU = C oracle, 1 core, extrapolated from 3 units; 3 rows checked equal"})
+
 print(json.dumps({"peak_gb_s": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(pp) else "fallback",
                   "cpu_cores_used_by_oracle": 1, "rows": rows}, indent=1))

@@ -197,3 +197,17 @@ def test_full_size_roundtrip_and_oracle(cfg):
         m0, lm0, i0 = PC.embed(imgs[u], pays[u], int(cap[u]), T, bd)
         assert np.array_equal(marked[u], m0) and np.array_equal(lm[u], lm0)
         assert i0["sse"] == int(info2[u, 6]) and i0["n_flagged"] == int(info2[u, 5]) and i0["cap0"] == int(info2[u, 3])
+
+
+def test_sweep_pairs_series_matches_oracle():
+    """BASELINE configs[4] in miniature: every (image, T) pair of a small series."""
+    from codec_tcc_b200 import shard
+    imgs = synth_batch(3, 96, 160, 65535, 70)
+    pays = np.random.default_rng(2).integers(0, 256, (3, 96 * 160 // 8), dtype=np.uint8)
+    Ts = [1, 8, 64, 300]
+    table = shard.sweep_sharded(imgs, pays, Ts, 16)      # world size 1 here: the whole grid
+    assert table.shape == (12, 10) and np.array_equal(table[:, 0], np.repeat(np.arange(3), 4))
+    for row in table:
+        u, T = int(row[0]), int(row[1])
+        _, _, i0 = PC.embed(imgs[u], pays[u], 96 * 160, T, 16)
+        assert [int(v) for v in row[3:8]] == [i0[k] for k in ("capacity", "cap0", "cap1", "n_flagged", "sse")]
