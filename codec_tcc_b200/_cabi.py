@@ -195,6 +195,33 @@ def workspace(device: int | None = None) -> Workspace:
     return ws
 
 
+class DeviceBuffer:
+    """Plain device memory owned by Python (cudaMalloc through the C ABI): for
+    device-resident chains of calls in the numpy API that should not bounce
+    intermediates through the host."""
+
+    def __init__(self, ws: Workspace, nbytes: int):
+        self.ws, self.nbytes = ws, int(nbytes)
+        p = _vp()
+        check(lib().peeb_dev_alloc(ws.handle, max(self.nbytes, 1), C.byref(p)), "peeb_dev_alloc")
+        self.ptr = p.value
+        self._finalizer = weakref.finalize(self, lib().peeb_dev_free, ws.handle, p)
+
+    def upload(self, arr: np.ndarray, offset: int = 0):
+        arr = np.ascontiguousarray(arr)
+        check(lib().peeb_memcpy_h2d(self.ws.handle, self.ptr + offset, arr.ctypes.data, arr.nbytes, self.ws.stream),
+              "peeb_memcpy_h2d")
+
+    def download(self, arr: np.ndarray, offset: int = 0):
+        """Copies into ``arr`` (C-contiguous) and waits for the stream."""
+        check(lib().peeb_memcpy_d2h(self.ws.handle, arr.ctypes.data, self.ptr + offset, arr.nbytes, self.ws.stream),
+              "peeb_memcpy_d2h")
+        return arr
+
+    def free(self):
+        self._finalizer()
+
+
 # ---------------------------------------------------------------- helpers
 def ptr(a) -> int:
     """Address of a numpy array's data (or pass an int through)."""

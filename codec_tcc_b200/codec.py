@@ -28,7 +28,7 @@ from ._cabi import check, lib, ptr, workspace
 __all__ = [
     "message_to_bits", "distribute_message_segments", "calculate_entropy", "calculate_mutual_information",
     "adaptive_modalities_decomposition", "merge_modalities", "extract_local_planes", "lsb_embed_multi_plane",
-    "lsb_embed_block_then_multiplane", "decode_message",
+    "lsb_embed_block_then_multiplane", "decode_message", "embed_pipeline",
 ]
 
 VERBOSE = False  # the reference prints from inside its numerics (src/codec.py:568,577-578); opt in to that
@@ -282,12 +282,13 @@ def _best_tile_offset(ref_plane, sbs, device=None):
     return _tile_argmax_from_moments(plane, sbs, sums)
 
 
-def _tile_argmax_from_moments(plane, sbs, sums):
+def _tile_argmax_from_moments(plane, sbs, sums, shape=None):
     """Host half of the tile search: var = (n*sq - s^2)/n^2 per tile is compared
     exactly (rationals).  When exact ties (or near ties) involve a tile whose
     float evaluation is not exact, the reference's float result decides, so
-    ``float(np.var(tile))`` is evaluated for those few tiles only."""
-    h, w = plane.shape
+    ``float(np.var(tile))`` is evaluated for those few tiles only.  ``plane`` may
+    be a zero-argument callable that fetches the plane only in that case."""
+    h, w = shape if shape is not None else plane.shape
     ty, tx = -(-h // sbs), -(-w // sbs)
     th = np.minimum(sbs, h - np.arange(ty) * sbs)
     tw = np.minimum(sbs, w - np.arange(tx) * sbs)
@@ -296,17 +297,21 @@ def _tile_argmax_from_moments(plane, sbs, sums):
     approx = (npx.astype(np.float64) * s2 - s1.astype(np.float64) ** 2) / (npx.astype(np.float64) ** 2)
     top = approx.max()
     short = np.flatnonzero(approx >= top - abs(top) * 1e-9 - 1e-300)
-    exact = [Fraction(int(npx[t]) * int(s2[t]) - int(s1[t]) ** 2, int(npx[t]) ** 2) for t in short]
-    best = max(exact)
+    # exact values once per distinct (n, sum, sum of squares)
+    trip, inv = np.unique(np.stack([npx[short], s1[short], s2[short]], axis=1), axis=0, return_inverse=True)
+    vals = [Fraction(int(n) * int(q) - int(a) ** 2, int(n) ** 2) for n, a, q in trip]
+    best = max(vals)
+    is_best = np.array([v == best for v in vals])[inv.reshape(-1)]
     binary = bool(np.all(s1[short] == s2[short]))  # 0/1 tiles: sum == sum of squares
-    cands = [int(t) for t, v in zip(short, exact) if v == best]
-    if binary and len(cands) == len(short) and all(_dyadic_mean(int(s1[t]), int(npx[t])) for t in cands):
-        pick = cands[0]
+    exact_float = all(_dyadic_mean(int(a), int(n)) for (n, a, q), v in zip(trip, vals) if v == best)
+    if binary and bool(is_best.all()) and exact_float:
+        pick = int(short[0])
     else:
+        arr = plane() if callable(plane) else plane
         pick, best_f = None, -1.0
         for t in (int(v) for v in short):  # raster order over the short list
             y, x = (t // tx) * sbs, (t % tx) * sbs
-            f = float(np.var(plane[y:y + sbs, x:x + sbs]))
+            f = float(np.var(arr[y:y + sbs, x:x + sbs]))
             if f > best_f:
                 best_f, pick = f, t
     return (pick // tx) * sbs * w + (pick % tx) * sbs
@@ -410,3 +415,93 @@ def decode_message(stego_planes, bitmaps, metadata):
     nbytes = allbits.size // 8
     raw = np.packbits(allbits[:nbytes * 8]).tobytes()
     return raw.decode("utf-8", errors="replace")
+
+
+# ------------------------------------------------------------------ the reference's encode flow, device resident
+def embed_pipeline(image_array, message_bits, beta=0.8, search_block_size=16, align_across_planes=False,
+                   hybrid=True, nbits=None, device=None):
+    """Steps 3-5 of the reference's ``main()`` (src/codec.py:868-880) in one call:
+    ``adaptive_modalities_decomposition`` -> ``lsb_embed_block_then_multiplane`` (or
+    ``lsb_embed_multi_plane`` with ``hybrid=False``) -> ``merge_modalities``, with the bit planes
+    living only in device memory: one upload of the image, one download of the stego image and the
+    uint8 bitmaps.  Results are identical to chaining the three functions.
+
+    -> ``(stego_image, bitmaps (s, h, w) uint8, meta)`` with ``meta = {'s', 'segments_lengths',
+    'segments_indices', 'total_used', 'start_offset'}`` (what ``create_header`` needs, :895-905).
+    """
+    img = _cabi.as_image(image_array, "image_array")
+    if img.ndim != 2:
+        raise ValueError("A imagem deve ser 2D (grayscale).")  # src/codec.py:34
+    nb = img.dtype.itemsize * 8 if nbits is None else int(nbits)
+    if nb < 1 or nb > 16:
+        raise ValueError("nbits must be 1..16")
+    h, w = img.shape
+    npx, item = img.size, img.dtype.itemsize
+    L, ws = lib(), workspace(device)
+    st = ws.stream
+    d_img = _cabi.DeviceBuffer(ws, npx * item)
+    d_hist = _cabi.DeviceBuffer(ws, 65536 * 4 + 16 * 8)
+    d_planes = _cabi.DeviceBuffer(ws, nb * npx * item)
+    d_img.upload(img)
+    # (1) split point from the device histogram (float64 sums on the host, numpy's order)
+    check(L.peeb_hist_planes(ws.handle, d_img.ptr, npx, item, d_hist.ptr, d_hist.ptr + 65536 * 4, st), "peeb_hist_planes")
+    hist = d_hist.download(np.zeros(65536, np.uint32))
+    ones = d_hist.download(np.zeros(16, np.uint64), 65536 * 4).astype(np.int64)
+    nbins = 256 if item == 1 else 65536
+    hist = hist[:nbins].astype(np.int64)
+    total_info = _entropy_from_counts(hist, npx)
+    acc, s = 0.0, 1
+    for i in range(nb):
+        acc += _plane_information(hist, int(ones[i]), npx, i, nbins) if i < 8 * item else 0.0
+        if acc >= beta * total_info:
+            s = i + 1
+            break
+    # (2) all planes on the device; the first s are the local ones
+    check(L.peeb_planes_unpack(ws.handle, d_img.ptr, npx, item, 0, nb, d_planes.ptr, st), "peeb_planes_unpack")
+    # (3) start offset from the tile moments of local plane 0
+    start = 0
+    if hybrid:
+        sbs = int(search_block_size)
+        if sbs < 1:
+            raise ValueError("search_block_size must be positive")
+        ntiles = (-(-h // sbs)) * (-(-w // sbs))
+        d_sums = _cabi.DeviceBuffer(ws, ntiles * 16)
+        check(L.peeb_tile_moments(ws.handle, d_planes.ptr, h, w, item, sbs, d_sums.ptr, st), "peeb_tile_moments")
+        sums = d_sums.download(np.zeros((ntiles, 2), np.int64))
+        start = _tile_argmax_from_moments(lambda: d_planes.download(np.empty((h, w), img.dtype)), sbs, sums, (h, w))
+        d_sums.free()
+    # (4) segment plan + embed into the local planes (in a second buffer), bitmaps beside
+    segments, sizes, order = distribute_message_segments([None] * s, message_bits)
+    starts, lens, offs = np.zeros(s, np.int64), np.zeros(s, np.int64), np.zeros(s, np.int64)
+    chunks, at, used, cur = [], 0, 0, start
+    for seg, plane_idx in zip(segments, order):
+        n_seg = min(len(seg), npx)
+        packed = _bits_to_packed(seg[:n_seg])
+        starts[plane_idx], lens[plane_idx], offs[plane_idx] = cur, n_seg, 8 * at
+        chunks.append(packed)
+        at += packed.size
+        used += n_seg
+        if hybrid and not align_across_planes and npx:
+            cur = (cur + n_seg) % npx
+    payload = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+    d_pay = _cabi.DeviceBuffer(ws, payload.size + 16)
+    if payload.size:
+        d_pay.upload(payload)
+    d_out = _cabi.DeviceBuffer(ws, nb * npx * item)   # stego planes (local) followed by the global planes
+    d_bm = _cabi.DeviceBuffer(ws, s * npx)
+    check(L.peeb_lsb_embed(ws.handle, d_planes.ptr, npx, item, s, ptr(starts), ptr(lens), ptr(offs), d_pay.ptr,
+                           8 * payload.size, d_out.ptr, d_bm.ptr, st), "peeb_lsb_embed")
+    # (5) merge: local stego planes + untouched global planes -> stego image
+    if nb > s:
+        check(L.peeb_planes_unpack(ws.handle, d_img.ptr, npx, item, s, nb - s, d_out.ptr + s * npx * item, st),
+              "peeb_planes_unpack")
+    out_dtype = np.uint16 if nb > 8 else np.uint8
+    d_stego = _cabi.DeviceBuffer(ws, npx * out_dtype().itemsize)
+    check(L.peeb_planes_pack(ws.handle, d_out.ptr, npx, item, nb, d_stego.ptr, st), "peeb_planes_pack")
+    stego = d_stego.download(np.empty((h, w), out_dtype))
+    bitmaps = d_bm.download(np.empty((s, h, w), np.uint8))
+    for b in (d_img, d_hist, d_planes, d_pay, d_out, d_bm, d_stego):
+        b.free()
+    meta = {"s": s, "segments_lengths": sizes if hybrid else [int(v) for v in lens],
+            "segments_indices": order, "total_used": used, "start_offset": int(start)}
+    return stego, bitmaps, meta

@@ -148,3 +148,20 @@ def test_normalisation_branch_and_mixed_inputs():
     assert set(res) >= {"mse", "psnr", "ssim", "diferenca_media", "diferenca_max", "percentual_mudanca"}
     with pytest.raises(TypeError):
         an.calcular_mse(a.astype(np.float64) + 0.5, b)
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_embed_pipeline_equals_chained_reference_flow(golden, golden_images, name):
+    """The device-resident encode flow (src/codec.py:868-880 in one call) against the golden
+    vectors of the chained reference functions."""
+    img = golden_images[name]
+    for case in golden["images"][name]["lsb_cases"]:
+        bits = GC.case_bits(case, img, codec)
+        stego, bitmaps, meta = codec.embed_pipeline(img, bits, beta=case["beta"], search_block_size=case["sbs"],
+                                                    align_across_planes=case["align"],
+                                                    hybrid=case["embedder"] == "hybrid")
+        assert meta["s"] == case["s"] and meta["total_used"] == case["total_used"]
+        assert [int(v) for v in meta["segments_lengths"]] == case["segments_lengths"]
+        assert [int(v) for v in meta["segments_indices"]] == case["segment_indices"]
+        assert str(stego.dtype) == case["stego_dtype"] and GC.sha(stego) == case["stego_sha"]
+        assert bitmaps.dtype == np.uint8 and GC.sha(bitmaps) == case["bitmaps_sha"]
