@@ -815,8 +815,14 @@ static int make_geom(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int
     return PEEB_OK;
 }
 
+// first-generation kernels stay selectable for A/B runs (PEEB_PEE_V1=1)
+static bool use_v1() {
+    static const bool v = getenv("PEEB_PEE_V1") != nullptr;
+    return v;
+}
+
 // upload T / n_bits (host arrays) into table set `slot` of the workspace; returns device pointers
-static int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, const int64_t* n_bits,
+int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, const int64_t* n_bits,
                               int bit_depth, size_t extra_bytes, cudaStream_t st, int** dT, unsigned** dN,
                               char** extra) {
     const size_t head = align_up((size_t)n_units * 8, 256);
@@ -885,6 +891,9 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     PEEB_REQUIRE(n_units >= 1, "peeb_pee_embed_batch: n_units must be >= 1");
     PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_embed_batch: payload must be 4-byte aligned");
     PEEB_CUDA(cudaSetDevice(ws->device));
+    if (h >= 3 && w >= 3 && !use_v1())
+        return embed_batch_impl2(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, T, n_bits, payload, payload_stride,
+                                 marked, marked_stride, lm, lm_stride, info, st, slot);
     PeeGeom g;
     int rc = make_geom(ws, h, w, itemsize, bit_depth, 1, g);
     if (rc) return rc;
@@ -940,6 +949,17 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
     PEEB_REQUIRE(n_units >= 1 && n_units <= 65535, "peeb_pee_extract_batch: n_units must be 1..65535");
     PEEB_REQUIRE(((uintptr_t)payload_out & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_extract_batch: payload_out must be 4-byte aligned");
     PEEB_CUDA(cudaSetDevice(ws->device));
+    for (int u = 0; u < n_units; ++u) {
+        const size_t pb = peeb_payload_bytes(n_bits[u]);
+        PEEB_REQUIRE(n_units == 1 || (int64_t)pb <= payload_stride, "peeb_pee_extract_batch: payload_stride too small for unit %d", u);
+    }
+    if (h >= 3 && w >= 3 && !use_v1()) {
+        // zero every unit's output words (the gather kernel ORs the boundary words in)
+        if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
+        else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
+        return extract_batch_impl2(ws, marked, marked_stride, n_units, h, w, itemsize, bit_depth, T, n_bits, lm, lm_stride,
+                                   payload_out, payload_stride, recovered, recovered_stride, info, st, slot);
+    }
     PeeGeom g;
     int rc = make_geom(ws, h, w, itemsize, bit_depth, 2, g);
     if (rc) return rc;

@@ -119,4 +119,16 @@ __device__ __forceinline__ void expand_payload(const unsigned* __restrict__ pay,
     }
 }
 
+// host side shared by the two translation units
+int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, const int64_t* n_bits, int bit_depth,
+                       size_t extra_bytes, cudaStream_t st, int** dT, unsigned** dN, char** extra);
+int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
+                      int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
+                      int64_t* info, cudaStream_t st, int slot);
+int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
+                        int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm,
+                        int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,
+                        int64_t recovered_stride, int64_t* info, cudaStream_t st, int slot);
+
 }  // namespace peeb

@@ -1,0 +1,1195 @@
+// Row a10, second-generation kernels: the "row pair" layout.
+//
+// The first-generation kernels (peeb_pee.cu) walk 128-column strips downwards and rank carriers
+// with warp ballots; ncu showed them bound by the integer ALU pipe at ~60 executed instructions per
+// colour pixel.  These kernels cut that to about a third:
+//
+//   * a LANE owns two adjacent image rows of a cell (<= 64 columns) and walks them left to right in
+//     16-byte steps, so its carriers come in raster order: the rank of a carrier inside a
+//     (row, cell) is a lane-local running count, the payload bits of a cell are a 32-bit window in
+//     a register (no ballots, no POPC, no per-bit shared-memory bytes);
+//   * the two rows of a lane have opposite colour parity, so the code of a step is static; rows
+//     above/below come from shared memory (4 x LDS.128 per 2 row-steps);
+//   * the rhombus predictor never unpacks pixels: 4x - (N+S+W+E) is accumulated straight from the
+//     packed words with IDP.2A / IDP.4A (integer dot product with byte weights, FMA pipe), and with
+//     the accumulator preloaded with 3 + 4T one arithmetic shift gives e + T
+//     (e = x - floor(S/4) = ceil((4x - S)/4));
+//   * classification is branch-free: delta = clamp(e + T, 0, 2T) - T covers expand / shift+ / shift-
+//     (SURVEY Appendix A), one unsigned compare gives the overflow flag for all three classes;
+//   * rows whose pixels must not change (outside the pass, outside the image interior) run with
+//     T = 0, which makes every pixel a shift by 0: no special cases in the step code.
+//
+// Band / look-back / staging structure is unchanged: one CTA per band of R rows (+2 halo rows per
+// side), TMA bulk row copies into a padded, bank-conflict-free shared layout, pass-0 counts from a
+// separate count kernel, decoupled look-back for pass 1, per-band bit staging + gather for extract.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <type_traits>
+
+#include "peeb_common.cuh"
+#include "peeb_pee.cuh"
+
+namespace peeb {
+
+#ifdef PEEB_PHASE_TIMING
+// development aid: per-phase clock64 totals of thread 0 of every embed CTA (see scripts/phase_timing.py)
+__device__ unsigned long long g_phase[16];
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
+#define PHASE_INIT long long _t0 = clock64()
+#else
+#define PHASE_MARK(i) do {} while (0)
+#define PHASE_INIT do {} while (0)
+#endif
+
+struct Geom2 {
+    int h, w, itemsize, maxval;
+    int R, nb;              // band height, bands per unit
+    int rowbytes, pitch;    // pitch = align_up(rowbytes, 128) + 16: consecutive rows fall 16 bytes apart in the banks
+    int bulk;
+    int cws;                // 16-byte steps per cell
+    int CW;                 // cell width in pixels (<= 64, so a cell holds <= 32 carriers of one colour)
+    int ncol;               // cells per row
+    int rpw, rpw_log2;      // row pairs per warp item (power of two); 32/rpw cells side by side
+    int lmw, lmpitch;       // location map: global row bytes, shared row pitch (bytes, multiple of 4)
+    int bandwords;          // extract staging: 32-bit words per (unit, pass, band)
+    int threads;
+    int minb;               // CTAs per SM the launch is sized for
+};
+
+struct Smem2 {
+    size_t img, lm, tab, misc, bar, pw, tn0, tw0, tw1, stream, total;
+};
+__host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 embed, 2 extract*/) {
+    Smem2 L{};
+    size_t o = 0;
+    L.img = o; o += align_up((size_t)16 + (size_t)(g.R + 5) * g.pitch + 192, 16);
+    L.lm = o; o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
+    L.tab = o; o += align_up((size_t)(g.R + 2) * g.ncol * sizeof(int), 16);
+    L.misc = o; o += 64 * sizeof(int);
+    L.bar = o; o += 16;
+    L.pw = L.tn0 = L.tw0 = L.tw1 = L.stream = o;
+    if (kind == 1) {
+        L.pw = o; o += align_up(((size_t)(g.R + 2) * ((g.w + 1) / 2) / 32 + 8) * sizeof(unsigned), 16);
+    } else if (kind == 2) {
+        const size_t cells = (size_t)g.R * g.ncol;
+        L.tn0 = o; o += align_up(cells * sizeof(int), 16);
+        L.tw0 = o; o += align_up(cells * sizeof(unsigned), 16);
+        L.tw1 = o; o += align_up(cells * sizeof(unsigned), 16);
+        L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
+    }
+    L.total = o;
+    return L;
+}
+
+// byte offset of shared row `rs` (0 = image row r_first); every second group of 8 rows is shifted
+// by 16 bytes so that lanes two rows apart (the row-pair layout) still hit distinct banks
+__device__ __forceinline__ int row_off(const Geom2& g, int rs) { return 16 + rs * g.pitch + ((rs & 8) << 1); }
+
+// ------------------------------------------------------------------ band staging
+// Staging is split in two so that table loads and other set-up overlap the copy: issue_rows2 starts
+// it (TMA bulk row copies by the lanes of warp 0, or plain loads), wait_rows2 makes the rows visible.
+template <typename PixT>
+__device__ __forceinline__ void issue_rows2(const Geom2& g, const unsigned char* usrc, unsigned char* simg, int r_first,
+                                            int lo, int hi, uint64_t* bar) {
+    if (hi <= lo) return;
+    if (g.bulk) {
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)(hi - lo) * (unsigned)g.rowbytes);
+            __syncwarp();
+            for (int r = lo + (int)threadIdx.x; r < hi; r += 32)
+                bulk_g2s(simg + row_off(g, r - r_first), usrc + (size_t)r * g.rowbytes, (unsigned)g.rowbytes, bar);
+        }
+    } else {
+        for (int r = lo + (int)(threadIdx.x >> 5); r < hi; r += (int)(blockDim.x >> 5)) {
+            const PixT* s = reinterpret_cast<const PixT*>(usrc + (size_t)r * g.rowbytes);
+            PixT* d = reinterpret_cast<PixT*>(simg + row_off(g, r - r_first));
+            for (int c = threadIdx.x & 31; c < g.w; c += 32) d[c] = s[c];
+        }
+    }
+}
+__device__ __forceinline__ void wait_rows2(const Geom2& g, int lo, int hi, uint64_t* bar) {
+    if (g.bulk && hi > lo) mbar_wait(bar, 0);
+    __syncthreads();
+}
+template <typename PixT>
+__device__ __forceinline__ void load_rows2(const Geom2& g, const unsigned char* usrc, unsigned char* simg, int r_first,
+                                           int lo, int hi, uint64_t* bar) {
+    issue_rows2<PixT>(g, usrc, simg, r_first, lo, hi, bar);
+    wait_rows2(g, lo, hi, bar);
+}
+
+// Exclusive scan of data[0..n) in place by the whole block with ONE internal barrier: every thread
+// owns a run of consecutive entries.  Callers synchronise before (data complete) and after (offsets
+// visible).  Returns the total to every thread.  warp_sums: >= 33 ints of shared memory.
+__device__ __forceinline__ int block_scan_runs(int* data, int n, int* warp_sums) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int sum = 0;
+    for (int k = lo; k < hi; ++k) sum += data[k];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int k = 0; k < nwarps; ++k) {
+        const int ws = warp_sums[k];
+        if (k < warp) before += ws;
+        total += ws;
+    }
+    int run = before + incl - sum;
+    for (int k = lo; k < hi; ++k) {
+        const int v = data[k];
+        data[k] = run;
+        run += v;
+    }
+    return total;
+}
+
+// callers synchronise the block before (all pixel writes done)
+template <typename PixT>
+__device__ __forceinline__ void store_rows2(const Geom2& g, unsigned char* udst, const unsigned char* simg, int r_first,
+                                            int lo, int hi) {
+    if (hi <= lo) return;
+    if (g.bulk) {
+        if (threadIdx.x < 32) {
+            fence_async_smem();
+            for (int r = lo + (int)threadIdx.x; r < hi; r += 32)
+                bulk_s2g(udst + (size_t)r * g.rowbytes, simg + row_off(g, r - r_first), (unsigned)g.rowbytes);
+            bulk_commit();
+            bulk_wait_read0();
+        }
+    } else {
+        for (int r = lo + (int)(threadIdx.x >> 5); r < hi; r += (int)(blockDim.x >> 5)) {
+            const PixT* s = reinterpret_cast<const PixT*>(simg + row_off(g, r - r_first));
+            PixT* d = reinterpret_cast<PixT*>(udst + (size_t)r * g.rowbytes);
+            for (int c = threadIdx.x & 31; c < g.w; c += 32) d[c] = s[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ packed-pixel arithmetic
+__device__ __forceinline__ int idp2(unsigned a, unsigned b, int c) {  // c + a.lo16*b.s8[0] + a.hi16*b.s8[1]
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int idp4(unsigned a, unsigned b, int c) {  // c + sum a.u8[k]*b.s8[k]
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+template <int J> __device__ __forceinline__ unsigned comp(const uint4& v) {
+    return J == 0 ? v.x : J == 1 ? v.y : J == 2 ? v.z : v.w;
+}
+template <int J> __device__ __forceinline__ unsigned& compr(uint4& v) {
+    if constexpr (J == 0) return v.x; else if constexpr (J == 1) return v.y; else if constexpr (J == 2) return v.z; else return v.w;
+}
+// word J of the step, or the last word of the previous step (J = -1) / first of the next (J = 4)
+template <int J> __device__ __forceinline__ unsigned compx(const uint4& v, unsigned prev, unsigned next) {
+    if constexpr (J < 0) return prev; else if constexpr (J > 3) return next; else return comp<J>(v);
+}
+
+// A 16-byte step holds NS colour pixels of a row; slot S sits at column 2S + Q of the step, Q the
+// column parity of the colour in that row.  qsum = init + 4x - (N + S + W + E) from packed words.
+template <typename PixT> struct PixOps;
+template <> struct PixOps<unsigned short> {
+    static constexpr int ITEM = 2, NS = 4, PXS = 8;
+    template <int Q, int S>
+    static __device__ __forceinline__ int qsum(const uint4& M, unsigned prev, unsigned next, const uint4& U,
+                                               const uint4& D, int init) {
+        if constexpr (Q == 0) {  // pixel = low half of word S: W = high half of word S-1, E = high half of word S
+            int q = idp2(comp<S>(D), 0x00ffu, init);
+            q = idp2(comp<S>(U), 0x00ffu, q);
+            q = idp2(compx<S - 1>(M, prev, next), 0xff00u, q);
+            return idp2(comp<S>(M), 0xff04u, q);
+        } else {                 // pixel = high half of word S: W = low half of word S, E = low half of word S+1
+            int q = idp2(comp<S>(D), 0xff00u, init);
+            q = idp2(comp<S>(U), 0xff00u, q);
+            q = idp2(compx<S + 1>(M, prev, next), 0x00ffu, q);
+            return idp2(comp<S>(M), 0x04ffu, q);
+        }
+    }
+    template <int Q, int S> static __device__ __forceinline__ int getx(const uint4& M) {
+        return idp2(comp<S>(M), Q == 0 ? 0x0001u : 0x0100u, 0);
+    }
+    template <int Q, int S> static __device__ __forceinline__ void setx(uint4& M, int v) {
+        unsigned& wv = compr<S>(M);
+        wv = __byte_perm(wv, (unsigned)v, Q == 0 ? 0x3254 : 0x5410);
+    }
+};
+template <> struct PixOps<unsigned char> {
+    static constexpr int ITEM = 1, NS = 8, PXS = 16;
+    static constexpr __host__ __device__ unsigned wcentre(int B) {
+        unsigned wv = 4u << (8 * B);
+        if (B > 0) wv |= 0xffu << (8 * (B - 1));
+        if (B < 3) wv |= 0xffu << (8 * (B + 1));
+        return wv;
+    }
+    template <int Q, int S>
+    static __device__ __forceinline__ int qsum(const uint4& M, unsigned prev, unsigned next, const uint4& U,
+                                               const uint4& D, int init) {
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;  // word, byte inside the word
+        constexpr unsigned wv = 0xffu << (8 * B);
+        int q = idp4(comp<J>(D), wv, init);
+        q = idp4(comp<J>(U), wv, q);
+        if constexpr (B == 0) q = idp4(compx<J - 1>(M, prev, next), 0xff000000u, q);
+        if constexpr (B == 3) q = idp4(compx<J + 1>(M, prev, next), 0x000000ffu, q);
+        return idp4(comp<J>(M), wcentre(B), q);
+    }
+    template <int Q, int S> static __device__ __forceinline__ int getx(const uint4& M) {
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;
+        return idp4(comp<J>(M), 1u << (8 * B), 0);
+    }
+    template <int Q, int S> static __device__ __forceinline__ void setx(uint4& M, int v) {
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;
+        constexpr unsigned sel = B == 0 ? 0x3214u : B == 1 ? 0x3240u : B == 2 ? 0x3410u : 0x4210u;
+        unsigned& wv = compr<J>(M);
+        wv = __byte_perm(wv, (unsigned)v, sel);
+    }
+};
+
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+__device__ __forceinline__ uint4 lds128(const unsigned char* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void sts128(unsigned char* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// per-row constants of the embed side (T = 0: every pixel is "shifted by 0", i.e. left alone)
+struct KE {
+    int init, T8, T2, negT, T;
+};
+__device__ __forceinline__ KE make_ke(int T) { return KE{3 + 4 * T, 8 * T, 2 * T, -T, T}; }
+// extract side
+struct KX {
+    int init, T16, T2, T;
+};
+__device__ __forceinline__ KX make_kx(int T) { return KX{3 + 8 * T, 16 * T, 2 * T, T}; }
+
+struct Stats2 {
+    long long sse = 0;
+    unsigned flagged = 0;
+};
+
+// ---- predicated tails (explicit PTX: the compiler turns these into select chains otherwise) ----
+// embed: a carrier (q < 8T unsigned, i.e. -T <= e < T; range already checked) takes the next payload bit
+__device__ __forceinline__ void take_bit(int& nv, unsigned& W, int q, int T8) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 b;\n\t"
+        "setp.lt.u32 p, %2, %3;\n\t"
+        "shr.u32 b, %1, 31;\n\t"
+        "@p add.s32 %0, %0, b;\n\t"
+        "@p shl.b32 %1, %1, 1;\n\t}"
+        : "+r"(nv), "+r"(W) : "r"(q), "r"(T8));
+}
+// count: carrier <=> q < 8T and 0 <= v < maxval (v = x + e)
+__device__ __forceinline__ void count_if(int& n, int q, int T8, int v, int maxval) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.lt.u32 p, %1, %2;\n\t"
+        "setp.lt.and.u32 p, %3, %4, p;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t}"
+        : "+r"(n) : "r"(q), "r"(T8), "r"(v), "r"(maxval));
+}
+// extract: a carrier (q < 16T, i.e. -2T <= e' < 2T) appends bit 0 of e' + 2T = bit 2 of q to W
+__device__ __forceinline__ void collect_bit(unsigned& W, int& n, int q, int T16) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+        "setp.lt.u32 p, %2, %3;\n\t"
+        "shl.b32 t, %2, 29;\n\t"
+        "@p shf.l.wrap.b32 %0, t, %0, 1;\n\t"
+        "@p add.s32 %1, %1, 1;\n\t}"
+        : "+r"(W), "+r"(n) : "r"(q), "r"(T16));
+}
+
+// ------------------------------------------------------------------ the sweep
+// Rows [row_lo, row_hi) of the staged band, colour with column parity QA in row row_lo.  A warp
+// item = (group of rpw row pairs) x (32/rpw neighbouring cells); lane -> (row pair, cell).
+template <typename PixT, int QA, class Body>
+__device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int r_first, int row_lo, int row_hi, int T,
+                                       Body& body) {
+    using P = PixOps<PixT>;
+    if (row_hi <= row_lo) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int rp = lane & (g.rpw - 1), part = lane >> g.rpw_log2, parts = 32 >> g.rpw_log2;
+    const int npairs = (row_hi - row_lo + 1) >> 1;
+    const int ngroups = (npairs + g.rpw - 1) >> g.rpw_log2;
+    const int nic = (g.ncol + parts - 1) / parts;
+    const int nitems = ngroups * nic;
+    for (int item = warp; item < nitems; item += nwarps) {
+        const int grp = item / nic, ic = item - grp * nic;
+        int rowa = row_lo + 2 * (grp * g.rpw + rp);
+        int cell = ic * parts + part;
+        const bool colv = cell < g.ncol;
+        const bool acta = colv && rowa < row_hi, actb = colv && rowa + 1 < row_hi;
+        if (rowa >= row_hi) rowa = row_lo;  // idle lane: any staged row will do, nothing is written
+        if (!colv) cell = g.ncol - 1;
+        const int c0 = cell * g.CW;
+        const int rs = rowa - r_first;
+        const unsigned char* pu = simg + row_off(g, rs - 1) + c0 * P::ITEM;
+        unsigned char* pa = simg + row_off(g, rs) + c0 * P::ITEM;
+        unsigned char* pb = simg + row_off(g, rs + 1) + c0 * P::ITEM;
+        const unsigned char* pd = simg + row_off(g, rs + 2) + c0 * P::ITEM;
+        body.begin(rowa, cell, acta, actb, T);
+        // the row whose colour sits on even columns looks one word back, the other one word ahead
+        unsigned prev = *reinterpret_cast<const unsigned*>((QA == 0 ? pa : pb) - 4);
+#ifdef PEEB_PREFETCH  // measured slower on B200 at 3 CTAs/SM (register pressure); kept for experiments
+        // the words of step s+1 are fetched while step s computes (reads run at most one step past the
+        // cell; the staging buffer has slack for that)
+        uint4 U = lds128(pu), D = lds128(pd), A = lds128(pa), B = lds128(pb);
+        unsigned next = *reinterpret_cast<const unsigned*>((QA == 0 ? pb : pa) + 16);
+        for (int s = 0; s < g.cws; ++s) {
+            const int c = c0 + s * P::PXS;
+            const uint4 nU = lds128(pu + 16), nD = lds128(pd + 16), nA = lds128(pa + 16), nB = lds128(pb + 16);
+            const unsigned nnext = *reinterpret_cast<const unsigned*>((QA == 0 ? pb : pa) + 32);
+            const unsigned newprev = QA == 0 ? A.w : B.w;
+            const bool special = __any_sync(0xffffffffu, body.special(c, s));
+            body.template step<QA>(c, s, special, U, A, B, D, prev, next, pa, pb);
+            prev = newprev;
+            U = nU; D = nD; A = nA; B = nB; next = nnext;
+            pu += 16; pa += 16; pb += 16; pd += 16;
+        }
+#else
+        for (int s = 0; s < g.cws; ++s) {
+            const int c = c0 + s * P::PXS;
+            const uint4 U = lds128(pu), D = lds128(pd);
+            uint4 A = lds128(pa), B = lds128(pb);
+            const unsigned next = *reinterpret_cast<const unsigned*>((QA == 0 ? pb : pa) + 16);
+            const unsigned newprev = QA == 0 ? A.w : B.w;
+            // steps that touch a border column (or, for extract, location-map bits) take the generic code
+            const bool special = __any_sync(0xffffffffu, body.special(c, s));
+            body.template step<QA>(c, s, special, U, A, B, D, prev, next, pa, pb);
+            prev = newprev;
+            pu += 16; pa += 16; pb += 16; pd += 16;
+        }
+#endif
+        body.end();
+    }
+}
+template <typename PixT, class Body>
+__device__ __forceinline__ void sweep2_colour(const Geom2& g, unsigned char* simg, int r_first, int colour, int row_lo,
+                                              int row_hi, int T, Body& body) {
+    if ((row_lo + colour) & 1) sweep2<PixT, 1>(g, simg, r_first, row_lo, row_hi, T, body);
+    else sweep2<PixT, 0>(g, simg, r_first, row_lo, row_hi, T, body);
+}
+
+__device__ __forceinline__ bool edge_step(const Geom2& g, int c, int pxs) { return c == 0 || c + pxs > g.w - 1; }
+
+// ---- count carriers of one colour per (row, cell) ----------------------------------------------
+template <typename PixT, bool GLOBAL>
+struct Count2 {
+    using P = PixOps<PixT>;
+    const Geom2& g;
+    int row0;               // image row of table row 0
+    unsigned char* rowcnt;  // GLOBAL: bytes in global memory, [row * ncol + cell]
+    int* tab;               // !GLOBAL: shared table
+    int total;              // GLOBAL: carriers seen by this lane
+    KE ka, kb;
+    int na, nb, ia;
+    bool acta, actb;
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
+        acta = a; actb = b;
+        ka = make_ke(a ? T : 0); kb = make_ke(b ? T : 0);
+        na = nb = 0;
+        ia = (rowa - row0) * g.ncol + cell;
+    }
+    __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
+    template <int Q, bool EDGE>
+    __device__ __forceinline__ void row(const uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
+                                        const KE& k, int c, int& n) {
+        static_for<0, P::NS>([&](auto Sc) {
+            constexpr int S = decltype(Sc)::value;
+            KE kk = k;
+            if (EDGE) {
+                const int col = c + 2 * S + Q;
+                kk = make_ke((col >= 1 && col <= g.w - 2) ? k.T : 0);
+            }
+            const int q = P::template qsum<Q, S>(M, prev, next, U, D, kk.init);
+            const int x = P::template getx<Q, S>(M);
+            count_if(n, q, kk.T8, x + (q >> 2) + kk.negT, g.maxval);
+        });
+    }
+    template <int QA>
+    __device__ __forceinline__ void step(int c, int, bool special, const uint4& U, uint4& A, uint4& B, const uint4& D,
+                                         unsigned prev, unsigned next, unsigned char*, unsigned char*) {
+        if (special) {
+            row<QA, true>(A, prev, next, U, B, ka, c, na);
+            row<1 - QA, true>(B, prev, next, A, D, kb, c, nb);
+        } else {
+            row<QA, false>(A, prev, next, U, B, ka, c, na);
+            row<1 - QA, false>(B, prev, next, A, D, kb, c, nb);
+        }
+    }
+    __device__ __forceinline__ void end() {
+        if (GLOBAL) {
+            if (acta) rowcnt[ia] = (unsigned char)na;
+            if (actb) rowcnt[ia + g.ncol] = (unsigned char)nb;
+            total += na + nb;  // inactive rows run with T = 0 and count nothing
+        } else {
+            if (acta) tab[ia] = na;
+            if (actb) tab[ia + g.ncol] = nb;
+        }
+    }
+};
+
+// ---- full apply of one colour ---------------------------------------------------------------------
+// tab[(row-row0)*ncol + cell] = offset of the cell's first carrier in the band's bit window `pw`
+// (32-bit words, stream bit k at bit 31-(k&31) of word k>>5), counted from bit `bitbase`.
+// A step first runs the fast code, which assumes that no pixel over/underflows (every expandable
+// pixel is a carrier, nothing goes to the location map) and only watches for a value leaving
+// [0, maxval); if any lane of the warp sees one, or the step touches a border column, the step is
+// redone from the saved words by the generic code.
+template <typename PixT>
+struct Apply2 {
+    using P = PixOps<PixT>;
+    const Geom2& g;
+    int row0, own_lo, own_hi;
+    const int* tab;
+    const unsigned* pw;
+    int bitbase;
+    unsigned* slm;  // location-map rows of the band (row r0 first), lmpitch bytes apart
+    int lm_row0;
+    Stats2* st;
+    KE ka, kb;
+    unsigned Wa, Wb;
+    long long ssea, sseb;
+    bool sta, stb, owna, ownb;
+    unsigned* lma;
+    __device__ __forceinline__ unsigned window(int o) const {
+        const int p = bitbase + o;
+        return __funnelshift_l(pw[(p >> 5) + 1], pw[p >> 5], p & 31);
+    }
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
+        sta = a; stb = b;
+        ka = make_ke(a ? T : 0); kb = make_ke(b ? T : 0);
+        const int ia = (rowa - row0) * g.ncol + cell;
+        Wa = a ? window(tab[ia]) : 0u;
+        Wb = b ? window(tab[ia + g.ncol]) : 0u;
+        owna = a && rowa >= own_lo && rowa < own_hi;
+        ownb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
+        ssea = sseb = 0;
+        lma = slm + (rowa - lm_row0) * (g.lmpitch >> 2);
+    }
+    __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
+    template <int Q>
+    __device__ __forceinline__ bool fast(uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
+                                         const KE& k, unsigned& W, long long& sse) {
+        bool bad = false;
+        static_for<0, P::NS>([&](auto Sc) {
+            constexpr int S = decltype(Sc)::value;
+            const int q = P::template qsum<Q, S>(M, prev, next, U, D, k.init);
+            const int x = P::template getx<Q, S>(M);
+            const int cc = max(min(q >> 2, k.T2), 0);               // clamp(e + T, 0, 2T)
+            int nv = x + cc + k.negT;                               // x + e | x + T | x - T
+            bad |= (unsigned)nv >= (unsigned)g.maxval;              // (maxval itself is fine for a shift: rare, generic code sorts it out)
+            take_bit(nv, W, q, k.T8);
+            const int d = nv - x;
+            sse += (long long)d * (long long)d;
+            P::template setx<Q, S>(M, nv);
+        });
+        return bad;
+    }
+    template <int Q>
+    __device__ __forceinline__ void generic(uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
+                                            const KE& k, int c, unsigned& W, long long& sse, bool own, unsigned* lmrow) {
+        static_for<0, P::NS>([&](auto Sc) {
+            constexpr int S = decltype(Sc)::value;
+            const int col = c + 2 * S + Q;
+            const KE kk = make_ke((col >= 1 && col <= g.w - 2) ? k.T : 0);
+            const int q = P::template qsum<Q, S>(M, prev, next, U, D, kk.init);
+            const int x = P::template getx<Q, S>(M);
+            const bool expd = (unsigned)q < (unsigned)kk.T8;        // -T <= e < T
+            const int cc = max(min(q >> 2, kk.T2), 0);
+            const int nv0 = x + cc + kk.negT;
+            const unsigned lim = (unsigned)g.maxval - (expd ? 1u : 0u);
+            const bool ok = (unsigned)nv0 <= lim;                   // else: location map, pixel unchanged
+            int nv = ok ? nv0 : x;
+            if (expd && ok) {                                       // carrier: next payload bit of the cell
+                nv += (int)(W >> 31);
+                W <<= 1;
+            }
+            const int d = nv - x;
+            sse += (long long)d * (long long)d;
+            if (own && !ok && kk.T != 0) {
+                atomicOr(lmrow + (col >> 5), lm_bitmask(col));
+                ++st->flagged;
+            }
+            P::template setx<Q, S>(M, nv);
+        });
+    }
+    template <int QA>
+    __device__ __forceinline__ void step(int c, int, bool special, const uint4& U, uint4& A, uint4& B, const uint4& D,
+                                         unsigned prev, unsigned next, unsigned char* pa, unsigned char* pb) {
+        const uint4 A0 = A, B0 = B;
+        const unsigned Wa0 = Wa, Wb0 = Wb;
+        const long long sa0 = ssea, sb0 = sseb;
+        bool redo = special;
+        if (!special) {
+            bool bad = fast<QA>(A, prev, next, U, B0, ka, Wa, ssea);
+            bad |= fast<1 - QA>(B, prev, next, A, D, kb, Wb, sseb);
+            redo = __any_sync(0xffffffffu, bad);
+        }
+        if (redo) {
+            A = A0; B = B0; Wa = Wa0; Wb = Wb0; ssea = sa0; sseb = sb0;
+            generic<QA>(A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
+            generic<1 - QA>(B, prev, next, A, D, kb, c, Wb, sseb, ownb, lma + (g.lmpitch >> 2));
+        }
+        if (c < g.w) {
+            if (sta) sts128(pa, A);
+            if (stb) sts128(pb, B);
+        }
+    }
+    __device__ __forceinline__ void end() {
+        if (owna) st->sse += ssea;
+        if (ownb) st->sse += sseb;
+    }
+};
+
+// Copies the payload words covering stream bits [B0, B0 + total] into shared memory, byte-swapped
+// so that stream bit k is bit 31-(k&31) of its word; bits at or past n_bits read as 0 (zero padding).
+__device__ __forceinline__ void stage_payload(const unsigned* __restrict__ pay, unsigned B0, int total, unsigned n_bits,
+                                              unsigned* pw) {
+    const unsigned w0 = B0 >> 5;
+    const int nw = (int)(((B0 & 31u) + (unsigned)total + 31u) >> 5) + 2;
+    for (int j = threadIdx.x; j < nw; j += blockDim.x) {
+        const unsigned wi = w0 + (unsigned)j;
+        const unsigned long long bit0 = (unsigned long long)wi << 5;
+        unsigned v = 0;
+        if (bit0 < n_bits) {
+            v = __byte_perm(__ldg(pay + wi), 0, 0x0123);
+            const unsigned rem = n_bits - (unsigned)bit0;
+            if (rem < 32u) v &= ~(0xffffffffu >> rem);
+        }
+        pw[j] = v;
+    }
+}
+
+// ------------------------------------------------------------------ K_A: pass-0 counts
+template <typename PixT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch bt, int* __restrict__ band_cnt,
+                                                              unsigned char* __restrict__ rowcnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem2 L = layout2(g, 0);
+    unsigned char* simg = smem_raw + L.img;
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
+    if (threadIdx.x == 0) { misc[0] = 0; if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); } }
+    __syncthreads();
+    const int r0 = band * g.R, r_first = r0 - 2;
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    load_rows2<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    Count2<PixT, true> body{g, 0, rowcnt + (long long)unit * g.h * g.ncol, nullptr, 0};
+    sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, bt.T[unit], body);
+    int tot = body.total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(misc, tot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int all = misc[0];
+        band_cnt[unit * g.nb + band] = all;
+        if (all) atomicAdd(reinterpret_cast<unsigned long long*>(bt.info + (long long)unit * PEEB_INFO + 3), (unsigned long long)all);
+    }
+}
+
+// ------------------------------------------------------------------ K_B: fused two-pass embed
+template <typename PixT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch bt, const int* __restrict__ band_cnt,
+                                                              const unsigned char* __restrict__ rowcnt,
+                                                              unsigned* __restrict__ ticket,
+                                                              unsigned long long* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem2 L = layout2(g, 1);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + L.lm);
+    int* tab = reinterpret_cast<int*>(smem_raw + L.tab);
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    unsigned* pw = reinterpret_cast<unsigned*>(smem_raw + L.pw);
+
+    // in-order ticket: a band only ever waits on bands with smaller tickets
+    if (threadIdx.x == 0) {
+        misc[40] = (int)atomicAdd(ticket, 1u);
+        if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
+    }
+    __syncthreads();
+    const int tk = misc[40];
+    const int unit = tk / g.nb, band = tk - unit * g.nb;
+    const int r0 = band * g.R, r_first = r0 - 2;
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    const int T = bt.T[unit];
+    const unsigned n_bits = bt.n_bits[unit];
+    const unsigned* payload = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
+    long long* info = bt.info + (long long)unit * PEEB_INFO;
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
+    const int n0 = max(p0_hi - p0_lo, 0) * g.ncol, n1 = max(own_hi - own_lo, 0) * g.ncol;
+
+    // the copy of the band runs while the tables are fetched and the payload window of pass 0 is staged
+    const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
+    PHASE_INIT;
+    issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+    for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
+    {
+        const unsigned char* rc = rowcnt + ((long long)unit * g.h + p0_lo) * g.ncol;
+        for (int k = threadIdx.x; k < n0; k += blockDim.x) tab[k] = rc[k];
+    }
+    if (threadIdx.x >= 32 && threadIdx.x < 64) {  // warp 1 (warp 0 is busy issuing the copies)
+        const int lane = threadIdx.x & 31;
+        int before = 0, all = 0;
+        for (int k = lane; k < g.nb; k += 32) {
+            const int cc = band_cnt[unit * g.nb + k];
+            all += cc;
+            if (k < band) before += cc;
+        }
+        // carriers of the halo row above precede this band in raster order
+        if (p0_lo < own_lo) {
+            const unsigned char* rc = rowcnt + ((long long)unit * g.h + p0_lo) * g.ncol;
+            for (int k = lane; k < g.ncol; k += 32) before -= rc[k];
+        }
+        before = (int)warp_sum_i64(before);
+        all = (int)warp_sum_i64(all);
+        if (lane == 0) { misc[41] = before; misc[42] = all; }
+    }
+    __syncthreads();
+    PHASE_MARK(0);  // tables
+    Stats2 st;
+
+    // ---- pass 0 (colour 0): band rows and one halo row on each side
+    {
+        const unsigned B0 = (unsigned)misc[41];  // stream index of the first carrier of row p0_lo
+        stage_payload(payload, B0, max(p0_hi - p0_lo, 0) * ((g.w + 1) >> 1), n_bits, pw);  // upper bound: no need to wait for the scan
+        block_scan_runs(tab, n0, misc);
+        PHASE_MARK(1);  // payload staging + scan
+        wait_rows2(g, s_lo, s_hi, bar);
+        PHASE_MARK(2);  // band copy wait
+        Apply2<PixT> body{g, p0_lo, own_lo, own_hi, tab, pw, (int)(B0 & 31u), slm, r0, &st};
+        sweep2_colour<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
+        PHASE_MARK(3);  // apply 0 (own warp)
+    }
+    __syncthreads();
+    PHASE_MARK(4);  // barrier
+
+    // ---- pass 1 (colour 1) over the band rows: count, order (look-back over earlier bands), apply
+    {
+        Count2<PixT, false> body{g, own_lo, nullptr, tab, 0};
+        sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
+    }
+    PHASE_MARK(5);  // count 1
+    __syncthreads();
+    PHASE_MARK(6);  // barrier
+    {
+        const int total = block_scan_runs(tab, n1, misc);
+        PHASE_MARK(7);  // scan
+        if (threadIdx.x < 32) {
+            // decoupled look-back, one predecessor per lane: aggregates are summed back to the nearest
+            // band that already knows its inclusive prefix
+            const int lane = threadIdx.x;
+            unsigned long long* stt = status + (long long)unit * g.nb;
+            if (lane == 0) atomicExch(stt + band, ST_AGG | (unsigned)total);
+            unsigned before = 0;
+            for (int k0 = band - 1; k0 >= 0; k0 -= 32) {
+                const int k = k0 - lane;
+                unsigned long long v = ST_PFX;  // lanes before band 0: prefix 0
+                if (k >= 0) do { v = *reinterpret_cast<volatile unsigned long long*>(stt + k); } while ((v & ST_MASK) == 0);
+                const unsigned pfx = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_PFX);
+                const int first = __ffs(pfx) - 1;  // nearest band with a prefix (-1: none in this window)
+                unsigned val = (first < 0 || lane <= first) ? (unsigned)(v & 0xffffffffu) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                before += val;
+                if (first >= 0) break;
+            }
+            if (lane == 0) {
+                atomicExch(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
+                misc[43] = (int)before;
+                if (total) atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
+            }
+        }
+        PHASE_MARK(8);  // look-back
+        __syncthreads();
+        const unsigned B1 = (unsigned)(misc[42] + misc[43]);  // cap0 + earlier bands' pass-1 carriers
+        stage_payload(payload, B1, total, n_bits, pw);
+        __syncthreads();
+        PHASE_MARK(9);  // payload staging
+        Apply2<PixT> body{g, own_lo, own_lo, own_hi, tab, pw, (int)(B1 & 31u), slm, r0, &st};
+        sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
+        PHASE_MARK(10);  // apply 1
+    }
+
+    {
+        const long long sse = warp_sum_i64(st.sse);
+        const long long fl = warp_sum_i64((long long)st.flagged);
+        if ((threadIdx.x & 31) == 0) {
+            if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(info + 6), (unsigned long long)sse);
+            if (fl) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)fl);
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(11);  // stats + barrier
+    const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
+    if (bt.dst) store_rows2<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, b_lo, b_hi);
+    PHASE_MARK(12);  // store
+    if (bt.lm) {
+        unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw;
+        const int nrows = b_hi - b_lo;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
+            const int wpr = g.lmw >> 2;
+            for (int r = warp; r < nrows; r += nwarps)
+                for (int k = lane; k < wpr; k += 32)
+                    reinterpret_cast<unsigned*>(glm)[r * wpr + k] = slm[r * (g.lmpitch >> 2) + k];
+        } else {
+            const unsigned char* sb = reinterpret_cast<const unsigned char*>(slm);
+            for (int r = warp; r < nrows; r += nwarps)
+                for (int k = lane; k < g.lmw; k += 32) glm[(size_t)r * g.lmw + k] = sb[(size_t)r * g.lmpitch + k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K_X: extract
+// Carrier bits of a (row, cell) are collected MSB-first in a lane register (first carrier ends up
+// in the highest of the n used bits); tn/tw tables hold count and bits per cell of the own rows.
+template <typename PixT>
+struct Extract2 {
+    using P = PixOps<PixT>;
+    const Geom2& g;
+    int own_lo, own_hi;
+    const unsigned char* slm;  // location-map rows, row lm_row0 first
+    int lm_row0;
+    int* tn;
+    unsigned* tw;
+    KX ka, kb;
+    unsigned Wa, Wb;
+    int na, nb, ia;
+    bool sta, stb, reca, recb;
+    unsigned long long la, lb;  // location-map bytes of this lane's cell in rows a and b (byte k = columns 8k..8k+7 of the cell)
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
+        sta = a; stb = b;
+        ka = make_kx(a ? T : 0); kb = make_kx(b ? T : 0);
+        Wa = Wb = 0u; na = nb = 0;
+        ia = (rowa - own_lo) * g.ncol + cell;
+        reca = a && rowa >= own_lo && rowa < own_hi;
+        recb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
+        // fetched once per cell, ahead of use: the common all-zero case then costs one test per step
+        const unsigned char* lmpa = slm + (size_t)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3);
+        la = lb = 0ull;
+        const int nbytes = g.cws * (P::PXS >> 3);
+        for (int k = 0; k < nbytes; ++k) {
+            la |= (unsigned long long)lmpa[k] << (8 * k);
+            lb |= (unsigned long long)lmpa[g.lmpitch + k] << (8 * k);
+        }
+    }
+    __device__ __forceinline__ unsigned lmbits(unsigned long long v, int s) const {
+        return (unsigned)(v >> (s * P::PXS)) & (P::PXS == 8 ? 0xffu : 0xffffu);
+    }
+    __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS) || (la | lb) != 0ull; }
+    template <int Q, bool SPECIAL>
+    __device__ __forceinline__ void row(uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
+                                        const KX& k, int c, unsigned lmb, unsigned& W, int& n) {
+        static_for<0, P::NS>([&](auto Sc) {
+            constexpr int S = decltype(Sc)::value;
+            KX kk = k;
+            if (SPECIAL) {
+                constexpr int cs = 2 * S + Q;  // column inside the step
+                const int col = c + cs;
+                // packbits: column j of a byte at bit 7-j; 16-pixel steps read two bytes little-endian
+                const unsigned flag = (lmb >> ((cs & 8) + 7 - (cs & 7))) & 1u;
+                kk = make_kx((col >= 1 && col <= g.w - 2 && !flag) ? k.T : 0);
+            }
+            const int q = P::template qsum<Q, S>(M, prev, next, U, D, kk.init);  // 4(e' + 2T) + r, e' = x' - p
+            const int x = P::template getx<Q, S>(M);
+            const int cc = max(min((q + 4) >> 3, kk.T2), 0);                       // clamp(ceil(e'/2), -T, T) + T
+            collect_bit(W, n, q, kk.T16);
+            P::template setx<Q, S>(M, x - cc + kk.T);
+        });
+    }
+    template <int QA>
+    __device__ __forceinline__ void step(int c, int s, bool special, const uint4& U, uint4& A, uint4& B, const uint4& D,
+                                         unsigned prev, unsigned next, unsigned char* pa, unsigned char* pb) {
+        if (special) {
+            row<QA, true>(A, prev, next, U, B, ka, c, lmbits(la, s), Wa, na);
+            row<1 - QA, true>(B, prev, next, A, D, kb, c, lmbits(lb, s), Wb, nb);
+        } else {
+            row<QA, false>(A, prev, next, U, B, ka, c, 0u, Wa, na);
+            row<1 - QA, false>(B, prev, next, A, D, kb, c, 0u, Wb, nb);
+        }
+        if (c < g.w) {
+            if (sta) sts128(pa, A);
+            if (stb) sts128(pb, B);
+        }
+    }
+    __device__ __forceinline__ void end() {
+        if (reca) { tn[ia] = na; tw[ia] = Wa; }
+        if (recb) { tn[ia + g.ncol] = nb; tw[ia + g.ncol] = Wb; }
+    }
+};
+
+// grid = n_units * nb.  stage_bits: per (unit, pass, band) `bandwords` words, stream bit k at bit
+// 31-(k&31) of word k>>5; stage_cnt: carriers per (unit, pass, band).
+template <typename PixT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatch bt, unsigned* __restrict__ stage_bits,
+                                                                int* __restrict__ stage_cnt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem2 L = layout2(g, 2);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned char* slm = smem_raw + L.lm;
+    int* tn1 = reinterpret_cast<int*>(smem_raw + L.tab);
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    int* tn0 = reinterpret_cast<int*>(smem_raw + L.tn0);
+    unsigned* tw0 = reinterpret_cast<unsigned*>(smem_raw + L.tw0);
+    unsigned* tw1 = reinterpret_cast<unsigned*>(smem_raw + L.tw1);
+    unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + L.stream);  // [2][bandwords]: pass 0, pass 1
+
+    const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
+    const int r0 = band * g.R, r_first = r0 - 2;
+    if (g.bulk && threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    const int T = bt.T[unit];
+    const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
+    issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+    {   // location-map rows [r0-1, r0+R+1) -> slm
+        const int l_lo = max(r0 - 1, 0), l_hi = min(r0 + g.R + 1, g.h);
+        const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
+            const int wpr = g.lmw >> 2;
+            unsigned* sw = reinterpret_cast<unsigned*>(slm);
+            for (int r = l_lo + warp; r < l_hi; r += nwarps) {
+                const unsigned* gw = reinterpret_cast<const unsigned*>(glm + (size_t)r * g.lmw);
+                for (int k = lane; k < wpr; k += 32) sw[(size_t)(r - (r0 - 1)) * (g.lmpitch >> 2) + k] = gw[k];
+            }
+        } else {
+            for (int r = l_lo + warp; r < l_hi; r += nwarps)
+                for (int k = lane; k < g.lmw; k += 32) slm[(size_t)(r - (r0 - 1)) * g.lmpitch + k] = glm[(size_t)r * g.lmw + k];
+        }
+        // bytes between lmw and the pitch are read by steps past the row end: keep them defined
+        const int padb = g.lmpitch - g.lmw;
+        for (int r = warp; r < g.R + 2; r += nwarps)
+            if (lane < padb) slm[(size_t)r * g.lmpitch + g.lmw + lane] = 0;
+        for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
+    }
+    wait_rows2(g, s_lo, s_hi, bar);
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
+    const int n = max(own_hi - own_lo, 0) * g.ncol;
+    {   // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
+        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn1, tw1};
+        sweep2_colour<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
+    }
+    __syncthreads();
+    {
+        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn0, tw0};
+        sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
+    }
+    __syncthreads();
+
+    for (int pass = 0; pass < 2; ++pass) {
+        int* cnt = pass == 0 ? tn0 : tn1;
+        const unsigned* tw = pass == 0 ? tw0 : tw1;
+        unsigned* out = stream + (size_t)pass * g.bandwords;
+        // the scan turns counts into bit offsets; a piece's size is the next offset minus its own
+        const int total = block_scan_runs(cnt, n, misc);
+        __syncthreads();
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int o = cnt[k];
+            const int cc = (k + 1 < n ? cnt[k + 1] : total) - o;
+            if (cc > 0) {
+                const int sh = o & 31;
+                const unsigned long long v = (unsigned long long)tw[k] << (64 - cc - sh);
+                atomicOr(out + (o >> 5), (unsigned)(v >> 32));
+                if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
+            }
+        }
+        __syncthreads();
+        const long long slot = ((long long)unit * 2 + pass) * g.nb + band;
+        if (threadIdx.x == 0) stage_cnt[slot] = total;
+        unsigned* gout = stage_bits + slot * g.bandwords;
+        const int nw = (total + 31) >> 5;
+        for (int k = threadIdx.x; k < nw; k += blockDim.x) gout[k] = out[k];
+        __syncthreads();
+    }
+    if (bt.dst)
+        store_rows2<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
+}
+
+// ------------------------------------------------------------------ K_G: payload assembly
+// grid = (2*nb, n_units).  Piece p of a unit = pass-0 band p (p < nb) or pass-1 band p-nb; its
+// global bit offset is the sum of the earlier pieces' counts.  Output is MSB-first packed,
+// truncated to n_bits; payload_out is zeroed by the caller.
+__global__ void __launch_bounds__(128) pee2_gather_kernel(int nb, int bandwords, PeeBatch bt,
+                                                          const unsigned* __restrict__ stage_bits,
+                                                          const int* __restrict__ stage_cnt) {
+    const int unit = blockIdx.y, piece = blockIdx.x;
+    const int* cnts = stage_cnt + (long long)unit * 2 * nb;
+    long long before = 0, all = 0;
+    for (int k = threadIdx.x; k < 2 * nb; k += blockDim.x) {
+        const int c = cnts[k];
+        all += c;
+        if (k < piece) before += c;
+    }
+    before = warp_sum_i64(before);
+    all = warp_sum_i64(all);
+    __shared__ long long s_b[4], s_a[4];
+    if ((threadIdx.x & 31) == 0) { s_b[threadIdx.x >> 5] = before; s_a[threadIdx.x >> 5] = all; }
+    __syncthreads();
+    before = s_b[0] + s_b[1] + s_b[2] + s_b[3];
+    all = s_a[0] + s_a[1] + s_a[2] + s_a[3];
+    const long long n_bits = bt.n_bits[unit];
+    long long* info = bt.info + (long long)unit * PEEB_INFO;
+    if (piece == 0 && threadIdx.x == 0) {
+        long long c0 = 0;
+        for (int k = 0; k < nb; ++k) c0 += cnts[k];
+        info[0] = bt.T[unit]; info[1] = n_bits; info[2] = all; info[3] = c0; info[4] = all - c0;
+        info[5] = 0; info[6] = 0; info[7] = n_bits > all ? PEEB_E_CAPACITY : 0;
+    }
+    const int cnt = cnts[piece];
+    if (cnt == 0 || before >= n_bits) return;
+    const unsigned* src = stage_bits + ((long long)unit * 2 * nb + piece) * bandwords;
+    unsigned* out = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
+    const int nsrc = (cnt + 31) >> 5;
+    const long long first = before >> 5, last = (before + cnt - 1) >> 5;
+    const int sh = (int)(before & 31);
+    for (long long mw = first + threadIdx.x; mw <= last; mw += blockDim.x) {
+        const int i = (int)(mw - first);
+        const unsigned cur = i < nsrc ? src[i] : 0u;
+        const unsigned prev = (i >= 1 && i - 1 < nsrc) ? src[i - 1] : 0u;
+        unsigned val = __funnelshift_r(cur, prev, sh);  // stream bits [32 mw, 32 mw + 32), first bit on top
+        const long long bit0 = mw << 5;
+        if (bit0 + 32 > n_bits) {  // drop bits at or past n_bits
+            const int keep = (int)(n_bits - bit0);
+            val = keep <= 0 ? 0u : (val & ~(0xffffffffu >> keep));
+        }
+        if (val == 0) continue;
+        const unsigned packed = __byte_perm(val, 0, 0x0123);
+        if (mw == first || mw == last) atomicOr(out + mw, packed);
+        else out[mw] = packed;
+    }
+}
+
+__global__ void pee2_finalize_kernel(PeeBatch bt) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= bt.n_units) return;
+    long long* info = bt.info + (long long)u * PEEB_INFO;
+    info[0] = bt.T[u];
+    info[1] = bt.n_bits[u];
+    info[2] = info[3] + info[4];
+    info[7] = ((long long)bt.n_bits[u] > info[2]) ? PEEB_E_CAPACITY : 0;
+}
+
+// ------------------------------------------------------------------ host side
+static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
+
+static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int kind, Geom2& g) {
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "pee: itemsize must be 1 or 2");
+    PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "pee: bit_depth %d out of range for itemsize %d", bit_depth, itemsize);
+    PEEB_REQUIRE(h >= 1 && w >= 1 && (long long)h * w < (1ll << 31), "pee: image size %dx%d unsupported", h, w);
+    g.h = h; g.w = w; g.itemsize = itemsize;
+    g.maxval = (1 << bit_depth) - 1;
+    g.rowbytes = w * itemsize;
+    g.bulk = ws->use_bulk && (g.rowbytes % 16 == 0);
+    g.pitch = (int)align_up((size_t)g.rowbytes, 128) + 16;
+    g.lmw = (w + 7) / 8;
+    g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 12;
+    const int pxs = 16 / itemsize;
+    const int nsteps = (g.rowbytes + 15) / 16;
+    const size_t sm_total = (size_t)ws->max_smem_optin + 1024;  // 227 KB usable + 1 KB reserved per CTA
+    // Candidates: band heights R with R + 2 = 2 * rpw (a pass over the band and its halo rows fills
+    // whole warp items), CTA sizes, cell widths; score = modelled lane-steps per useful pixel.
+    double best = 1e30;
+    Geom2 bestg = g;
+    bool found = false;
+    const int forceR = getenv("PEEB_BAND_R") ? atoi(getenv("PEEB_BAND_R")) : 0;
+    const int forceT = getenv("PEEB_CTA_THREADS") ? atoi(getenv("PEEB_CTA_THREADS")) : 0;
+    const int forceCW = getenv("PEEB_CELL_W") ? atoi(getenv("PEEB_CELL_W")) : 0;
+    const int forceB = getenv("PEEB_CTA_MINB") ? atoi(getenv("PEEB_CTA_MINB")) : 0;
+    for (int R : {62, 58, 54, 30, 26, 14, 6, 2}) {
+        if (forceR && R != forceR) continue;
+        Geom2 t = g;
+        t.R = R;
+        t.rpw_log2 = ilog2((R + 2) / 2);
+        if ((1 << t.rpw_log2) < (R + 2) / 2) ++t.rpw_log2;
+        t.rpw = 1 << t.rpw_log2;
+        const int parts = 32 / t.rpw;
+        for (int cws = 64 / pxs; cws >= 1; --cws) {
+            t.cws = cws; t.CW = cws * pxs;
+            if (forceCW && t.CW != forceCW) continue;
+            t.ncol = (nsteps + cws - 1) / cws;
+            t.bandwords = (R * ((w + 1) / 2) + 31) / 32 + 2;
+            const size_t smem = layout2(t, kind).total;
+            if (smem > (size_t)ws->max_smem_optin) continue;
+            const int nic = (t.ncol + parts - 1) / parts;  // warp items of a one-group pass
+            for (int threads : {256, 512, 1024}) {
+                if (forceT && threads != forceT) continue;
+                const int nwarps = threads / 32;
+                int cps = (int)(sm_total / (smem + 1024));
+                cps = std::min(cps, 2048 / threads);
+                if (cps < 1) continue;
+                // registers: 64K per SM; the row-pair step wants ~80 per thread
+                const int regs = 65536 / (cps * threads);
+                if (regs < 64) cps = std::max(1, 65536 / (64 * threads));
+                if (forceB) cps = std::min(cps, forceB);
+                const int rounds = (nic + nwarps - 1) / nwarps;
+                // Model (fitted to B200 runs): lane-steps issued per useful row-step
+                // (idle lanes, halo rows, unbalanced rounds), divided by how well the resident warps hide
+                // the per-band latencies (24 warps per SM ~ saturation), with a penalty when the
+                // register budget per thread falls under what the row-pair step needs without spilling.
+                const double work = (double)rounds * nwarps * 32 * (cws + 2.5) * 2;  // + per-item set-up, ~2.5 steps
+                const double fixed = 4096.0;  // per-band latencies (tables, look-back, store) in lane-steps per pass
+                const double useful = (double)R * nsteps;
+                const double warps_sm = (double)cps * threads / 32.0;
+                const double occ = std::pow(std::min(1.0, warps_sm / 24.0), 0.7);
+                const double regpen = (65536 / (cps * threads) < 72) ? 1.3 : 1.0;
+                const double score = (work + fixed) / useful / occ * regpen;
+                if (score < best) {
+                    best = score; bestg = t; bestg.threads = threads; bestg.minb = cps; found = true;
+                }
+            }
+        }
+    }
+    if (!found) {
+        set_error("pee: image width %d needs more shared memory than one SM has", w);
+        return PEEB_E_UNSUPPORTED;
+    }
+    g = bestg;
+    g.nb = (h + g.R - 1) / g.R;
+    if (getenv("PEEB_DEBUG_GEOM")) {
+        static int printed[3] = {0, 0, 0};
+        if (printed[kind]++ < 1)
+            fprintf(stderr, "[peeb] %dx%dx%d kind %d: R=%d rpw=%d CW=%d ncol=%d threads=%d minb=%d smem=%zu score=%.3f\n", h, w, itemsize,
+                    kind, g.R, g.rpw, g.CW, g.ncol, g.threads, g.minb, layout2(g, kind).total, best);
+    }
+    return PEEB_OK;
+}
+
+template <typename K>
+static int set_smem2(K kernel, size_t bytes) {
+    PEEB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PEEB_OK;
+}
+
+template <typename PixT, int NT, int MINB>
+static int launch_embed2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long long nbands, int* band_cnt,
+                         unsigned char* rowcnt, unsigned* ticket, unsigned long long* status, cudaStream_t st) {
+    const size_t smem0 = layout2(g, 0).total, smem1 = layout2(g, 1).total;
+    int rc = set_smem2(pee2_count_kernel<PixT, NT, MINB>, smem0); if (rc) return rc;
+    rc = set_smem2(pee2_embed_kernel<PixT, NT, MINB>, smem1); if (rc) return rc;
+    { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
+      pee2_count_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem0, st>>>(g, bt, band_cnt, rowcnt); }
+    { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+      pee2_embed_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem1, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
+    return PEEB_OK;
+}
+template <typename PixT, int NT, int MINB>
+static int launch_extract2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long long nbands, unsigned* stage_bits,
+                           int* stage_cnt, cudaStream_t st) {
+    const size_t smem = layout2(g, 2).total;
+    int rc = set_smem2(pee2_extract_kernel<PixT, NT, MINB>, smem); if (rc) return rc;
+    ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
+    pee2_extract_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem, st>>>(g, bt, stage_bits, stage_cnt);
+    return PEEB_OK;
+}
+// (CTA size, CTAs per SM) pairs the kernels are compiled for: registers per thread = 64K / (NT * MINB)
+#define PEEB_DISPATCH2_T(FN, PIXT, ...)                                                     \
+    (g.threads == 256 ? (g.minb >= 3 ? FN<PIXT, 256, 3>(__VA_ARGS__) : g.minb == 2 ? FN<PIXT, 256, 2>(__VA_ARGS__) \
+                                                                    : FN<PIXT, 256, 1>(__VA_ARGS__))               \
+     : g.threads == 512 ? (g.minb >= 2 ? FN<PIXT, 512, 2>(__VA_ARGS__) : FN<PIXT, 512, 1>(__VA_ARGS__))           \
+                        : FN<PIXT, 1024, 1>(__VA_ARGS__))
+#define PEEB_DISPATCH2(FN, ...) \
+    (g.itemsize == 2 ? PEEB_DISPATCH2_T(FN, unsigned short, __VA_ARGS__) : PEEB_DISPATCH2_T(FN, unsigned char, __VA_ARGS__))
+
+int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
+                      int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
+                      int64_t* info, cudaStream_t st, int slot) {
+    Geom2 g;
+    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 1, g);
+    if (rc) return rc;
+    if (g.bulk && ((((uintptr_t)src) | (uintptr_t)marked | (uint64_t)src_stride | (uint64_t)marked_stride) & 15))
+        g.bulk = 0;  // unaligned user buffers: plain copies
+    const long long nbands = (long long)n_units * g.nb;
+    PEEB_REQUIRE(nbands < (1ll << 30), "peeb_pee_embed_batch: too many bands");
+    int* dT; unsigned* dN; char* extra;
+    const size_t cnt_bytes = align_up((size_t)nbands * sizeof(int), 256);
+    const size_t st_bytes = align_up((size_t)nbands * sizeof(unsigned long long), 256);
+    const size_t rc_bytes = align_up((size_t)n_units * h * g.ncol, 256);
+    rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256 + rc_bytes, st, &dT, &dN, &extra);
+    if (rc) return rc;
+    int* band_cnt = (int*)extra;
+    unsigned long long* status = (unsigned long long*)(extra + cnt_bytes);
+    unsigned* ticket = (unsigned*)(extra + cnt_bytes + st_bytes);
+    unsigned char* rowcnt = (unsigned char*)(extra + cnt_bytes + st_bytes + 256);
+    PEEB_CUDA(cudaMemsetAsync(status, 0, st_bytes + 256, st));
+    PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
+    PeeBatch bt{};
+    bt.src = (const unsigned char*)src; bt.src_stride = src_stride;
+    bt.dst = (unsigned char*)marked; bt.dst_stride = marked_stride;
+    bt.lm = lm; bt.lm_stride = lm_stride;
+    bt.payload = payload; bt.payload_stride = payload_stride;
+    bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
+    if (rc) return rc;
+    PEEB_CUDA(cudaGetLastError());
+    { ProfScope p(ws, PEEB_K_PEE_FINAL, st);
+      pee2_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt); }
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
+                        int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm,
+                        int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,
+                        int64_t recovered_stride, int64_t* info, cudaStream_t st, int slot) {
+    Geom2 g;
+    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 2, g);
+    if (rc) return rc;
+    if (g.bulk && ((((uintptr_t)marked) | (uintptr_t)recovered | (uint64_t)marked_stride | (uint64_t)recovered_stride) & 15))
+        g.bulk = 0;
+    const long long nbands = (long long)n_units * g.nb;
+    PEEB_REQUIRE(nbands < (1ll << 30), "peeb_pee_extract_batch: too many bands");
+    int* dT; unsigned* dN; char* extra;
+    const size_t cnt_bytes = align_up((size_t)nbands * 2 * sizeof(int), 256);
+    rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, cnt_bytes, st, &dT, &dN, &extra);
+    if (rc) return rc;
+    int* stage_cnt = (int*)extra;
+    rc = scratch_reserve(ws->pbits[slot], (size_t)nbands * 2 * g.bandwords * sizeof(unsigned) + 256);
+    if (rc) return rc;
+    unsigned* stage_bits = (unsigned*)ws->pbits[slot].ptr;
+    PeeBatch bt{};
+    bt.src = (const unsigned char*)marked; bt.src_stride = marked_stride;
+    bt.dst = (unsigned char*)recovered; bt.dst_stride = recovered_stride;
+    bt.lm = const_cast<uint8_t*>(lm); bt.lm_stride = lm_stride;
+    bt.payload = nullptr; bt.payload_stride = payload_stride; bt.payload_out = payload_out;
+    bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    rc = PEEB_DISPATCH2(launch_extract2, ws, g, bt, nbands, stage_bits, stage_cnt, st);
+    if (rc) return rc;
+    PEEB_CUDA(cudaGetLastError());
+    {
+        ProfScope p(ws, PEEB_K_PEE_GATHER, st);
+        dim3 grid((unsigned)(2 * g.nb), (unsigned)n_units);
+        pee2_gather_kernel<<<grid, 128, 0, st>>>(g.nb, g.bandwords, bt, stage_bits, stage_cnt);
+    }
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+}  // namespace peeb
+
+#ifdef PEEB_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int peeb_debug_phases(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, peeb::g_phase, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(peeb::g_phase, z, sizeof(z)); }
+    return 0;
+}
+#endif

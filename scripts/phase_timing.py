@@ -1,0 +1,51 @@
+"""Development aid: per-phase time of the PEE embed kernel (thread 0 of every CTA, clock64 deltas).
+Needs a library built with PEEB_NVCC_EXTRA=-DPEEB_PHASE_TIMING (python -m codec_tcc_b200.build --force).
+usage: python scripts/phase_timing.py [n_images h w bit_depth T]"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from codec_tcc_b200 import _cabi, device as D
+from codec_tcc_b200.synth import synth_batch
+
+NAMES = ["tables", "payload+scan0", "band copy wait", "apply0", "barrier", "count1", "barrier", "scan1", "look-back",
+         "stage payload 1", "apply1", "stats+barrier", "store"]
+
+
+def main():
+    a = [int(x) for x in sys.argv[1:]]
+    n, h, w, bd, T = (a + [512, 512, 512, 16, 96][len(a):])[:5]
+    _cabi.lib()
+    fn = C.CDLL(_cabi.library_path()).peeb_debug_phases
+    fn.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    dev = torch.device("cuda:0")
+    maxval = (1 << bd) - 1
+    imgs = synth_batch(n, h, w, maxval, 2)
+    d_imgs = torch.from_numpy(imgs.view(np.int16) if imgs.dtype == np.uint16 else imgs).to(dev)
+    stride = D.payload_stride(h * w)
+    d_pays = torch.from_numpy(np.random.default_rng(7).integers(0, 256, (n, stride), dtype=np.uint8)).to(dev)
+    big = np.full(n, h * w, np.int64)
+    _, _, d_info = D.pee_embed_device(d_imgs, d_pays, big, T, bd, marked=False, lm=False)
+    cap = d_info[:, 2].cpu().numpy().astype(np.int64)
+    d_marked = torch.empty_like(d_imgs)
+    d_lm = torch.empty((n, h, (w + 7) // 8), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm)
+    buf = (C.c_ulonglong * 16)()
+    fn(buf, 1)
+    reps = 5
+    for _ in range(reps):
+        D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm)
+    fn(buf, 0)
+    tot = sum(buf[i] for i in range(13))
+    print(f"embed kernel phases, {n}x{h}x{w} bd={bd} T={T}: mean cycles per CTA (thread 0), share")
+    for i, nm in enumerate(NAMES):
+        print(f"  {nm:18s} {buf[i] / reps:14.0f} total  {100.0 * buf[i] / max(tot, 1):5.1f}%")
+
+
+if __name__ == "__main__":
+    main()
