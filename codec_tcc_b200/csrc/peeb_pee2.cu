@@ -94,12 +94,13 @@ __device__ __forceinline__ void issue_rows2(const Geom2& g, const unsigned char*
                                             int lo, int hi, uint64_t* bar) {
     if (hi <= lo) return;
     if (g.bulk) {
-        if (threadIdx.x < 32) {
-            if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)(hi - lo) * (unsigned)g.rowbytes);
-            __syncwarp();
-            for (int r = lo + (int)threadIdx.x; r < hi; r += 32)
+        // a warp issues its bulk copies one lane after the other: spread the rows over the warps,
+        // four lanes each (the transaction count may be posted after the first copies complete)
+        if (threadIdx.x == 0) mbar_expect_tx(bar, (unsigned)(hi - lo) * (unsigned)g.rowbytes);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if (lane < 4)
+            for (int r = lo + warp * 4 + lane; r < hi; r += nwarps * 4)
                 bulk_g2s(simg + row_off(g, r - r_first), usrc + (size_t)r * g.rowbytes, (unsigned)g.rowbytes, bar);
-        }
     } else {
         for (int r = lo + (int)(threadIdx.x >> 5); r < hi; r += (int)(blockDim.x >> 5)) {
             const PixT* s = reinterpret_cast<const PixT*>(usrc + (size_t)r * g.rowbytes);
@@ -157,9 +158,10 @@ __device__ __forceinline__ void store_rows2(const Geom2& g, unsigned char* udst,
                                             int lo, int hi) {
     if (hi <= lo) return;
     if (g.bulk) {
-        if (threadIdx.x < 32) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        if (lane < 4) {
             fence_async_smem();
-            for (int r = lo + (int)threadIdx.x; r < hi; r += 32)
+            for (int r = lo + warp * 4 + lane; r < hi; r += nwarps * 4)
                 bulk_s2g(udst + (size_t)r * g.rowbytes, simg + row_off(g, r - r_first), (unsigned)g.rowbytes);
             bulk_commit();
             bulk_wait_read0();
@@ -259,6 +261,16 @@ template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& 
         f(std::integral_constant<int, I>{});
         static_for<I + 1, N>(f);
     }
+}
+
+// look-back status words: the value is the whole message, so relaxed gpu-scope accesses suffice
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ uint4 lds128(const unsigned char* p) { return *reinterpret_cast<const uint4*>(p); }
@@ -553,21 +565,22 @@ struct Apply2 {
 
 // Copies the payload words covering stream bits [B0, B0 + total] into shared memory, byte-swapped
 // so that stream bit k is bit 31-(k&31) of its word; bits at or past n_bits read as 0 (zero padding).
+__device__ __forceinline__ unsigned payload_word(const unsigned* __restrict__ pay, unsigned B0, int j, int nw,
+                                                unsigned n_bits) {
+    const unsigned wi = (B0 >> 5) + (unsigned)j;
+    const unsigned long long bit0 = (unsigned long long)wi << 5;
+    unsigned v = 0;
+    if (j < nw && bit0 < n_bits) {
+        v = __byte_perm(__ldg(pay + wi), 0, 0x0123);
+        const unsigned rem = n_bits - (unsigned)bit0;
+        if (rem < 32u) v &= ~(0xffffffffu >> rem);
+    }
+    return v;
+}
 __device__ __forceinline__ void stage_payload(const unsigned* __restrict__ pay, unsigned B0, int total, unsigned n_bits,
                                               unsigned* pw) {
-    const unsigned w0 = B0 >> 5;
     const int nw = (int)(((B0 & 31u) + (unsigned)total + 31u) >> 5) + 2;
-    for (int j = threadIdx.x; j < nw; j += blockDim.x) {
-        const unsigned wi = w0 + (unsigned)j;
-        const unsigned long long bit0 = (unsigned long long)wi << 5;
-        unsigned v = 0;
-        if (bit0 < n_bits) {
-            v = __byte_perm(__ldg(pay + wi), 0, 0x0123);
-            const unsigned rem = n_bits - (unsigned)bit0;
-            if (rem < 32u) v &= ~(0xffffffffu >> rem);
-        }
-        pw[j] = v;
-    }
+    for (int j = threadIdx.x; j < nw; j += blockDim.x) pw[j] = payload_word(pay, B0, j, nw, n_bits);
 }
 
 // ------------------------------------------------------------------ K_A: pass-0 counts
@@ -621,8 +634,11 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
     }
     __syncthreads();
+    // Tickets run band-major over the batch (band 0 of every unit, then band 1, ...): with more units
+    // than resident CTAs the earlier bands of a unit have finished when a band looks back, so the
+    // look-back finds an inclusive prefix at once instead of waiting on bands that run beside it.
     const int tk = misc[40];
-    const int unit = tk / g.nb, band = tk - unit * g.nb;
+    const int band = tk / bt.n_units, unit = tk - band * bt.n_units;
     const int r0 = band * g.R, r_first = r0 - 2;
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     const int T = bt.T[unit];
@@ -633,31 +649,40 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
     const int n0 = max(p0_hi - p0_lo, 0) * g.ncol, n1 = max(own_hi - own_lo, 0) * g.ncol;
 
-    // the copy of the band runs while the tables are fetched and the payload window of pass 0 is staged
+    // Small reads first: issued after the band's own bulk copies they would queue behind ~64 KB of
+    // traffic on this SM's path to L2.  Order: tables -> payload words of pass 0 -> band copy.
     const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
     PHASE_INIT;
-    issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
-    for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
     {
         const unsigned char* rc = rowcnt + ((long long)unit * g.h + p0_lo) * g.ncol;
-        for (int k = threadIdx.x; k < n0; k += blockDim.x) tab[k] = rc[k];
-    }
-    if (threadIdx.x >= 32 && threadIdx.x < 64) {  // warp 1 (warp 0 is busy issuing the copies)
-        const int lane = threadIdx.x & 31;
-        int before = 0, all = 0;
-        for (int k = lane; k < g.nb; k += 32) {
-            const int cc = band_cnt[unit * g.nb + k];
-            all += cc;
-            if (k < band) before += cc;
+        int rcv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = threadIdx.x + i * blockDim.x;
+            rcv[i] = k < n0 ? rc[k] : 0;
         }
-        // carriers of the halo row above precede this band in raster order
-        if (p0_lo < own_lo) {
-            const unsigned char* rc = rowcnt + ((long long)unit * g.h + p0_lo) * g.ncol;
-            for (int k = lane; k < g.ncol; k += 32) before -= rc[k];
+        if (threadIdx.x >= 32 && threadIdx.x < 64) {  // warp 1: pass-0 prefix of this band, cap0 of the unit
+            const int lane = threadIdx.x & 31;
+            int before = 0, all = 0;
+            for (int k = lane; k < g.nb; k += 32) {
+                const int cc = band_cnt[unit * g.nb + k];
+                all += cc;
+                if (k < band) before += cc;
+            }
+            // carriers of the halo row above precede this band in raster order
+            if (p0_lo < own_lo)
+                for (int k = lane; k < g.ncol; k += 32) before -= rc[k];
+            before = (int)warp_sum_i64(before);
+            all = (int)warp_sum_i64(all);
+            if (lane == 0) { misc[41] = before; misc[42] = all; }
         }
-        before = (int)warp_sum_i64(before);
-        all = (int)warp_sum_i64(all);
-        if (lane == 0) { misc[41] = before; misc[42] = all; }
+        for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int k = threadIdx.x + i * blockDim.x;
+            if (k < n0) tab[k] = rcv[i];
+        }
+        for (int k = threadIdx.x + 4 * blockDim.x; k < n0; k += blockDim.x) tab[k] = rc[k];
     }
     __syncthreads();
     PHASE_MARK(0);  // tables
@@ -666,7 +691,19 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     // ---- pass 0 (colour 0): band rows and one halo row on each side
     {
         const unsigned B0 = (unsigned)misc[41];  // stream index of the first carrier of row p0_lo
-        stage_payload(payload, B0, max(p0_hi - p0_lo, 0) * ((g.w + 1) >> 1), n_bits, pw);  // upper bound: no need to wait for the scan
+        // payload window: an upper bound of the band's carriers, so that it need not wait for the scan
+        const int maxbits = max(p0_hi - p0_lo, 0) * ((g.w + 1) >> 1);
+        const int nw = (int)(((B0 & 31u) + (unsigned)maxbits + 31u) >> 5) + 2;
+        unsigned pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pv[i] = payload_word(payload, B0, threadIdx.x + i * blockDim.x, nw, n_bits);
+        issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int j = threadIdx.x + i * blockDim.x;
+            if (j < nw) pw[j] = pv[i];
+        }
+        for (int j = threadIdx.x + 4 * blockDim.x; j < nw; j += blockDim.x) pw[j] = payload_word(payload, B0, j, nw, n_bits);
         block_scan_runs(tab, n0, misc);
         PHASE_MARK(1);  // payload staging + scan
         wait_rows2(g, s_lo, s_hi, bar);
@@ -694,12 +731,12 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
             // band that already knows its inclusive prefix
             const int lane = threadIdx.x;
             unsigned long long* stt = status + (long long)unit * g.nb;
-            if (lane == 0) atomicExch(stt + band, ST_AGG | (unsigned)total);
+            if (lane == 0) st_relaxed_gpu(stt + band, ST_AGG | (unsigned)total);
             unsigned before = 0;
             for (int k0 = band - 1; k0 >= 0; k0 -= 32) {
                 const int k = k0 - lane;
                 unsigned long long v = ST_PFX;  // lanes before band 0: prefix 0
-                if (k >= 0) do { v = *reinterpret_cast<volatile unsigned long long*>(stt + k); } while ((v & ST_MASK) == 0);
+                if (k >= 0) do { v = ld_relaxed_gpu(stt + k); } while ((v & ST_MASK) == 0);
                 const unsigned pfx = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_PFX);
                 const int first = __ffs(pfx) - 1;  // nearest band with a prefix (-1: none in this window)
                 unsigned val = (first < 0 || lane <= first) ? (unsigned)(v & 0xffffffffu) : 0u;
@@ -709,7 +746,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
                 if (first >= 0) break;
             }
             if (lane == 0) {
-                atomicExch(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
+                st_relaxed_gpu(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
                 misc[43] = (int)before;
                 if (total) atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
             }
@@ -857,19 +894,32 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     const int T = bt.T[unit];
     const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
-    issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
-    {   // location-map rows [r0-1, r0+R+1) -> slm
+    PHASE_INIT;
+    {   // location-map rows [r0-1, r0+R+1) -> slm; their loads are issued before the band's bulk copies
+        // (small reads would otherwise queue behind them)
         const int l_lo = max(r0 - 1, 0), l_hi = min(r0 + g.R + 1, g.h);
         const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
-            const int wpr = g.lmw >> 2;
+            const int wpr = g.lmw >> 2, nwords = (l_hi - l_lo) * wpr;
+            const unsigned* gw = reinterpret_cast<const unsigned*>(glm + (size_t)l_lo * g.lmw);
             unsigned* sw = reinterpret_cast<unsigned*>(slm);
-            for (int r = l_lo + warp; r < l_hi; r += nwarps) {
-                const unsigned* gw = reinterpret_cast<const unsigned*>(glm + (size_t)r * g.lmw);
-                for (int k = lane; k < wpr; k += 32) sw[(size_t)(r - (r0 - 1)) * (g.lmpitch >> 2) + k] = gw[k];
+            unsigned v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = threadIdx.x + i * blockDim.x;
+                v[i] = k < nwords ? __ldg(gw + k) : 0u;
             }
+            issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = threadIdx.x + i * blockDim.x;
+                if (k < nwords) sw[(size_t)(l_lo - (r0 - 1) + k / wpr) * (g.lmpitch >> 2) + (k % wpr)] = v[i];
+            }
+            for (int k = threadIdx.x + 4 * blockDim.x; k < nwords; k += blockDim.x)
+                sw[(size_t)(l_lo - (r0 - 1) + k / wpr) * (g.lmpitch >> 2) + (k % wpr)] = __ldg(gw + k);
         } else {
+            issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
             for (int r = l_lo + warp; r < l_hi; r += nwarps)
                 for (int k = lane; k < g.lmw; k += 32) slm[(size_t)(r - (r0 - 1)) * g.lmpitch + k] = glm[(size_t)r * g.lmw + k];
         }
@@ -880,19 +930,24 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
     }
     wait_rows2(g, s_lo, s_hi, bar);
+    PHASE_MARK(0);  // load
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
     const int n = max(own_hi - own_lo, 0) * g.ncol;
     {   // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
         Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn1, tw1};
         sweep2_colour<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
+        PHASE_MARK(1);  // sweep colour 1
     }
     __syncthreads();
+    PHASE_MARK(2);
     {
         Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn0, tw0};
         sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
+        PHASE_MARK(3);  // sweep colour 0
     }
     __syncthreads();
+    PHASE_MARK(4);
 
     for (int pass = 0; pass < 2; ++pass) {
         int* cnt = pass == 0 ? tn0 : tn1;
@@ -919,8 +974,10 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         for (int k = threadIdx.x; k < nw; k += blockDim.x) gout[k] = out[k];
         __syncthreads();
     }
+    PHASE_MARK(5);  // scans + stream assembly + staging writes
     if (bt.dst)
         store_rows2<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
+    PHASE_MARK(6);  // store
 }
 
 // ------------------------------------------------------------------ K_G: payload assembly

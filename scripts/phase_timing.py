@@ -17,7 +17,7 @@ NAMES = ["tables", "payload+scan0", "band copy wait", "apply0", "barrier", "coun
 
 
 def main():
-    a = [int(x) for x in sys.argv[1:]]
+    a = [int(x) for x in sys.argv[1:] if not x.startswith('--')]
     n, h, w, bd, T = (a + [512, 512, 512, 16, 96][len(a):])[:5]
     _cabi.lib()
     fn = C.CDLL(_cabi.library_path()).peeb_debug_phases
@@ -41,6 +41,19 @@ def main():
     for _ in range(reps):
         D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm)
     fn(buf, 0)
+    if "--extract" in sys.argv:
+        d_rec = torch.empty_like(d_imgs); d_out = torch.empty((n, stride), dtype=torch.uint8, device=dev)
+        D.pee_extract_device(d_marked, d_lm, T, cap, bd, payload_out=d_out, recovered=d_rec)
+        fn(buf, 1)
+        for _ in range(reps):
+            D.pee_extract_device(d_marked, d_lm, T, cap, bd, payload_out=d_out, recovered=d_rec)
+        fn(buf, 0)
+        names = ["load", "sweep colour 1", "barrier", "sweep colour 0", "barrier", "scan+assemble+stage", "store"]
+        tot = sum(buf[i] for i in range(7))
+        print("extract kernel phases")
+        for i, nm in enumerate(names):
+            print(f"  {nm:22s} {buf[i] / reps:14.0f} total  {100.0 * buf[i] / max(tot, 1):5.1f}%")
+        return
     tot = sum(buf[i] for i in range(13))
     print(f"embed kernel phases, {n}x{h}x{w} bd={bd} T={T}: mean cycles per CTA (thread 0), share")
     for i, nm in enumerate(NAMES):
