@@ -152,10 +152,12 @@ __device__ __forceinline__ int block_scan_runs(int* data, int n, int* warp_sums)
     return total;
 }
 
-// callers synchronise the block before (all pixel writes done)
+// Write-back of band rows, split so that the tail work of a kernel overlaps it.  Callers synchronise
+// the block before store_rows2_issue (all pixel writes done) and call store_rows2_wait before the
+// shared buffer is reused or the kernel ends.
 template <typename PixT>
-__device__ __forceinline__ void store_rows2(const Geom2& g, unsigned char* udst, const unsigned char* simg, int r_first,
-                                            int lo, int hi) {
+__device__ __forceinline__ void store_rows2_issue(const Geom2& g, unsigned char* udst, const unsigned char* simg,
+                                                  int r_first, int lo, int hi) {
     if (hi <= lo) return;
     if (g.bulk) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -164,7 +166,6 @@ __device__ __forceinline__ void store_rows2(const Geom2& g, unsigned char* udst,
             for (int r = lo + warp * 4 + lane; r < hi; r += nwarps * 4)
                 bulk_s2g(udst + (size_t)r * g.rowbytes, simg + row_off(g, r - r_first), (unsigned)g.rowbytes);
             bulk_commit();
-            bulk_wait_read0();
         }
     } else {
         for (int r = lo + (int)(threadIdx.x >> 5); r < hi; r += (int)(blockDim.x >> 5)) {
@@ -172,6 +173,39 @@ __device__ __forceinline__ void store_rows2(const Geom2& g, unsigned char* udst,
             PixT* d = reinterpret_cast<PixT*>(udst + (size_t)r * g.rowbytes);
             for (int c = threadIdx.x & 31; c < g.w; c += 32) d[c] = s[c];
         }
+    }
+}
+__device__ __forceinline__ void store_rows2_wait(const Geom2& g) {
+    if (g.bulk && (threadIdx.x & 31) < 4) bulk_wait_read0();
+}
+
+// Two tables scanned at once (same contract as block_scan_runs; warp_sums: >= 64 ints).
+__device__ __forceinline__ void block_scan_runs2(int* da, int* db, int n, int* warp_sums, int& tota, int& totb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    int sa = 0, sb = 0;
+    for (int k = lo; k < hi; ++k) { sa += da[k]; sb += db[k]; }
+    int ia = sa, ib = sb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (lane == 31) { warp_sums[warp] = ia; warp_sums[32 + warp] = ib; }
+    __syncthreads();
+    int ba = 0, bb = 0;
+    tota = totb = 0;
+    for (int k = 0; k < nwarps; ++k) {
+        const int wa = warp_sums[k], wb = warp_sums[32 + k];
+        if (k < warp) { ba += wa; bb += wb; }
+        tota += wa; totb += wb;
+    }
+    int ra = ba + ia - sa, rb = bb + ib - sb;
+    for (int k = lo; k < hi; ++k) {
+        const int va = da[k], vb = db[k];
+        da[k] = ra; db[k] = rb;
+        ra += va; rb += vb;
     }
 }
 
@@ -489,9 +523,11 @@ struct Apply2 {
         lma = slm + (rowa - lm_row0) * (g.lmpitch >> 2);
     }
     __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
+    // All predictions read the words as loaded (M); results go to a separate copy (O), so the pixels
+    // of a step form independent dependency chains that the scheduler can interleave.
     template <int Q>
-    __device__ __forceinline__ bool fast(uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
-                                         const KE& k, unsigned& W, long long& sse) {
+    __device__ __forceinline__ bool fast(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
+                                         const uint4& D, const KE& k, unsigned& W, long long& sse) {
         bool bad = false;
         static_for<0, P::NS>([&](auto Sc) {
             constexpr int S = decltype(Sc)::value;
@@ -503,13 +539,14 @@ struct Apply2 {
             take_bit(nv, W, q, k.T8);
             const int d = nv - x;
             sse += (long long)d * (long long)d;
-            P::template setx<Q, S>(M, nv);
+            P::template setx<Q, S>(O, nv);
         });
         return bad;
     }
     template <int Q>
-    __device__ __forceinline__ void generic(uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
-                                            const KE& k, int c, unsigned& W, long long& sse, bool own, unsigned* lmrow) {
+    __device__ __forceinline__ void generic(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
+                                            const uint4& D, const KE& k, int c, unsigned& W, long long& sse, bool own,
+                                            unsigned* lmrow) {
         static_for<0, P::NS>([&](auto Sc) {
             constexpr int S = decltype(Sc)::value;
             const int col = c + 2 * S + Q;
@@ -532,7 +569,7 @@ struct Apply2 {
                 atomicOr(lmrow + (col >> 5), lm_bitmask(col));
                 ++st->flagged;
             }
-            P::template setx<Q, S>(M, nv);
+            P::template setx<Q, S>(O, nv);
         });
     }
     template <int QA>
@@ -543,14 +580,14 @@ struct Apply2 {
         const long long sa0 = ssea, sb0 = sseb;
         bool redo = special;
         if (!special) {
-            bool bad = fast<QA>(A, prev, next, U, B0, ka, Wa, ssea);
-            bad |= fast<1 - QA>(B, prev, next, A, D, kb, Wb, sseb);
+            bool bad = fast<QA>(A0, A, prev, next, U, B0, ka, Wa, ssea);
+            bad |= fast<1 - QA>(B0, B, prev, next, A0, D, kb, Wb, sseb);
             redo = __any_sync(0xffffffffu, bad);
         }
         if (redo) {
             A = A0; B = B0; Wa = Wa0; Wb = Wb0; ssea = sa0; sseb = sb0;
-            generic<QA>(A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
-            generic<1 - QA>(B, prev, next, A, D, kb, c, Wb, sseb, ownb, lma + (g.lmpitch >> 2));
+            generic<QA>(A0, A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
+            generic<1 - QA>(B0, B, prev, next, A0, D, kb, c, Wb, sseb, ownb, lma + (g.lmpitch >> 2));
         }
         if (c < g.w) {
             if (sta) sts128(pa, A);
@@ -762,7 +799,10 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         PHASE_MARK(10);  // apply 1
     }
 
-    {
+    __syncthreads();
+    const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
+    if (bt.dst) store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, b_lo, b_hi);
+    {   // statistics and the location map go out while the rows drain
         const long long sse = warp_sum_i64(st.sse);
         const long long fl = warp_sum_i64((long long)st.flagged);
         if ((threadIdx.x & 31) == 0) {
@@ -770,11 +810,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
             if (fl) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)fl);
         }
     }
-    __syncthreads();
-    PHASE_MARK(11);  // stats + barrier
-    const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
-    if (bt.dst) store_rows2<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, b_lo, b_hi);
-    PHASE_MARK(12);  // store
+    PHASE_MARK(11);  // stats
     if (bt.lm) {
         unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw;
         const int nrows = b_hi - b_lo;
@@ -790,6 +826,8 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
                 for (int k = lane; k < g.lmw; k += 32) glm[(size_t)r * g.lmw + k] = sb[(size_t)r * g.lmpitch + k];
         }
     }
+    store_rows2_wait(g);
+    PHASE_MARK(12);  // location map + store drain
 }
 
 // ------------------------------------------------------------------ K_X: extract
@@ -830,8 +868,8 @@ struct Extract2 {
     }
     __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS) || (la | lb) != 0ull; }
     template <int Q, bool SPECIAL>
-    __device__ __forceinline__ void row(uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
-                                        const KX& k, int c, unsigned lmb, unsigned& W, int& n) {
+    __device__ __forceinline__ void row(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
+                                        const uint4& D, const KX& k, int c, unsigned lmb, unsigned& W, int& n) {
         static_for<0, P::NS>([&](auto Sc) {
             constexpr int S = decltype(Sc)::value;
             KX kk = k;
@@ -846,18 +884,19 @@ struct Extract2 {
             const int x = P::template getx<Q, S>(M);
             const int cc = max(min((q + 4) >> 3, kk.T2), 0);                       // clamp(ceil(e'/2), -T, T) + T
             collect_bit(W, n, q, kk.T16);
-            P::template setx<Q, S>(M, x - cc + kk.T);
+            P::template setx<Q, S>(O, x - cc + kk.T);
         });
     }
     template <int QA>
     __device__ __forceinline__ void step(int c, int s, bool special, const uint4& U, uint4& A, uint4& B, const uint4& D,
                                          unsigned prev, unsigned next, unsigned char* pa, unsigned char* pb) {
+        const uint4 A0 = A, B0 = B;  // predictions read the words as loaded: independent chains per pixel
         if (special) {
-            row<QA, true>(A, prev, next, U, B, ka, c, lmbits(la, s), Wa, na);
-            row<1 - QA, true>(B, prev, next, A, D, kb, c, lmbits(lb, s), Wb, nb);
+            row<QA, true>(A0, A, prev, next, U, B0, ka, c, lmbits(la, s), Wa, na);
+            row<1 - QA, true>(B0, B, prev, next, A0, D, kb, c, lmbits(lb, s), Wb, nb);
         } else {
-            row<QA, false>(A, prev, next, U, B, ka, c, 0u, Wa, na);
-            row<1 - QA, false>(B, prev, next, A, D, kb, c, 0u, Wb, nb);
+            row<QA, false>(A0, A, prev, next, U, B0, ka, c, 0u, Wa, na);
+            row<1 - QA, false>(B0, B, prev, next, A0, D, kb, c, 0u, Wb, nb);
         }
         if (c < g.w) {
             if (sta) sts128(pa, A);
@@ -949,34 +988,38 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     __syncthreads();
     PHASE_MARK(4);
 
-    for (int pass = 0; pass < 2; ++pass) {
-        int* cnt = pass == 0 ? tn0 : tn1;
-        const unsigned* tw = pass == 0 ? tw0 : tw1;
-        unsigned* out = stream + (size_t)pass * g.bandwords;
-        // the scan turns counts into bit offsets; a piece's size is the next offset minus its own
-        const int total = block_scan_runs(cnt, n, misc);
-        __syncthreads();
-        for (int k = threadIdx.x; k < n; k += blockDim.x) {
-            const int o = cnt[k];
-            const int cc = (k + 1 < n ? cnt[k + 1] : total) - o;
-            if (cc > 0) {
-                const int sh = o & 31;
-                const unsigned long long v = (unsigned long long)tw[k] << (64 - cc - sh);
-                atomicOr(out + (o >> 5), (unsigned)(v >> 32));
-                if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
-            }
+    // the recovered rows leave while the carrier bits are assembled
+    if (bt.dst)
+        store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
+    // the scans turn counts into bit offsets; a piece's size is the next offset minus its own
+    int total0, total1;
+    block_scan_runs2(tn0, tn1, n, misc, total0, total1);
+    __syncthreads();
+    for (int k2 = threadIdx.x; k2 < 2 * n; k2 += blockDim.x) {
+        const int pass = k2 >= n, k = k2 - pass * n;
+        const int* cnt = pass ? tn1 : tn0;
+        const int o = cnt[k];
+        const int cc = (k + 1 < n ? cnt[k + 1] : (pass ? total1 : total0)) - o;
+        if (cc > 0) {
+            unsigned* out = stream + (size_t)pass * g.bandwords;
+            const int sh = o & 31;
+            const unsigned long long v = (unsigned long long)(pass ? tw1 : tw0)[k] << (64 - cc - sh);
+            atomicOr(out + (o >> 5), (unsigned)(v >> 32));
+            if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        const int total = pass ? total1 : total0;
         const long long slot = ((long long)unit * 2 + pass) * g.nb + band;
         if (threadIdx.x == 0) stage_cnt[slot] = total;
         unsigned* gout = stage_bits + slot * g.bandwords;
+        const unsigned* out = stream + (size_t)pass * g.bandwords;
         const int nw = (total + 31) >> 5;
         for (int k = threadIdx.x; k < nw; k += blockDim.x) gout[k] = out[k];
-        __syncthreads();
     }
     PHASE_MARK(5);  // scans + stream assembly + staging writes
-    if (bt.dst)
-        store_rows2<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
+    store_rows2_wait(g);
     PHASE_MARK(6);  // store
 }
 
