@@ -258,6 +258,9 @@ template <> struct PixOps<unsigned short> {
         unsigned& wv = compr<S>(M);
         wv = __byte_perm(wv, (unsigned)v, Q == 0 ? 0x3254 : 0x5410);
     }
+    template <int Q, int S> static __device__ __forceinline__ int add4x(const uint4& M, int acc) {  // acc + 4x
+        return idp2(comp<S>(M), Q == 0 ? 0x0004u : 0x0400u, acc);
+    }
 };
 template <> struct PixOps<unsigned char> {
     static constexpr int ITEM = 1, NS = 8, PXS = 16;
@@ -287,6 +290,10 @@ template <> struct PixOps<unsigned char> {
         constexpr unsigned sel = B == 0 ? 0x3214u : B == 1 ? 0x3240u : B == 2 ? 0x3410u : 0x4210u;
         unsigned& wv = compr<J>(M);
         wv = __byte_perm(wv, (unsigned)v, sel);
+    }
+    template <int Q, int S> static __device__ __forceinline__ int add4x(const uint4& M, int acc) {  // acc + 4x
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;
+        return idp4(comp<J>(M), 4u << (8 * B), acc);
     }
 };
 
@@ -369,7 +376,8 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
     const int nic = (g.ncol + parts - 1) / parts;
     const int nitems = ngroups * nic;
     for (int item = warp; item < nitems; item += nwarps) {
-        const int grp = item / nic, ic = item - grp * nic;
+        int grp = 0, ic = item;
+        if (ngroups > 1) { grp = item / nic; ic = item - grp * nic; }
         int rowa = row_lo + 2 * (grp * g.rpw + rp);
         int cell = ic * parts + part;
         const bool colv = cell < g.ncol;
@@ -402,6 +410,7 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
             pu += 16; pa += 16; pb += 16; pd += 16;
         }
 #else
+#pragma unroll 1
         for (int s = 0; s < g.cws; ++s) {
             const int c = c0 + s * P::PXS;
             const uint4 U = lds128(pu), D = lds128(pd);
@@ -456,9 +465,9 @@ struct Count2 {
                 const int col = c + 2 * S + Q;
                 kk = make_ke((col >= 1 && col <= g.w - 2) ? k.T : 0);
             }
-            const int q = P::template qsum<Q, S>(M, prev, next, U, D, kk.init);
-            const int x = P::template getx<Q, S>(M);
-            count_if(n, q, kk.T8, x + (q >> 2) + kk.negT, g.maxval);
+            const int q = P::template qsum<Q, S>(M, prev, next, U, D, kk.init);  // 4(e + T) + r, 0 <= r <= 3
+            // 4(x + e) + r = q + 4x - 4T: the carrier value x + e is in [0, maxval) iff that is in [0, 4 maxval)
+            count_if(n, q, kk.T8, P::template add4x<Q, S>(M, q) + 4 * kk.negT, 4 * g.maxval);
         });
     }
     template <int QA>
