@@ -55,6 +55,7 @@ struct Geom2 {
     int bandwords;          // extract staging: 32-bit words per (unit, pass, band)
     int threads;
     int minb;               // CTAs per SM the launch is sized for
+    int lm_direct;          // embed: location-map bits go straight to global memory (no shared copy)
 };
 
 struct Smem2 {
@@ -64,8 +65,10 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 e
     Smem2 L{};
     size_t o = 0;
     L.img = o; o += align_up((size_t)16 + (size_t)(g.R + 5) * g.pitch + 192, 16);
-    L.lm = o; o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
-    L.tab = o; o += align_up((size_t)(g.R + 2) * g.ncol * sizeof(int), 16);
+    L.lm = o;
+    if (kind == 2 || (kind == 1 && !g.lm_direct)) o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
+    L.tab = o;
+    if (kind != 0) o += align_up((size_t)(g.R + 2) * g.ncol * sizeof(int), 16);
     L.misc = o; o += 64 * sizeof(int);
     L.bar = o; o += 16;
     L.pw = L.tn0 = L.tw0 = L.tw1 = L.stream = o;
@@ -508,8 +511,9 @@ struct Apply2 {
     const int* tab;
     const unsigned* pw;
     int bitbase;
-    unsigned* slm;  // location-map rows of the band (row r0 first), lmpitch bytes apart
-    int lm_row0;
+    unsigned* slm;  // location-map rows (row lm_row0 first), lmwords words apart: shared copy of the band, or
+                    // the unit's rows in global memory (null: the caller wants no map)
+    int lm_row0, lmwords;
     Stats2* st;
     KE ka, kb;
     unsigned Wa, Wb;
@@ -529,7 +533,7 @@ struct Apply2 {
         owna = a && rowa >= own_lo && rowa < own_hi;
         ownb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
         ssea = sseb = 0;
-        lma = slm + (rowa - lm_row0) * (g.lmpitch >> 2);
+        lma = slm ? slm + (long long)(rowa - lm_row0) * lmwords : nullptr;
     }
     __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
     // All predictions read the words as loaded (M); results go to a separate copy (O), so the pixels
@@ -575,7 +579,7 @@ struct Apply2 {
             const int d = nv - x;
             sse += (long long)d * (long long)d;
             if (own && !ok && kk.T != 0) {
-                atomicOr(lmrow + (col >> 5), lm_bitmask(col));
+                if (lmrow) atomicOr(lmrow + (col >> 5), lm_bitmask(col));
                 ++st->flagged;
             }
             P::template setx<Q, S>(O, nv);
@@ -596,7 +600,7 @@ struct Apply2 {
         if (redo) {
             A = A0; B = B0; Wa = Wa0; Wb = Wb0; ssea = sa0; sseb = sb0;
             generic<QA>(A0, A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
-            generic<1 - QA>(B0, B, prev, next, A0, D, kb, c, Wb, sseb, ownb, lma + (g.lmpitch >> 2));
+            generic<1 - QA>(B0, B, prev, next, A0, D, kb, c, Wb, sseb, ownb, lma ? lma + lmwords : nullptr);
         }
         if (c < g.w) {
             if (sta) sts128(pa, A);
@@ -722,7 +726,14 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
             all = (int)warp_sum_i64(all);
             if (lane == 0) { misc[41] = before; misc[42] = all; }
         }
-        for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
+        if (!g.lm_direct) {
+            for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
+        } else if (bt.lm) {
+            // flagged pixels are rare: their bits are OR-ed straight into the (zeroed) global rows of this band
+            const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
+            unsigned* glm = reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw);
+            for (int k = threadIdx.x; k < (b_hi - b_lo) * (g.lmw >> 2); k += blockDim.x) glm[k] = 0u;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int k = threadIdx.x + i * blockDim.x;
@@ -733,6 +744,12 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     __syncthreads();
     PHASE_MARK(0);  // tables
     Stats2 st;
+    unsigned* lmbase = slm;
+    int lmrow0 = r0, lmwords = g.lmpitch >> 2;
+    if (g.lm_direct) {
+        lmbase = bt.lm ? reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride) : nullptr;
+        lmrow0 = 0; lmwords = g.lmw >> 2;
+    }
 
     // ---- pass 0 (colour 0): band rows and one halo row on each side
     {
@@ -754,7 +771,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         PHASE_MARK(1);  // payload staging + scan
         wait_rows2(g, s_lo, s_hi, bar);
         PHASE_MARK(2);  // band copy wait
-        Apply2<PixT> body{g, p0_lo, own_lo, own_hi, tab, pw, (int)(B0 & 31u), slm, r0, &st};
+        Apply2<PixT> body{g, p0_lo, own_lo, own_hi, tab, pw, (int)(B0 & 31u), lmbase, lmrow0, lmwords, &st};
         sweep2_colour<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
         PHASE_MARK(3);  // apply 0 (own warp)
     }
@@ -803,7 +820,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         stage_payload(payload, B1, total, n_bits, pw);
         __syncthreads();
         PHASE_MARK(9);  // payload staging
-        Apply2<PixT> body{g, own_lo, own_lo, own_hi, tab, pw, (int)(B1 & 31u), slm, r0, &st};
+        Apply2<PixT> body{g, own_lo, own_lo, own_hi, tab, pw, (int)(B1 & 31u), lmbase, lmrow0, lmwords, &st};
         sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
         PHASE_MARK(10);  // apply 1
     }
@@ -820,7 +837,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         }
     }
     PHASE_MARK(11);  // stats
-    if (bt.lm) {
+    if (bt.lm && !g.lm_direct) {
         unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw;
         const int nrows = b_hi - b_lo;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -1099,7 +1116,7 @@ __global__ void pee2_finalize_kernel(PeeBatch bt) {
 // ------------------------------------------------------------------ host side
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 
-static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int kind, Geom2& g) {
+static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, int kind, bool lm_direct_ok, Geom2& g) {
     PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "pee: itemsize must be 1 or 2");
     PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "pee: bit_depth %d out of range for itemsize %d", bit_depth, itemsize);
     PEEB_REQUIRE(h >= 1 && w >= 1 && (long long)h * w < (1ll << 31), "pee: image size %dx%d unsupported", h, w);
@@ -1110,6 +1127,7 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
     g.pitch = (int)align_up((size_t)g.rowbytes, 128) + 16;
     g.lmw = (w + 7) / 8;
     g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 12;
+    g.lm_direct = (kind == 1 && lm_direct_ok && (g.lmw & 3) == 0 && !getenv("PEEB_LM_SHARED")) ? 1 : 0;
     const int pxs = 16 / itemsize;
     const int nsteps = (g.rowbytes + 15) / 16;
     const size_t sm_total = (size_t)ws->max_smem_optin + 1024;  // 227 KB usable + 1 KB reserved per CTA
@@ -1157,8 +1175,10 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
                 const double fixed = 4096.0;  // per-band latencies (tables, look-back, store) in lane-steps per pass
                 const double useful = (double)R * nsteps;
                 const double warps_sm = (double)cps * threads / 32.0;
-                const double occ = std::pow(std::min(1.0, warps_sm / 24.0), 0.7);
-                const double regpen = (65536 / (cps * threads) < 72) ? 1.3 : 1.0;
+                // fewer, larger CTAs hide each other's barriers and latencies less well than three small ones
+                const double occ = std::pow(std::min(1.0, warps_sm / 24.0), 0.7) * (cps >= 3 ? 1.0 : 0.85);
+                // the embed step spills under ~72 registers per thread; count and extract fit 64
+                const double regpen = (kind == 1 && 65536 / (cps * threads) < 72) ? 1.45 : 1.0;
                 const double score = (work + fixed) / useful / occ * regpen;
                 if (score < best) {
                     best = score; bestg = t; bestg.threads = threads; bestg.minb = cps; found = true;
@@ -1172,6 +1192,8 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
     }
     g = bestg;
     g.nb = (h + g.R - 1) / g.R;
+    g.R = (h + g.nb - 1) / g.nb;  // same number of bands, rows spread evenly
+    g.bandwords = (g.R * ((w + 1) / 2) + 31) / 32 + 2;
     if (getenv("PEEB_DEBUG_GEOM")) {
         static int printed[3] = {0, 0, 0};
         if (printed[kind]++ < 1)
@@ -1222,7 +1244,7 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
                       int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
                       int64_t* info, cudaStream_t st, int slot) {
     Geom2 g;
-    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 1, g);
+    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 1, (((uintptr_t)lm | (uint64_t)lm_stride) & 3) == 0, g);
     if (rc) return rc;
     if (g.bulk && ((((uintptr_t)src) | (uintptr_t)marked | (uint64_t)src_stride | (uint64_t)marked_stride) & 15))
         g.bulk = 0;  // unaligned user buffers: plain copies
@@ -1260,7 +1282,7 @@ int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, 
                         int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,
                         int64_t recovered_stride, int64_t* info, cudaStream_t st, int slot) {
     Geom2 g;
-    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 2, g);
+    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 2, false, g);
     if (rc) return rc;
     if (g.bulk && ((((uintptr_t)marked) | (uintptr_t)recovered | (uint64_t)marked_stride | (uint64_t)recovered_stride) & 15))
         g.bulk = 0;
