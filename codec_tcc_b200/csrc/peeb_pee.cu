@@ -1079,7 +1079,7 @@ static int64_t max_payload_bytes(int n_units, const int64_t* n_bits) {
 // Units per chunk of a host batch: small enough that several chunks overlap their PCIe copies
 // with each other's kernels, large enough to fill the GPU.
 static int chunk_units(int n_units, size_t unit_bytes) {
-    size_t target = 16u << 20;
+    size_t target = 32u << 20;  // B200 + PCIe gen5: 32 MB measured best (scripts/e2e_chunk_sweep.sh); ~40 us of host work per chunk
     if (const char* e = getenv("PEEB_CHUNK_MB")) target = (size_t)atoi(e) << 20;  // tuning experiments
     long long c = (long long)((target + unit_bytes - 1) / unit_bytes);
     if (c < 1) c = 1;
