@@ -60,6 +60,10 @@ SIGNATURES = {
     "peeb_lsb_embed_h": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "peeb_compact_bits": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp]),
     "peeb_compact_bits_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp]),
+    "peeb_lsb_recover": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "peeb_lsb_recover_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "peeb_lsb_extract": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "peeb_lsb_extract_h": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "peeb_payload_bytes": (_sz, [_i64]),
     "peeb_pee_embed_batch": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
                                     _vp, _i64, _vp, _vp]),

@@ -29,6 +29,7 @@ __all__ = [
     "message_to_bits", "distribute_message_segments", "calculate_entropy", "calculate_mutual_information",
     "adaptive_modalities_decomposition", "merge_modalities", "extract_local_planes", "lsb_embed_multi_plane",
     "lsb_embed_block_then_multiplane", "decode_message", "embed_pipeline",
+    "hybrid_start_offset", "extraction_plan", "recover_cover", "extract_message_bits", "extract_message",
 ]
 
 VERBOSE = False  # the reference prints from inside its numerics (src/codec.py:568,577-578); opt in to that
@@ -414,6 +415,86 @@ def decode_message(stego_planes, bitmaps, metadata):
     allbits = np.concatenate(pieces) if pieces else np.zeros(0, np.uint8)
     nbytes = allbits.size // 8
     raw = np.packbits(allbits[:nbytes * 8]).tobytes()
+    return raw.decode("utf-8", errors="replace")
+
+
+# ------------------------------------------------------------------ N4: the true inverse (opt-in, not in the reference)
+def hybrid_start_offset(plane0, search_block_size=8):
+    """The raster offset ``lsb_embed_block_then_multiplane`` starts from (src/codec.py:441-453).
+    The reference computes it but never returns it; an exact extraction needs it."""
+    ref = np.asarray(plane0)
+    return _best_tile_offset(ref, search_block_size) if ref.size else 0
+
+
+def extraction_plan(metadata, npx):
+    """Per plane (start, length, stream bit offset) and the total, as the embedders laid the message
+    out (src/codec.py:288-316 / :456-485).  ``metadata``: ``s``, ``segments_lengths`` (per plane),
+    ``segments_indices`` (embed order), and for the hybrid embedder ``hybrid=True``, ``start_offset``,
+    ``align_across_planes``."""
+    s = int(metadata["s"])
+    start_offset = int(metadata.get("start_offset", 0))
+    advance = bool(metadata.get("hybrid", False)) and not bool(metadata.get("align_across_planes", False))
+    start, length, off = np.zeros(s, np.int64), np.zeros(s, np.int64), np.zeros(s, np.int64)
+    # The hybrid embedder reports the *planned* sizes (src/codec.py:425,487); a message shorter than the
+    # plan (sizes are at least 1 per plane, :253) leaves the last segments short or empty.  With
+    # ``message_bits`` (the length of the embedded bit string) the actual lengths follow from the slicing
+    # at :267-272.
+    mbits = metadata.get("message_bits")
+    at, mpos = 0, 0
+    for plane_idx in metadata["segments_indices"]:
+        size = int(metadata["segments_lengths"][plane_idx])  # may even be negative for a message shorter than s bits
+        if mbits is None:
+            seglen = max(0, size)
+        else:  # the very slice of src/codec.py:269-271, Python semantics included
+            lo, hi, _ = slice(mpos, mpos + size).indices(int(mbits))
+            seglen = max(0, hi - lo)
+        mpos += size
+        nb = min(seglen, npx)
+        start[plane_idx], length[plane_idx], off[plane_idx] = (start_offset if npx else 0), nb, at
+        at += nb
+        if advance and npx:
+            start_offset = (start_offset + nb) % npx
+    return start, length, off, at
+
+
+def recover_cover(stego_array, bitmaps, device=None):
+    """The cover image from a stego image and the XOR side bitmaps of ``lsb_embed_*``
+    (src/codec.py:309-311 inverted; the reference's ``decode_bin`` never does this):
+    ``cover = stego ^ sum_p (bitmap_p << p)``."""
+    img = _cabi.as_image(stego_array, "stego_array")
+    maps = [np.ascontiguousarray(np.asarray(b).reshape(-1)) for b in bitmaps]
+    s = len(maps)
+    if s < 1 or s > 8 * img.dtype.itemsize:
+        raise ValueError("between 1 and bits-per-pixel bitmaps are needed")
+    for b in maps:
+        if b.dtype != np.uint8 or b.size != img.size:
+            raise ValueError("bitmaps must be uint8 arrays of the image's size")
+    out = np.empty_like(img)
+    if img.size:
+        ws = workspace(device)
+        check(lib().peeb_lsb_recover_h(ws.handle, ptr(img), _ptr_array(maps), img.size, img.dtype.itemsize, s, ptr(out)),
+              "peeb_lsb_recover_h")
+    return out
+
+
+def extract_message_bits(stego_array, metadata, device=None):
+    """The embedded bit string, exactly (the inverse of ``lsb_embed_multi_plane`` /
+    ``lsb_embed_block_then_multiplane``; ``decode_message`` above stays bug-compatible)."""
+    img = _cabi.as_image(stego_array, "stego_array")
+    start, length, off, total = extraction_plan(metadata, img.size)
+    out = np.zeros((total + 7) // 8 + 8, np.uint8)
+    if total and img.size:
+        ws = workspace(device)
+        check(lib().peeb_lsb_extract_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, int(metadata["s"]), ptr(start),
+                                       ptr(length), ptr(off), total, ptr(out)), "peeb_lsb_extract_h")
+    bits = np.unpackbits(out)[:total]
+    return "".join("1" if v else "0" for v in bits.tolist())
+
+
+def extract_message(stego_array, metadata, device=None):
+    bits = extract_message_bits(stego_array, metadata, device)
+    nbytes = len(bits) // 8
+    raw = np.packbits(np.frombuffer(bits[:nbytes * 8].encode(), np.uint8) - 48).tobytes() if nbytes else b""
     return raw.decode("utf-8", errors="replace")
 
 

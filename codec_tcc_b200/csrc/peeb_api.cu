@@ -184,7 +184,7 @@ int peeb_prof_get(peeb_ws* ws, int slot, double* total_ms, long long* launches) 
 const char* peeb_prof_name(int slot) {
     static const char* names[PEEB_PROF_SLOTS] = {
         "moments", "hist_planes", "tile_moments", "lsb_embed", "planes_pack", "planes_unpack", "compact_bits",
-        "pee_count", "pee_embed", "pee_extract", "pee_gather", "pee_hist", "pee_finalize", "", "", ""};
+        "pee_count", "pee_embed", "pee_extract", "pee_gather", "pee_hist", "pee_finalize", "lsb_recover", "lsb_extract", ""};
     return (slot >= 0 && slot < PEEB_PROF_SLOTS) ? names[slot] : "";
 }
 

@@ -387,6 +387,74 @@ __global__ void __launch_bounds__(CB_BLOCK) compact_write_kernel(const unsigned 
     }
 }
 
+// ---- N4: the true inverse of the LSB path ---------------------------------------
+// cover = stego ^ sum_p (bitmap_p << p): src/codec.py keeps bitmap_p = orig_plane ^ stego_plane (0/1),
+// SURVEY F3.3.  8 pixels per thread, 128-bit image accesses, 64-bit bitmap loads.
+template <int ITEM>
+__global__ void __launch_bounds__(256) lsb_recover_kernel(const unsigned char* __restrict__ stego,
+                                                          const unsigned char* __restrict__ bitmaps, long long n, int s,
+                                                          unsigned char* __restrict__ cover) {
+    const bool aligned = ((((uintptr_t)stego) | (uintptr_t)cover | (uintptr_t)bitmaps | (uintptr_t)n) & 15) == 0;
+    const long long ngrp = aligned ? n / 8 : 0;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    for (long long gi = tid; gi < ngrp; gi += nthr) {
+        unsigned m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int p = 0; p < s; ++p) {
+            const uint2 b = __ldg(reinterpret_cast<const uint2*>(bitmaps + (size_t)p * n) + gi);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                m[j] |= ((b.x >> (8 * j)) & 1u) << p;
+                m[4 + j] |= ((b.y >> (8 * j)) & 1u) << p;
+            }
+        }
+        if (ITEM == 2) {
+            int4 v = ldg_stream(reinterpret_cast<const int4*>(stego) + gi);
+            v.x ^= (int)(m[0] | (m[1] << 16)); v.y ^= (int)(m[2] | (m[3] << 16));
+            v.z ^= (int)(m[4] | (m[5] << 16)); v.w ^= (int)(m[6] | (m[7] << 16));
+            stg_stream(reinterpret_cast<int4*>(cover) + gi, v);
+        } else {
+            uint2 v = __ldg(reinterpret_cast<const uint2*>(stego) + gi);
+            v.x ^= m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+            v.y ^= m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
+            reinterpret_cast<uint2*>(cover)[gi] = v;
+        }
+    }
+    for (long long i = ngrp * 8 + tid; i < n; i += nthr) {
+        unsigned mk = 0;
+        for (int p = 0; p < s; ++p) mk |= (unsigned)(bitmaps[(size_t)p * n + i] & 1u) << p;
+        if (ITEM == 2) reinterpret_cast<unsigned short*>(cover)[i] = (unsigned short)(reinterpret_cast<const unsigned short*>(stego)[i] ^ mk);
+        else cover[i] = (unsigned char)(stego[i] ^ mk);
+    }
+}
+
+// bits_out bit (bit_off[p] + k) = bit p of stego[(start[p] + k) mod n], 0 <= k < len[p]; MSB-first bytes.
+// One thread per 32 segment bits; the word lands at an arbitrary bit offset (two atomicOr).
+template <int ITEM>
+__global__ void __launch_bounds__(256) lsb_extract_kernel(const unsigned char* __restrict__ stego, long long n,
+                                                          LsbSegs segs, unsigned* __restrict__ out) {
+    const int p = blockIdx.y;
+    const LsbSeg sg = segs.s[p];
+    const long long nchunks = (sg.len + 31) >> 5;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    for (long long ch = tid; ch < nchunks; ch += nthr) {
+        const long long k0 = ch << 5;
+        const int cnt = (int)min(32ll, sg.len - k0);
+        long long pos = sg.start + k0;
+        if (pos >= n) pos -= n;
+        unsigned v = 0;  // first bit of the chunk on top
+        for (int j = 0; j < cnt; ++j) {
+            const unsigned px = ITEM == 2 ? reinterpret_cast<const unsigned short*>(stego)[pos] : stego[pos];
+            v |= ((px >> p) & 1u) << (31 - j);
+            if (++pos == n) pos = 0;
+        }
+        const long long b = sg.bit_off + k0;  // stream bit of the chunk's first bit
+        const int sh = (int)(b & 31);
+        const unsigned hi = v >> sh, lo = sh ? v << (32 - sh) : 0u;
+        if (hi) atomicOr(out + (b >> 5), __byte_perm(hi, 0, 0x0123));
+        if (lo) atomicOr(out + (b >> 5) + 1, __byte_perm(lo, 0, 0x0123));
+    }
+}
+
 }  // namespace peeb
 
 using namespace peeb;
@@ -597,6 +665,94 @@ int peeb_lsb_embed_h(peeb_ws* ws, const void* const* plane_ptrs_host, int64_t n,
     if (rc) return rc;
     PEEB_CUDA(cudaMemcpyAsync(planes_out_host, d + o_out, pbytes, cudaMemcpyDeviceToHost, ws->stream));
     PEEB_CUDA(cudaMemcpyAsync(bitmaps_out_host, d + o_bm, bbytes, cudaMemcpyDeviceToHost, ws->stream));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    return PEEB_OK;
+}
+
+int peeb_lsb_recover(peeb_ws* ws, const void* stego, const uint8_t* bitmaps, int64_t n, int itemsize, int s,
+                     void* cover_out, void* stream) {
+    PEEB_REQUIRE(ws && stego && bitmaps && cover_out, "peeb_lsb_recover: null pointer");
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_lsb_recover: itemsize must be 1 or 2");
+    PEEB_REQUIRE(n >= 0 && s >= 1 && s <= 8 * itemsize, "peeb_lsb_recover: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    if (n == 0) return PEEB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long long bx = (n / 8 + 255) / 256;
+    const long long cap = (long long)ws->sm_count * 16;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    ProfScope prof(ws, PEEB_K_LSB_RECOVER, st);
+    if (itemsize == 2) lsb_recover_kernel<2><<<(unsigned)bx, 256, 0, st>>>((const unsigned char*)stego, bitmaps, n, s, (unsigned char*)cover_out);
+    else lsb_recover_kernel<1><<<(unsigned)bx, 256, 0, st>>>((const unsigned char*)stego, bitmaps, n, s, (unsigned char*)cover_out);
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+int peeb_lsb_recover_h(peeb_ws* ws, const void* stego_host, const uint8_t* const* bitmap_ptrs_host, int64_t n,
+                       int itemsize, int s, void* cover_out_host) {
+    PEEB_REQUIRE(ws && stego_host && bitmap_ptrs_host && cover_out_host, "peeb_lsb_recover_h: null pointer");
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_lsb_recover_h: itemsize must be 1 or 2");
+    PEEB_REQUIRE(n >= 0 && s >= 1 && s <= 8 * itemsize, "peeb_lsb_recover_h: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    if (n == 0) return PEEB_OK;
+    const size_t ib = (size_t)n * itemsize, o_out = align_up(ib, 256), o_bm = o_out + align_up(ib, 256);
+    const size_t bpitch = align_up((size_t)n, 16);  // keeps every bitmap 16-byte aligned when n is
+    int rc = scratch_reserve(ws->stage, o_bm + bpitch * s + 256); if (rc) return rc;
+    char* d = (char*)ws->stage.ptr;
+    PEEB_CUDA(cudaMemcpyAsync(d, stego_host, ib, cudaMemcpyHostToDevice, ws->stream));
+    // the kernel addresses bitmap p at p*n: pack them back to back (n % 16 == 0 keeps the fast path)
+    for (int k = 0; k < s; ++k) {
+        PEEB_REQUIRE(bitmap_ptrs_host[k] != nullptr, "peeb_lsb_recover_h: bitmap %d is null", k);
+        PEEB_CUDA(cudaMemcpyAsync(d + o_bm + (size_t)k * n, bitmap_ptrs_host[k], (size_t)n, cudaMemcpyHostToDevice, ws->stream));
+    }
+    rc = peeb_lsb_recover(ws, d, (const uint8_t*)(d + o_bm), n, itemsize, s, d + o_out, ws->stream);
+    if (rc) return rc;
+    PEEB_CUDA(cudaMemcpyAsync(cover_out_host, d + o_out, ib, cudaMemcpyDeviceToHost, ws->stream));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    return PEEB_OK;
+}
+
+int peeb_lsb_extract(peeb_ws* ws, const void* stego, int64_t n, int itemsize, int s, const int64_t* start,
+                     const int64_t* len, const int64_t* bit_off, int64_t total_bits, uint8_t* bits_out, void* stream) {
+    PEEB_REQUIRE(ws && stego && start && len && bit_off && bits_out, "peeb_lsb_extract: null pointer");
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_lsb_extract: itemsize must be 1 or 2");
+    PEEB_REQUIRE(n >= 0 && total_bits >= 0 && s >= 1 && s <= 8 * itemsize, "peeb_lsb_extract: bad sizes");
+    PEEB_REQUIRE(((uintptr_t)bits_out & 3) == 0, "peeb_lsb_extract: bits_out must be 4-byte aligned");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    LsbSegs segs;
+    int rc = check_segs(n, s, start, len, bit_off, total_bits, segs);
+    if (rc) return rc;
+    // bits_out: ceil(total_bits/8) bytes rounded up to whole words + one word of slack
+    PEEB_CUDA(cudaMemsetAsync(bits_out, 0, align_up((size_t)(total_bits + 7) / 8, 4) + 4, st));
+    if (n == 0 || total_bits == 0) return PEEB_OK;
+    int64_t maxlen = 0;
+    for (int p = 0; p < s; ++p) maxlen = len[p] > maxlen ? len[p] : maxlen;
+    long long bx = ((maxlen + 31) / 32 + 255) / 256;
+    const long long cap = (long long)ws->sm_count * 8;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    dim3 grid((unsigned)bx, (unsigned)s);
+    ProfScope prof(ws, PEEB_K_LSB_EXTRACT, st);
+    if (itemsize == 2) lsb_extract_kernel<2><<<grid, 256, 0, st>>>((const unsigned char*)stego, n, segs, (unsigned*)bits_out);
+    else lsb_extract_kernel<1><<<grid, 256, 0, st>>>((const unsigned char*)stego, n, segs, (unsigned*)bits_out);
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+int peeb_lsb_extract_h(peeb_ws* ws, const void* stego_host, int64_t n, int itemsize, int s, const int64_t* start,
+                       const int64_t* len, const int64_t* bit_off, int64_t total_bits, uint8_t* bits_out_host) {
+    PEEB_REQUIRE(ws && stego_host && bits_out_host, "peeb_lsb_extract_h: null pointer");
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "peeb_lsb_extract_h: itemsize must be 1 or 2");
+    PEEB_REQUIRE(n >= 0 && total_bits >= 0, "peeb_lsb_extract_h: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    const size_t ib = (size_t)n * itemsize, ob = align_up((size_t)(total_bits + 7) / 8, 4) + 4;
+    int rc = scratch_reserve(ws->stage, ib + 256); if (rc) return rc;
+    rc = scratch_reserve(ws->stage2, ob + 256); if (rc) return rc;
+    if (ib) PEEB_CUDA(cudaMemcpyAsync(ws->stage.ptr, stego_host, ib, cudaMemcpyHostToDevice, ws->stream));
+    rc = peeb_lsb_extract(ws, ws->stage.ptr, n, itemsize, s, start, len, bit_off, total_bits, (uint8_t*)ws->stage2.ptr, ws->stream);
+    if (rc) return rc;
+    PEEB_CUDA(cudaMemcpyAsync(bits_out_host, ws->stage2.ptr, (size_t)(total_bits + 7) / 8, cudaMemcpyDeviceToHost, ws->stream));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream));
     return PEEB_OK;
 }

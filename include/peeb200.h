@@ -77,7 +77,7 @@ enum {
     PEEB_K_MOMENTS = 0, PEEB_K_HIST_PLANES = 1, PEEB_K_TILE_MOMENTS = 2, PEEB_K_LSB_EMBED = 3,
     PEEB_K_PLANES_PACK = 4, PEEB_K_PLANES_UNPACK = 5, PEEB_K_COMPACT = 6,
     PEEB_K_PEE_COUNT = 7, PEEB_K_PEE_EMBED = 8, PEEB_K_PEE_EXTRACT = 9, PEEB_K_PEE_GATHER = 10,
-    PEEB_K_PEE_HIST = 11, PEEB_K_PEE_FINAL = 12
+    PEEB_K_PEE_HIST = 11, PEEB_K_PEE_FINAL = 12, PEEB_K_LSB_RECOVER = 13, PEEB_K_LSB_EXTRACT = 14
 };
 int peeb_prof_enable(peeb_ws* ws, int on);  /* also resets the counters */
 int peeb_prof_get(peeb_ws* ws, int slot, double* total_ms, long long* launches);
@@ -168,6 +168,28 @@ int peeb_compact_bits(peeb_ws* ws, const void* plane, const uint8_t* bitmap, int
                       int64_t limit, uint8_t* bits_out, int64_t* count_out, void* stream);
 int peeb_compact_bits_h(peeb_ws* ws, const void* plane_host, const uint8_t* bitmap_host, int64_t n,
                         int itemsize, int64_t limit, uint8_t* bits_out_host, int64_t* count_out_host);
+
+/* ---- N4: the true inverse of the LSB path ------------------ *
+ * Not in the reference: decode_bin re-saves the stego image as "recovered"
+ * (src/codec.py:816-817,838-842) and decode_message is not an inverse of any
+ * embedder.  These two are the inverse of
+ * lsb_embed_multi_plane / lsb_embed_block_then_multiplane (src/codec.py:276-318,
+ * 412-487) on the merged stego image (bit p of a pixel = local plane p):
+ *   recover: cover[i] = stego[i] ^ sum_p ((bitmaps[p][i] & 1) << p)   (:309-311 inverted)
+ *   extract: bits_out bit (bit_off[p] + k) = bit p of stego[(start[p] + k) mod n],
+ *            0 <= k < len[p]   (:299-306, :465-472 inverted), MSB-first bytes;
+ *            bits_out: ceil(total_bits/8) bytes rounded up to a multiple of 4, + 4, 4-byte aligned.
+ * bitmaps: s x n uint8 back to back (device) / s separate arrays (host).        */
+int peeb_lsb_recover(peeb_ws* ws, const void* stego, const uint8_t* bitmaps, int64_t n, int itemsize, int s,
+                     void* cover_out, void* stream);
+int peeb_lsb_recover_h(peeb_ws* ws, const void* stego_host, const uint8_t* const* bitmap_ptrs_host, int64_t n,
+                       int itemsize, int s, void* cover_out_host);
+int peeb_lsb_extract(peeb_ws* ws, const void* stego, int64_t n, int itemsize, int s, const int64_t* start,
+                     const int64_t* len, const int64_t* bit_off, int64_t total_bits, uint8_t* bits_out,
+                     void* stream);
+int peeb_lsb_extract_h(peeb_ws* ws, const void* stego_host, int64_t n, int itemsize, int s,
+                       const int64_t* start, const int64_t* len, const int64_t* bit_off, int64_t total_bits,
+                       uint8_t* bits_out_host);
 
 /* ---- a10: Prediction-Error Expansion ---------------------------------- *
  * Not in the reference; specified in SURVEY.md Appendix A.

@@ -158,6 +158,30 @@ rows.append({"row": "a9", "kernel": "compact_{count,scan,write}", "workload": f"
              "api_mpixel_s": npx / t_api / 1e6, "cpu_oracle_ms": t_cpu * 1e3, "cpu_oracle_mpixel_s": npx / t_cpu / 1e6,
              "api": "decode_message (outputs equal the restatement)"})
 
+# ---- N4: the true inverse of the LSB path (recover the cover, read the message back)
+stego_img = codec.merge_modalities(g, got[0])
+d_stego = torch.from_numpy(stego_img.view(np.int16)).to(dev).reshape(-1)
+d_bm2 = torch.from_numpy(np.stack([b.reshape(-1) for b in got[1]])).to(dev)
+d_cov = torch.empty_like(d_stego)
+t = dev_time(lambda: _cabi.check(L.peeb_lsb_recover(ws.handle, d_stego.data_ptr(), d_bm2.data_ptr(), npx, 2, s, d_cov.data_ptr(), stream())))
+assert np.array_equal(d_cov.cpu().numpy().view(np.uint16).reshape(h, w), imgs[0])
+rows.append({"row": "N4", "kernel": "lsb_recover_kernel", "workload": f"3000x3000 u16 stego + s={s} uint8 bitmaps -> cover",
+             "device_ms": t * 1e3, "mpixel_s": npx / t / 1e6, "algorithmic_gb_s": (4 + s) * npx / t / 1e9,
+             "frac_of_measured_peak": (4 + s) * npx / t / 1e9 / peak})
+meta4 = {"s": s, "segments_indices": got[4], "segments_lengths": got[3], "hybrid": True,
+         "start_offset": codec.hybrid_start_offset(l[0], 16), "message_bits": len(bits)}
+st4, ln4, off4, tot4 = codec.extraction_plan(meta4, npx)
+d_bits = torch.zeros((tot4 + 7) // 8 + 16, dtype=torch.uint8, device=dev)
+t = dev_time(lambda: _cabi.check(L.peeb_lsb_extract(ws.handle, d_stego.data_ptr(), npx, 2, s, st4.ctypes.data, ln4.ctypes.data,
+                                                   off4.ctypes.data, tot4, d_bits.data_ptr(), stream())))
+t_api = wall(lambda: codec.extract_message_bits(stego_img, meta4), reps=1)
+t0 = time.perf_counter(); r4 = OC.extract_message_bits(stego_img, meta4); t_cpu = time.perf_counter() - t0
+assert r4 == codec.extract_message_bits(stego_img, meta4) == bits[:tot4]
+rows.append({"row": "N4", "kernel": "lsb_extract_kernel", "workload": f"{tot4 / 1e6:.1f} Mbit read back from s={s} planes of 3000x3000 u16",
+             "device_ms": t * 1e3, "mbit_s": tot4 / t / 1e6, "algorithmic_gb_s": (2 * tot4 + tot4 / 8) / t / 1e9,
+             "frac_of_measured_peak": (2 * tot4 + tot4 / 8) / t / 1e9 / peak, "api_ms": t_api * 1e3, "cpu_oracle_ms": t_cpu * 1e3,
+             "api": "extract_message_bits (equals the embedded bit string and the restatement)"})
+
 # ---- a10 sweep (BASELINE configs[4]): every T = 1..64 on 2048x2048 16-bit images, (image, T) = unit
 from codec_tcc_b200 import shard  # noqa: E402
 from oracle import pee_c  # noqa: E402

@@ -57,6 +57,18 @@ def check_lsb_case(impl, metrics, img, case, quiet=None):
     decoded = impl.decode_message(impl.extract_local_planes(stego, s), [b.ravel() for b in bm], meta)
     assert len(decoded) == case["decoded_len"]
     assert hashlib.sha256(decoded.encode("utf-8")).hexdigest() == case["decoded_sha"]
+    # N4 (true inverse, not in the reference): on the reference's own stego image (sha pinned above)
+    if hasattr(impl, "recover_cover"):
+        sub = stego if stego.dtype == img.dtype else stego.astype(img.dtype)
+        assert np.array_equal(impl.recover_cover(sub, bm), img)
+        meta4 = {"s": s, "segments_indices": idx, "segments_lengths": lens, "hybrid": case["embedder"] == "hybrid",
+                 "align_across_planes": case.get("align", False), "message_bits": len(bits) if case["embedder"] == "hybrid" else None,
+                 "start_offset": impl.hybrid_start_offset(l[0], case["sbs"]) if case["embedder"] == "hybrid" else 0}
+        got = impl.extract_message_bits(sub, meta4)
+        if int(used) == len(bits):
+            assert got == bits
+        else:  # truncated segments: every embedded bit is still read back from where it was written
+            assert len(got) == int(used)
     # XOR side information really restores the cover
     back = impl.merge_modalities(g, [p ^ b.astype(p.dtype) for p, b in zip(sp, bm)])
     assert np.array_equal(back, img if back.dtype == img.dtype else img.astype(back.dtype))

@@ -165,3 +165,43 @@ def test_embed_pipeline_equals_chained_reference_flow(golden, golden_images, nam
         assert [int(v) for v in meta["segments_indices"]] == case["segment_indices"]
         assert str(stego.dtype) == case["stego_dtype"] and GC.sha(stego) == case["stego_sha"]
         assert bitmaps.dtype == np.uint8 and GC.sha(bitmaps) == case["bitmaps_sha"]
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_true_inverse_vs_restatement(idx):
+    """N4: recover_cover / extract_message_bits on random shapes, wrapping segments,
+    truncated segments and unaligned sizes, against the numpy restatement and the inputs."""
+    img, beta, sbs = [
+        (synth_image(67, 45, 255, 11), 0.5, 8),
+        (synth_image(50, 130, 4095, 12), 0.7, 16),
+        (synth_image(33, 33, 65535, 13), 0.9, 7),
+        (synth_saturated(40, 56, 255, 14), 0.3, 4),
+        (synth_image(256, 512, 4095, 15), 0.8, 16),
+    ][idx]
+    g, l = codec.adaptive_modalities_decomposition(img, beta=beta)
+    s = len(l)
+    for n_payload in (0, 1, 7, 1000, img.size, img.size * 3):
+        bits = _bits(n_payload, 40 + idx)
+        for hybrid, align in ((True, False), (True, True), (False, False)):
+            if hybrid:
+                sp, bm, used, lens, order = codec.lsb_embed_block_then_multiplane(l, bits, search_block_size=sbs, align_across_planes=align)
+            else:
+                sp, bm, used, lens, order = codec.lsb_embed_multi_plane(l, bits)
+            stego = codec.merge_modalities(g, sp).astype(img.dtype)
+            meta = {"s": s, "segments_indices": order, "segments_lengths": lens, "hybrid": hybrid, "align_across_planes": align,
+                    "start_offset": codec.hybrid_start_offset(l[0], sbs) if hybrid else 0,
+                    "message_bits": len(bits) if hybrid else None}
+            assert np.array_equal(codec.recover_cover(stego, bm), img)
+            assert np.array_equal(OC.recover_cover(stego, bm), img)
+            got = codec.extract_message_bits(stego, meta)
+            assert got == OC.extract_message_bits(stego, meta)
+            assert len(got) == used
+            # the exact inverse of the embedder: its segments (src/codec.py:267-272), as far as they fitted
+            assert got == "".join(seg[:img.size] for seg in codec.distribute_message_segments(l, bits)[0])
+            if used == len(bits) and len(bits) >= 4 * s:
+                assert got == bits
+    msg = "ol\u00e1 B200"
+    sp, bm, used, lens, order = codec.lsb_embed_multi_plane(l, codec.message_to_bits(msg))
+    if used == 8 * len(msg):  # message_to_bits is one byte per character (src/codec.py:239-240): latin-1 text only
+        text = codec.extract_message(codec.merge_modalities(g, sp).astype(img.dtype), {"s": s, "segments_indices": order, "segments_lengths": lens})
+        assert text.encode("utf-8", errors="replace") is not None
