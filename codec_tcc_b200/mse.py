@@ -22,6 +22,7 @@ from fractions import Fraction
 import numpy as np
 
 from . import _cabi
+from . import dicom_raw
 from ._cabi import MOMENTS, check, lib, ptr, workspace
 
 __all__ = ["AnalisadorMSE", "image_moments"]
@@ -35,8 +36,9 @@ def _as_pixels(img, name):
     (src/mse.py:85) for the integer inputs the device path supports."""
     if isinstance(img, str):
         raise NotImplementedError(
-            "file paths go through the reference's DICOM/PIL loader (src/mse.py:13-72), which is host I/O "
-            "outside this package; load the pixels and pass the array")
+            "only uncompressed .dcm paths are read here (codec_tcc_b200.dicom_raw); other files go through the "
+            "reference's pydicom/PIL loader (src/mse.py:13-72), which is host I/O outside this package: load the "
+            "pixels and pass the array")
     a = np.asarray(img)
     if a.dtype in (np.uint8, np.uint16):
         return np.ascontiguousarray(a)
@@ -57,6 +59,15 @@ def _as_pixels(img, name):
 def image_moments(img1, img2, device=None, full=True) -> dict:
     """The twelve integers (see module docstring) as Python ints.  ``full=False``
     runs the lighter SSE-only kernel: only sse, max_a, max_b and n are filled."""
+    # file paths: the reference takes the value range from the file (2**BitsStored - 1) instead of the
+    # array maximum (src/mse.py:82-84 vs :85-87); uncompressed .dcm files are read without pydicom
+    ra = rb = None
+    if isinstance(img1, str) and img1.lower().endswith(".dcm"):
+        img1, info = dicom_raw.read_pixels(img1)
+        ra = (1 << info["BitsStored"]) - 1
+    if isinstance(img2, str) and img2.lower().endswith(".dcm"):
+        img2, info = dicom_raw.read_pixels(img2)
+        rb = (1 << info["BitsStored"]) - 1
     a = _as_pixels(img1, "img1")
     b = _as_pixels(img2, "img2")
     if a.shape != b.shape:
@@ -70,7 +81,12 @@ def image_moments(img1, img2, device=None, full=True) -> dict:
     ws = workspace(device)
     fn = lib().peeb_moments_h if full else lib().peeb_sse_h
     check(fn(ws.handle, ptr(a), ptr(b), a.size, a.dtype.itemsize, ptr(out)), "peeb_moments_h")
-    return {k: int(v) for k, v in zip(_KEYS, out)}
+    m = {k: int(v) for k, v in zip(_KEYS, out)}
+    if ra is not None:
+        m["max_a"] = ra
+    if rb is not None:
+        m["max_b"] = rb
+    return m
 
 
 def _scales(m):
@@ -94,6 +110,12 @@ class AnalisadorMSE:
     def __init__(self, device=None):
         self.resultados = []
         self._device = device
+
+    def carregar_imagem(self, caminho):
+        """src/mse.py:13-37 for uncompressed .dcm files: ``(float64 array, max_valor, bits_stored)``."""
+        if not caminho.lower().endswith(".dcm"):
+            raise NotImplementedError("only uncompressed .dcm files are read without the reference's PIL loader (src/mse.py:39-72)")
+        return dicom_raw.carregar_imagem(caminho)
 
     # -- a1 ---------------------------------------------------------------
     def calcular_mse(self, imagem1, imagem2):
