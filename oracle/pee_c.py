@@ -33,6 +33,10 @@ def lib():
         L.pee_ref_extract_batch.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, i64, vp, i32]
         L.pee_ref_extract_batch.restype = i32
         L.pee_ref_threads.restype = i32
+        L.pee_med_ref_embed.argtypes = [vp, i32, i32, i32, i64, i32, vp, i64, vp, vp, vp]
+        L.pee_med_ref_embed.restype = i32
+        L.pee_med_ref_extract.argtypes = [vp, i32, i32, i32, i32, vp, i64, vp, vp]
+        L.pee_med_ref_extract.restype = i32
         _lib = L
     return _lib
 
@@ -46,9 +50,9 @@ def _maxval(img, bit_depth):
     return bd, (1 << bd) - 1
 
 
-def embed(img, payload_packed, n_bits, T, bit_depth=None):
+def embed(img, payload_packed, n_bits, T, bit_depth=None, predictor="rhombus"):
     """-> (marked, lm_packed, info dict incl. 'status').  Does not raise on
-    overflow; status == -2 then."""
+    overflow; status == -2 then.  predictor: "rhombus" (Appendix A) or "med" (causal, N1)."""
     img = np.ascontiguousarray(img)
     h, w = img.shape
     _, maxval = _maxval(img, bit_depth)
@@ -60,19 +64,19 @@ def embed(img, payload_packed, n_bits, T, bit_depth=None):
     marked = np.empty_like(img)
     lm = np.empty((h, (w + 7) // 8), np.uint8)
     info = np.zeros(8, np.int64)
-    lib().pee_ref_embed(_p(img), h, w, img.dtype.itemsize, maxval, int(T), _p(pay), int(n_bits),
-                        _p(marked), _p(lm), _p(info))
+    fn = lib().pee_med_ref_embed if predictor == "med" else lib().pee_ref_embed
+    fn(_p(img), h, w, img.dtype.itemsize, maxval, int(T), _p(pay), int(n_bits), _p(marked), _p(lm), _p(info))
     return marked, lm, dict(zip(INFO_KEYS, (int(v) for v in info)))
 
 
-def extract(marked, lm_packed, T, n_bits):
+def extract(marked, lm_packed, T, n_bits, predictor="rhombus"):
     marked = np.ascontiguousarray(marked)
     h, w = marked.shape
     lm = np.ascontiguousarray(lm_packed, dtype=np.uint8)
     out = np.zeros(max(1, (n_bits + 7) // 8), np.uint8)
     rec = np.empty_like(marked)
-    rc = lib().pee_ref_extract(_p(marked), h, w, marked.dtype.itemsize, int(T), _p(lm), int(n_bits),
-                               _p(out), _p(rec))
+    fn = lib().pee_med_ref_extract if predictor == "med" else lib().pee_ref_extract
+    rc = fn(_p(marked), h, w, marked.dtype.itemsize, int(T), _p(lm), int(n_bits), _p(out), _p(rec))
     if rc != 0:
         raise ValueError("n_bits exceeds the number of carriers found")
     return out[: (n_bits + 7) // 8], rec

@@ -235,3 +235,52 @@ def pee_sweep(img, payload, T_values, bit_depth=None, n_bits=None):
         rows.append({"T": int(T), "capacity": cap0 + cap1, "cap0": cap0, "cap1": cap1,
                      "n_flagged": int(lm.sum()), "sse": sse, "mse": mse, "psnr": float(psnr)})
     return rows
+
+
+# --------------------------------------------------------------------------
+# N1: causal MED predictor, DESIGN.md "Appendix A2" -- *** PARITY UNPINNED ***.
+# Second, vectorised formulation of oracle/pee_ref.c:pee_med_ref_embed (masks + cumsum); the embedder
+# predicts from the ORIGINAL pixels, so it needs no sequential walk.  Extraction is inherently
+# sequential (it predicts from recovered pixels): only the C oracle restates it.
+# --------------------------------------------------------------------------
+def med_predict(img64):
+    """MED (JPEG-LS) prediction for pixels (1.., 1..) of an int64 image: a = W, b = N, c = NW."""
+    a, b, c = img64[1:, :-1], img64[:-1, 1:], img64[:-1, :-1]
+    return np.clip(a + b - c, np.minimum(a, b), np.maximum(a, b))
+
+
+def med_embed(img, payload, T, bit_depth=None, n_bits=None):
+    """-> (marked, lm_packed, info) like the C oracle (no exception on overflow: info['status'] = -2)."""
+    img = np.ascontiguousarray(img)
+    h, w = img.shape
+    _, maxval = _maxval(img, bit_depth)
+    bits = payload_to_bits(payload, n_bits)
+    n_bits = bits.size
+    cur = img.astype(np.int64)
+    lm = np.zeros((h, w), np.uint8)
+    cap = 0
+    if h >= 2 and w >= 2:
+        x = cur[1:, 1:]
+        p = med_predict(cur)
+        e = x - p
+        expd = (e >= -T) & (e < T)
+        v = p + 2 * e
+        flag = np.where(expd, (v < 0) | (v + 1 > maxval), np.where(e >= T, x + T > maxval, x - T < 0))
+        carrier = expd & ~flag
+        rank = np.cumsum(carrier.reshape(-1)) - 1          # raster order
+        cap = int(carrier.sum())
+        padded = np.zeros(max(cap, 1), np.int64)
+        padded[:min(cap, n_bits)] = bits[:min(cap, n_bits)]
+        b = np.where(carrier.reshape(-1), padded[np.clip(rank, 0, None)], 0).reshape(x.shape)
+        y = np.where(flag, x, np.where(expd, v + b, np.where(e >= T, x + T, x - T)))
+        out = cur.copy()
+        out[1:, 1:] = y
+        lm[1:, 1:] = flag
+        cur_out = out
+    else:
+        cur_out = cur
+    marked = cur_out.astype(img.dtype)
+    sse = int(((cur_out - cur) ** 2).sum())
+    info = {"T": int(T), "n_bits": int(n_bits), "capacity": cap, "cap0": cap, "cap1": 0, "n_flagged": int(lm.sum()),
+            "sse": sse, "status": -2 if n_bits > cap else 0}
+    return marked, np.packbits(lm, axis=1), info

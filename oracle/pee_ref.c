@@ -190,3 +190,81 @@ int pee_ref_threads(void)
     return 1;
 #endif
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * N1: the causal predictor family.  DESIGN.md "Appendix A2" -- *** PARITY UNPINNED ***.
+ * MED predictor (JPEG-LS): a = W, b = N, c = NW, p = clamp(a + b - c, min(a,b), max(a,b)).
+ * Domain: 1 <= i < h, 1 <= j < w (row 0 and column 0 never change).  ONE pass in raster order;
+ * the embedder predicts from ORIGINAL pixels (so it is fully parallel), the extractor from the
+ * pixels it has already recovered (W, N, NW come earlier in raster order: anti-diagonal wavefront).
+ * Classes, flags, carrier rule and zero padding are those of Appendix A; info cap0 = capacity, cap1 = 0.
+ * ------------------------------------------------------------------------------------------------ */
+static inline int64_t med_predict(int64_t a, int64_t b, int64_t c) {
+    const int64_t lo = a < b ? a : b, hi = a < b ? b : a;
+    int64_t p = a + b - c;
+    if (p < lo) p = lo;
+    if (p > hi) p = hi;
+    return p;
+}
+
+int pee_med_ref_embed(const void* img, int h, int w, int itemsize, int64_t maxval, int T,
+                      const uint8_t* payload, int64_t n_bits, void* marked, uint8_t* lm_packed, int64_t* info)
+{
+    const int lmw = (w + 7) / 8;
+    memcpy(marked, img, (size_t)h * w * itemsize);
+    memset(lm_packed, 0, (size_t)h * lmw);
+    int64_t cap = 0, flagged = 0, sse = 0, next_bit = 0;
+    for (int i = 1; i < h; ++i)
+        for (int j = 1; j < w; ++j) {
+            const int64_t at = (int64_t)i * w + j;
+            const int64_t x = px_get(img, itemsize, at);
+            const int64_t p = med_predict(px_get(img, itemsize, at - 1), px_get(img, itemsize, at - w),
+                                          px_get(img, itemsize, at - w - 1));
+            const int64_t e = x - p;
+            int64_t y = x;
+            int flag = 0;
+            if (e >= -T && e < T) {
+                const int64_t v = p + 2 * e;
+                if (v < 0 || v + 1 > maxval) flag = 1;
+                else { y = v + payload_bit(payload, n_bits, next_bit); ++next_bit; ++cap; }
+            } else if (e >= T) {
+                if (x + T > maxval) flag = 1; else y = x + T;
+            } else {
+                if (x - T < 0) flag = 1; else y = x - T;
+            }
+            if (flag) { lm_packed[(int64_t)i * lmw + (j >> 3)] |= (uint8_t)(0x80u >> (j & 7)); ++flagged; }
+            px_set(marked, itemsize, at, y);
+            sse += (y - x) * (y - x);
+        }
+    info[0] = T; info[1] = n_bits; info[2] = cap; info[3] = cap; info[4] = 0;
+    info[5] = flagged; info[6] = sse; info[7] = (n_bits > cap) ? -2 : 0;
+    return (int)info[7];
+}
+
+int pee_med_ref_extract(const void* marked, int h, int w, int itemsize, int T, const uint8_t* lm_packed,
+                        int64_t n_bits, uint8_t* payload_out, void* recovered)
+{
+    const int lmw = (w + 7) / 8;
+    memcpy(recovered, marked, (size_t)h * w * itemsize);
+    memset(payload_out, 0, (size_t)((n_bits + 7) / 8));
+    int64_t k = 0;
+    for (int i = 1; i < h; ++i)
+        for (int j = 1; j < w; ++j) {
+            if (lm_packed[(int64_t)i * lmw + (j >> 3)] & (0x80u >> (j & 7))) continue;
+            const int64_t at = (int64_t)i * w + j;
+            const int64_t x = px_get(recovered, itemsize, at);
+            const int64_t p = med_predict(px_get(recovered, itemsize, at - 1), px_get(recovered, itemsize, at - w),
+                                          px_get(recovered, itemsize, at - w - 1));
+            const int64_t ee = x - p;
+            int64_t e;
+            if (ee >= -2 * (int64_t)T && ee < 2 * (int64_t)T) {
+                if (k < n_bits && (ee & 1)) payload_out[k >> 3] |= (uint8_t)(0x80u >> (k & 7));
+                ++k;
+                e = ee >> 1;
+            } else if (ee >= 2 * (int64_t)T) e = ee - T;
+            else e = ee + T;
+            px_set(recovered, itemsize, at, p + e);
+        }
+    return n_bits > k ? -2 : 0;
+}
