@@ -73,6 +73,12 @@ SIGNATURES = {
     "peeb_pee_embed_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "peeb_pee_extract_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "peeb_pee_hist_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "peeb_pee_med_embed_batch": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
+                                        _vp, _i64, _vp, _vp]),
+    "peeb_pee_med_extract_batch": (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64,
+                                          _vp, _i64, _vp, _vp]),
+    "peeb_pee_med_embed_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "peeb_pee_med_extract_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,507 @@
+// N1: the causal predictor family of Prediction-Error Expansion -- DESIGN.md "Appendix A2".
+//
+//   predictor  MED (JPEG-LS): a = W, b = N, c = NW, p = clamp(a + b - c, min(a, b), max(a, b));
+//   domain     1 <= i < h, 1 <= j < w (row 0 and column 0 never change), ONE pass in raster order;
+//   classes, overflow flags, carrier rule, zero padding: as in Appendix A (peeb_pee2.cu).
+//
+// Embedding predicts from ORIGINAL pixels, so it is embarrassingly parallel: a count kernel, a scan of
+// the per-(row, 256-column chunk) counts and an apply kernel, all streaming from global memory.
+//
+// Extraction predicts from pixels it has already RECOVERED (W, N, NW): an anti-diagonal wavefront.
+// One CTA per image; a warp owns 32 consecutive rows (lane = row) and runs them skewed by one column
+// per lane, so the N / NW neighbours of a lane are what the lane above produced one and two
+// iterations earlier (two shuffles).  Consecutive 32-row groups are pipelined through the warps of
+// the CTA: the last row of a group goes to a shared-memory line buffer with a progress counter that
+// the first lane of the next group polls.  Carrier bits are collected MSB-first per row and
+// concatenated at the end by the same CTA.
+#include <algorithm>
+#include <cstdlib>
+
+#include "peeb_common.cuh"
+#include "peeb_pee.cuh"
+
+namespace peeb {
+
+constexpr int MCHUNK = 256;  // pixels per warp item (8 per lane)
+
+struct MedGeom {
+    int h, w, itemsize, maxval;
+    int nchunk;  // chunks per row
+    int lmw;
+    int rw;      // extract staging: 32-bit words per row
+};
+
+__device__ __forceinline__ int med3(int a, int b, int c) {
+    const int lo = min(a, b), hi = max(a, b);
+    return max(min(a + b - c, hi), lo);
+}
+
+// eight pixels of a row starting at column j0 (0 beyond the row end); vector load when the rows are aligned
+template <typename PixT>
+__device__ __forceinline__ void load8(const PixT* row, int j0, int w, bool vec, int (&v)[8]) {
+    if (vec && j0 + 8 <= w) {
+        if (sizeof(PixT) == 2) {
+            const uint4 q = *reinterpret_cast<const uint4*>(row + j0);
+            v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+            v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+        } else {
+            const uint2 q = *reinterpret_cast<const uint2*>(row + j0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[k] = (q.x >> (8 * k)) & 0xff; v[4 + k] = (q.y >> (8 * k)) & 0xff; }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = j0 + k < w ? (int)row[j0 + k] : 0;
+    }
+}
+template <typename PixT>
+__device__ __forceinline__ void store8(PixT* row, int j0, int w, bool vec, const int (&v)[8]) {
+    if (vec && j0 + 8 <= w) {
+        if (sizeof(PixT) == 2) {
+            uint4 q;
+            q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16);
+            *reinterpret_cast<uint4*>(row + j0) = q;
+        } else {
+            uint2 q;
+            q.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+            q.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24);
+            *reinterpret_cast<uint2*>(row + j0) = q;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (j0 + k < w) row[j0 + k] = (PixT)v[k];
+    }
+}
+
+// One warp item = (unit, row, chunk); lane -> 8 pixels.  APPLY = false: count carriers of the chunk;
+// APPLY = true: write marked pixels, the location-map byte of every 8 columns, SSE / flag statistics.
+template <typename PixT, bool APPLY>
+__global__ void __launch_bounds__(256) med_embed_kernel(MedGeom g, PeeBatch bt, unsigned short* __restrict__ cnt,
+                                                        const unsigned* __restrict__ off) {
+    const int lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long per_unit = (long long)g.h * g.nchunk;
+    if (item >= per_unit * bt.n_units) return;
+    const int unit = (int)(item / per_unit);
+    const int rem = (int)(item - (long long)unit * per_unit);
+    const int row = rem / g.nchunk, chunk = rem - row * g.nchunk;
+    const unsigned char* ubase = bt.src + (long long)unit * bt.src_stride;
+    const PixT* cur = reinterpret_cast<const PixT*>(ubase) + (size_t)row * g.w;
+    const bool vec_in = ((((uintptr_t)ubase) | ((uintptr_t)g.w * sizeof(PixT))) & (8 * sizeof(PixT) - 1)) == 0;
+    const int j0 = chunk * MCHUNK + 8 * lane;
+    const int T = bt.T[unit];
+    int x[8], nv[8];
+    load8<PixT>(cur, j0, g.w, vec_in, x);
+    int ncar = 0, nflag = 0;
+    unsigned carmask = 0, lmbyte = 0;
+    long long sse = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) nv[k] = x[k];
+    if (row >= 1) {
+        int up[8];
+        load8<PixT>(cur - g.w, j0, g.w, vec_in, up);
+        // W / NW of the lane's first pixel: the previous lane's last pixel (lane 0: one scalar load each)
+        int left = __shfl_up_sync(0xffffffffu, x[7], 1), upleft = __shfl_up_sync(0xffffffffu, up[7], 1);
+        if (lane == 0 && j0 > 0) { left = cur[j0 - 1]; upleft = cur[j0 - 1 - g.w]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = j0 + k;
+            const int a = k ? x[k - 1] : left, c = k ? up[k - 1] : upleft;
+            if (j >= 1 && j < g.w) {
+                const int t = x[k] - med3(a, up[k], c) + T;                      // e + T
+                const bool expd = (unsigned)t < (unsigned)(2 * T);               // -T <= e < T
+                const int nv0 = x[k] + max(min(t, 2 * T), 0) - T;                // x + e | x + T | x - T
+                const bool ok = (unsigned)nv0 <= (unsigned)g.maxval - (expd ? 1u : 0u);
+                if (expd && ok) { ++ncar; carmask |= 1u << k; }
+                if (ok) nv[k] = nv0; else { lmbyte |= 0x80u >> k; ++nflag; }
+            }
+        }
+    }
+    if (!APPLY) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ncar += __shfl_xor_sync(0xffffffffu, ncar, o);
+        if (lane == 0) cnt[item] = (unsigned short)ncar;
+        return;
+    }
+    // rank of the lane's first carrier inside the chunk, then the chunk's offset in the unit's raster order
+    int incl = ncar;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (ncar) {
+        const unsigned n_bits = bt.n_bits[unit];
+        const unsigned* pay = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
+        const unsigned base = off[item] + (unsigned)(incl - ncar);
+        unsigned win = 0;  // bits base .. base+7 on top, zero past n_bits
+        if (base < n_bits) {
+            const unsigned w0 = __byte_perm(__ldg(pay + (base >> 5)), 0, 0x0123), w1 = __byte_perm(__ldg(pay + (base >> 5) + 1), 0, 0x0123);
+            win = __funnelshift_l(w1, w0, base & 31);
+            if (n_bits - base < 32u) win &= ~(0xffffffffu >> (n_bits - base));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (carmask & (1u << k)) { nv[k] += (int)(win >> 31); win <<= 1; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const int d = nv[k] - x[k]; sse += (long long)d * d; }
+    if (bt.dst) {
+        unsigned char* obase = bt.dst + (long long)unit * bt.dst_stride;
+        const bool vec_out = ((((uintptr_t)obase) | ((uintptr_t)g.w * sizeof(PixT))) & (8 * sizeof(PixT) - 1)) == 0;
+        store8<PixT>(reinterpret_cast<PixT*>(obase) + (size_t)row * g.w, j0, g.w, vec_out, nv);
+    }
+    if (bt.lm && j0 < g.w) bt.lm[(long long)unit * bt.lm_stride + (size_t)row * g.lmw + (j0 >> 3)] = (unsigned char)lmbyte;
+    sse = warp_sum_i64(sse);
+    nflag = (int)warp_sum_i64(nflag);
+    if (lane == 0) {
+        long long* info = bt.info + (long long)unit * PEEB_INFO;
+        if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(info + 6), (unsigned long long)sse);
+        if (nflag) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)nflag);
+    }
+}
+
+// one CTA per unit: exclusive scan of the chunk counts (raster order), capacity into info
+__global__ void __launch_bounds__(1024) med_scan_kernel(MedGeom g, PeeBatch bt, const unsigned short* __restrict__ cnt,
+                                                        unsigned* __restrict__ off) {
+    __shared__ int ws[33];
+    const int unit = blockIdx.x;
+    const long long ne = (long long)g.h * g.nchunk;
+    const unsigned short* c = cnt + unit * ne;
+    unsigned* o = off + unit * ne;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned carry = 0;
+    for (long long base = 0; base < ne; base += blockDim.x) {
+        const long long idx = base + threadIdx.x;
+        const int v = idx < ne ? c[idx] : 0;
+        int incl = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += t;
+        }
+        if (lane == 31) ws[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int x = ws[lane];
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, x, s);
+                if (lane >= s) x += t;
+            }
+            ws[lane] = x;
+            if (lane == 31) ws[32] = x;
+        }
+        __syncthreads();
+        if (idx < ne) o[idx] = carry + (unsigned)((warp ? ws[warp - 1] : 0) + incl - v);
+        carry += (unsigned)ws[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        long long* info = bt.info + (long long)unit * PEEB_INFO;
+        info[0] = bt.T[unit]; info[1] = bt.n_bits[unit]; info[2] = carry; info[3] = carry; info[4] = 0;
+        info[7] = ((long long)bt.n_bits[unit] > (long long)carry) ? PEEB_E_CAPACITY : 0;
+    }
+}
+
+// ------------------------------------------------------------------ wavefront extract
+struct MedSmem {
+    size_t line, prog, rowoff, misc, total;
+};
+__host__ __device__ inline MedSmem med_layout(const MedGeom& g, int nwarps) {
+    MedSmem L{};
+    size_t o = 0;
+    L.line = o; o += align_up((size_t)(nwarps + 1) * g.w * sizeof(unsigned short), 16);
+    L.prog = o; o += align_up((size_t)(nwarps + 1) * sizeof(int), 16);
+    L.rowoff = o; o += align_up((size_t)(g.h + 1) * sizeof(int), 16);
+    L.misc = o; o += 64 * sizeof(int);
+    L.total = o;
+    return L;
+}
+
+template <typename PixT>
+__global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const MedSmem L = med_layout(g, nwarps);
+    unsigned short* line = reinterpret_cast<unsigned short*>(smem_raw + L.line);
+    volatile int* prog = reinterpret_cast<volatile int*>(smem_raw + L.prog);
+    int* rowoff = reinterpret_cast<int*>(smem_raw + L.rowoff);
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    const int unit = blockIdx.x, h = g.h, w = g.w, nslot = nwarps + 1;
+    const PixT* marked = reinterpret_cast<const PixT*>(bt.src + (long long)unit * bt.src_stride);
+    PixT* rec = bt.dst ? reinterpret_cast<PixT*>(bt.dst + (long long)unit * bt.dst_stride) : nullptr;
+    const unsigned char* lm = bt.lm + (long long)unit * bt.lm_stride;
+    unsigned* stage = stage_bits + (long long)unit * h * g.rw;
+    const int T = bt.T[unit];
+    for (int k = threadIdx.x; k <= h; k += blockDim.x) rowoff[k] = 0;
+    for (int k = threadIdx.x; k < nslot; k += blockDim.x) prog[k] = -1;
+    if (rec) for (int j = threadIdx.x; j < w; j += blockDim.x) rec[j] = marked[j];  // row 0 never changes
+    __syncthreads();
+
+    const int ngroups = (h - 1 + 31) / 32;
+    for (int grp = warp; grp < ngroups; grp += nwarps) {
+        const int rowi = 1 + 32 * grp + lane;
+        const bool valid = rowi < h;
+        const int lastl = min(31, h - 2 - 32 * grp);  // last lane that owns a row
+        const PixT* mrow = marked + (size_t)(valid ? rowi : 1) * w;
+        PixT* rrow = rec ? rec + (size_t)(valid ? rowi : 1) * w : nullptr;
+        const unsigned char* lrow = lm + (size_t)(valid ? rowi : 1) * g.lmw;
+        unsigned* srow = stage + (size_t)(valid ? rowi : 1) * g.rw;
+        unsigned short* myline = line + (size_t)(grp % nslot) * w;
+        const unsigned short* upline = line + (size_t)((grp + nslot - 1) % nslot) * w;
+        const int upslot = (grp + nslot - 1) % nslot, myslot = grp % nslot;
+        const int upbase = (grp - 1) * (w + 1), mybase = grp * (w + 1);
+        int cur1 = 0, cur2 = 0, aprev = 0, bprev0 = 0;
+        unsigned W = 0, lmbyte = 0;
+        int nW = 0, nwords = 0, ncar = 0;
+        for (int t = 0; t < w + 31; ++t) {
+            const int j = t - lane;
+            int b = __shfl_up_sync(0xffffffffu, cur1, 1), c = __shfl_up_sync(0xffffffffu, cur2, 1);
+            if (lane == 0 && j < w) {
+                int bnew;
+                if (grp == 0) bnew = marked[j];  // row 0
+                else {
+                    while (prog[upslot] < upbase + j + 1) {}
+                    bnew = reinterpret_cast<const volatile unsigned short*>(upline)[j];
+                }
+                c = bprev0; b = bnew; bprev0 = bnew;
+            }
+            __syncwarp();
+            if (valid && j >= 0 && j < w) {
+                const int x = mrow[j];
+                int val = x;
+                if (j >= 1) {
+                    if ((j & 7) == 0 || j == 1) lmbyte = lrow[j >> 3];
+                    const int Tl = ((lmbyte >> (7 - (j & 7))) & 1u) ? 0 : T;       // flagged pixels were left alone
+                    const int u = x - med3(aprev, b, c) + 2 * Tl;                  // e' + 2T
+                    const int cc = max(min((u + 1) >> 1, 2 * Tl), 0);              // clamp(ceil(e'/2), -T, T) + T
+                    val = x - cc + Tl;
+                    if ((unsigned)u < (unsigned)(4 * Tl)) {                        // carrier: -2T <= e' < 2T
+                        W = (W << 1) | (unsigned)(u & 1);
+                        ++ncar;
+                        if (++nW == 32) { srow[nwords++] = W; nW = 0; W = 0; }
+                    }
+                }
+                if (rrow) rrow[j] = (PixT)val;
+                cur2 = cur1; cur1 = val; aprev = val;
+                if (lane == lastl) {
+                    myline[j] = (unsigned short)val;
+                    __threadfence_block();
+                    prog[myslot] = mybase + j + 1;
+                }
+            }
+        }
+        if (valid) {
+            if (nW) srow[nwords] = W << (32 - nW);
+            rowoff[rowi] = ncar;
+        }
+    }
+    __syncthreads();
+
+    // ---- concatenate the rows' bit streams (raster order) into the unit's payload, MSB-first
+    const int total = block_excl_scan(rowoff, h, misc);
+    __syncthreads();
+    const long long n_bits = bt.n_bits[unit];
+    if (threadIdx.x == 0) {
+        long long* info = bt.info + (long long)unit * PEEB_INFO;
+        info[0] = T; info[1] = n_bits; info[2] = total; info[3] = total; info[4] = 0; info[5] = 0; info[6] = 0;
+        info[7] = n_bits > total ? PEEB_E_CAPACITY : 0;
+    }
+    unsigned* out = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
+    for (int r = 1 + warp; r < h; r += nwarps) {
+        const long long before = rowoff[r];
+        const int cnt = (r + 1 < h ? rowoff[r + 1] : total) - rowoff[r];
+        if (cnt == 0 || before >= n_bits) continue;
+        const unsigned* src = stage + (size_t)r * g.rw;
+        const int nsrc = (cnt + 31) >> 5;
+        const long long first = before >> 5, last = (before + cnt - 1) >> 5;
+        const int sh = (int)(before & 31);
+        for (long long mw = first + lane; mw <= last; mw += 32) {
+            const int i = (int)(mw - first);
+            const unsigned cur = i < nsrc ? src[i] : 0u;
+            const unsigned prev = (i >= 1 && i - 1 < nsrc) ? src[i - 1] : 0u;
+            unsigned val = __funnelshift_r(cur, prev, sh);
+            // the last staged word of a row may carry stale low bits only if cnt is a multiple of 32: none are written
+            const long long bit0 = mw << 5;
+            const long long endbit = before + cnt;                       // bits of this row end here
+            if (bit0 + 32 > endbit) val &= ~(0xffffffffu >> (int)(endbit - bit0));   // drop what is past the row's bits
+            if (bit0 + 32 > n_bits) {
+                const int keep = (int)(n_bits - bit0);
+                val = keep <= 0 ? 0u : (val & ~(0xffffffffu >> keep));
+            }
+            if (val == 0) continue;
+            atomicOr(out + mw, __byte_perm(val, 0, 0x0123));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static int med_geom(int h, int w, int itemsize, int bit_depth, MedGeom& g) {
+    PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "pee_med: itemsize must be 1 or 2");
+    PEEB_REQUIRE(bit_depth >= 1 && bit_depth <= 8 * itemsize, "pee_med: bit_depth %d out of range for itemsize %d", bit_depth, itemsize);
+    PEEB_REQUIRE(h >= 1 && w >= 1 && (long long)h * w < (1ll << 31), "pee_med: image size %dx%d unsupported", h, w);
+    PEEB_REQUIRE(w <= 65535, "pee_med: width %d unsupported (progress counters)", w);
+    g.h = h; g.w = w; g.itemsize = itemsize; g.maxval = (1 << bit_depth) - 1;
+    g.nchunk = (w + MCHUNK - 1) / MCHUNK;
+    g.lmw = (w + 7) / 8;
+    g.rw = (w + 31) / 32 + 1;
+    return PEEB_OK;
+}
+
+}  // namespace peeb
+
+using namespace peeb;
+
+extern "C" {
+
+int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                             int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
+                             int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
+                             int64_t* info, void* stream) {
+    PEEB_REQUIRE(ws && src && T && n_bits && payload && info, "peeb_pee_med_embed_batch: null pointer");
+    PEEB_REQUIRE(n_units >= 1, "peeb_pee_med_embed_batch: n_units must be >= 1");
+    PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_med_embed_batch: payload must be 4-byte aligned");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    MedGeom g;
+    int rc = med_geom(h, w, itemsize, bit_depth, g);
+    if (rc) return rc;
+    const long long ne = (long long)n_units * h * g.nchunk;
+    PEEB_REQUIRE(ne < (1ll << 31), "peeb_pee_med_embed_batch: batch too large");
+    int* dT; unsigned* dN; char* extra;
+    const size_t cnt_bytes = align_up((size_t)ne * sizeof(unsigned short), 256), off_bytes = align_up((size_t)ne * sizeof(unsigned), 256);
+    rc = upload_unit_tables(ws, 0, n_units, T, n_bits, bit_depth, cnt_bytes + off_bytes, st, &dT, &dN, &extra);
+    if (rc) return rc;
+    unsigned short* cnt = (unsigned short*)extra;
+    unsigned* off = (unsigned*)(extra + cnt_bytes);
+    PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
+    PeeBatch bt{};
+    bt.src = (const unsigned char*)src; bt.src_stride = src_stride;
+    bt.dst = (unsigned char*)marked; bt.dst_stride = marked_stride;
+    bt.lm = lm; bt.lm_stride = lm_stride;
+    bt.payload = payload; bt.payload_stride = payload_stride;
+    bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    const unsigned blocks = (unsigned)((ne + 7) / 8);
+    { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
+      if (itemsize == 2) med_embed_kernel<unsigned short, false><<<blocks, 256, 0, st>>>(g, bt, cnt, off);
+      else med_embed_kernel<unsigned char, false><<<blocks, 256, 0, st>>>(g, bt, cnt, off); }
+    med_scan_kernel<<<n_units, 1024, 0, st>>>(g, bt, cnt, off);
+    { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+      if (itemsize == 2) med_embed_kernel<unsigned short, true><<<blocks, 256, 0, st>>>(g, bt, cnt, off);
+      else med_embed_kernel<unsigned char, true><<<blocks, 256, 0, st>>>(g, bt, cnt, off); }
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
+                               int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm,
+                               int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,
+                               int64_t recovered_stride, int64_t* info, void* stream) {
+    PEEB_REQUIRE(ws && marked && T && n_bits && lm && payload_out && info, "peeb_pee_med_extract_batch: null pointer");
+    PEEB_REQUIRE(n_units >= 1, "peeb_pee_med_extract_batch: n_units must be >= 1");
+    PEEB_REQUIRE(((uintptr_t)payload_out & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_med_extract_batch: payload_out must be 4-byte aligned");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    MedGeom g;
+    int rc = med_geom(h, w, itemsize, bit_depth, g);
+    if (rc) return rc;
+    for (int u = 0; u < n_units; ++u)
+        PEEB_REQUIRE(n_units == 1 || (int64_t)peeb_payload_bytes(n_bits[u]) <= payload_stride, "peeb_pee_med_extract_batch: payload_stride too small for unit %d", u);
+    int* dT; unsigned* dN; char* extra;
+    rc = upload_unit_tables(ws, 0, n_units, T, n_bits, bit_depth, 256, st, &dT, &dN, &extra);
+    if (rc) return rc;
+    rc = scratch_reserve(ws->pbits[0], (size_t)n_units * h * g.rw * sizeof(unsigned) + 256);
+    if (rc) return rc;
+    if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
+    else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
+    PeeBatch bt{};
+    bt.src = (const unsigned char*)marked; bt.src_stride = marked_stride;
+    bt.dst = (unsigned char*)recovered; bt.dst_stride = recovered_stride;
+    bt.lm = const_cast<uint8_t*>(lm); bt.lm_stride = lm_stride;
+    bt.payload_out = payload_out; bt.payload_stride = payload_stride;
+    bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    // warps per CTA: one per 32-row group up to 16; fewer when the line buffers would not fit
+    int nwarps = std::max(1, std::min(16, (h - 1 + 31) / 32));
+    while (nwarps > 1 && med_layout(g, nwarps).total > (size_t)ws->max_smem_optin) nwarps /= 2;
+    const size_t smem = med_layout(g, nwarps).total;
+    PEEB_REQUIRE(smem <= (size_t)ws->max_smem_optin, "peeb_pee_med_extract_batch: image %dx%d needs more shared memory than one SM has", h, w);
+    ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
+    if (itemsize == 2) {
+        PEEB_CUDA(cudaFuncSetAttribute(med_extract_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        med_extract_kernel<unsigned short><<<n_units, nwarps * 32, smem, st>>>(g, bt, (unsigned*)ws->pbits[0].ptr);
+    } else {
+        PEEB_CUDA(cudaFuncSetAttribute(med_extract_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        med_extract_kernel<unsigned char><<<n_units, nwarps * 32, smem, st>>>(g, bt, (unsigned*)ws->pbits[0].ptr);
+    }
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+// ---- host-buffer variants: the whole batch is staged at once on the workspace stream (synchronous)
+int peeb_pee_med_embed_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                         const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host, int64_t payload_stride,
+                         void* marked_host, uint8_t* lm_host, int64_t* info_host) {
+    PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_med_embed_h: null pointer");
+    PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2) && payload_stride >= 0, "peeb_pee_med_embed_h: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256), lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
+    int64_t maxpb = 0;
+    for (int u = 0; u < n_units; ++u) {
+        PEEB_REQUIRE(n_bits[u] >= 0 && (n_bits[u] + 7) / 8 <= payload_stride, "peeb_pee_med_embed_h: payload %d shorter than n_bits", u);
+        maxpb = std::max<int64_t>(maxpb, (int64_t)peeb_payload_bytes(n_bits[u]));
+    }
+    const size_t pstride = align_up((size_t)std::max<int64_t>(payload_stride, maxpb), 16);
+    int rc = scratch_reserve(ws->stage, 2 * (size_t)n_units * img_al + 256); if (rc) return rc;
+    const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
+    rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
+    char* d1 = (char*)ws->stage.ptr; char* d2 = (char*)ws->stage2.ptr;
+    PEEB_CUDA(cudaMemcpy2DAsync(d1, img_al, src_host, img, img, n_units, cudaMemcpyHostToDevice, st));
+    PEEB_CUDA(cudaMemsetAsync(d2, 0, o_lm, st));
+    if (payload_stride > 0 && payload_host)
+        PEEB_CUDA(cudaMemcpy2DAsync(d2, pstride, payload_host, (size_t)payload_stride, (size_t)payload_stride, n_units, cudaMemcpyHostToDevice, st));
+    char* dm = d1 + (size_t)n_units * img_al;
+    rc = peeb_pee_med_embed_batch(ws, d1, (int64_t)img_al, n_units, h, w, itemsize, bit_depth, T, n_bits, (const uint8_t*)d2, (int64_t)pstride,
+                                  dm, (int64_t)img_al, (uint8_t*)(d2 + o_lm), (int64_t)lm_al, (int64_t*)(d2 + o_info), st);
+    if (rc) return rc;
+    if (marked_host) PEEB_CUDA(cudaMemcpy2DAsync(marked_host, img, dm, img_al, img, n_units, cudaMemcpyDeviceToHost, st));
+    if (lm_host) PEEB_CUDA(cudaMemcpy2DAsync(lm_host, lmb, d2 + o_lm, lm_al, lmb, n_units, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaMemcpyAsync(info_host, d2 + o_info, (size_t)n_units * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaStreamSynchronize(st));
+    return PEEB_OK;
+}
+
+int peeb_pee_med_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                           const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host, uint8_t* payload_out_host,
+                           int64_t payload_stride, void* recovered_host, int64_t* info_host) {
+    PEEB_REQUIRE(ws && marked_host && T && n_bits && lm_host && payload_out_host && info_host, "peeb_pee_med_extract_h: null pointer");
+    PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_med_extract_h: bad sizes");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = ws->stream;
+    const size_t img = (size_t)h * w * itemsize, img_al = align_up(img, 256), lmb = (size_t)h * ((w + 7) / 8), lm_al = align_up(lmb, 256);
+    int64_t maxpb = 0;
+    for (int u = 0; u < n_units; ++u) {
+        PEEB_REQUIRE(n_bits[u] >= 0 && (n_bits[u] + 7) / 8 <= payload_stride, "peeb_pee_med_extract_h: payload_out %d shorter than n_bits", u);
+        maxpb = std::max<int64_t>(maxpb, (int64_t)peeb_payload_bytes(n_bits[u]));
+    }
+    const size_t pstride = align_up((size_t)std::max<int64_t>(payload_stride, maxpb), 16);
+    int rc = scratch_reserve(ws->stage, 2 * (size_t)n_units * img_al + 256); if (rc) return rc;
+    const size_t o_lm = (size_t)n_units * pstride, o_info = o_lm + (size_t)n_units * lm_al;
+    rc = scratch_reserve(ws->stage2, o_info + (size_t)n_units * PEEB_INFO * 8 + 256); if (rc) return rc;
+    char* d1 = (char*)ws->stage.ptr; char* d2 = (char*)ws->stage2.ptr;
+    PEEB_CUDA(cudaMemcpy2DAsync(d1, img_al, marked_host, img, img, n_units, cudaMemcpyHostToDevice, st));
+    PEEB_CUDA(cudaMemcpy2DAsync(d2 + o_lm, lm_al, lm_host, lmb, lmb, n_units, cudaMemcpyHostToDevice, st));
+    char* dr = d1 + (size_t)n_units * img_al;
+    rc = peeb_pee_med_extract_batch(ws, d1, (int64_t)img_al, n_units, h, w, itemsize, bit_depth, T, n_bits, (const uint8_t*)(d2 + o_lm), (int64_t)lm_al,
+                                    (uint8_t*)d2, (int64_t)pstride, recovered_host ? dr : nullptr, (int64_t)img_al, (int64_t*)(d2 + o_info), st);
+    if (rc) return rc;
+    if (recovered_host) PEEB_CUDA(cudaMemcpy2DAsync(recovered_host, img, dr, img_al, img, n_units, cudaMemcpyDeviceToHost, st));
+    if (payload_stride > 0)
+        PEEB_CUDA(cudaMemcpy2DAsync(payload_out_host, (size_t)payload_stride, d2, pstride, (size_t)payload_stride, n_units, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaMemcpyAsync(info_host, d2 + o_info, (size_t)n_units * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaStreamSynchronize(st));
+    return PEEB_OK;
+}
+
+}  // extern "C"

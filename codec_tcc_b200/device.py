@@ -33,7 +33,8 @@ def payload_stride(max_bits: int) -> int:
     return (_cabi.payload_bytes(max_bits) + 15) // 16 * 16
 
 
-def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None, info=None, shared_cover=False):
+def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None, info=None, shared_cover=False,
+                     predictor="rhombus"):
     """imgs (n,h,w) [or (h,w) with shared_cover]; payloads (n, stride) uint8 with
     stride >= payload_stride(max n_bits); n_bits / T host int arrays.
     -> (marked, lm, info) tensors; enqueued, not synchronised."""
@@ -62,7 +63,10 @@ def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None,
     if info is None:
         info = torch.empty((n, INFO), dtype=torch.int64, device=dev)
     ws = workspace(dev.index if dev.index is not None else torch.cuda.current_device())
-    check(lib().peeb_pee_embed_batch(
+    if predictor == "med" and shared_cover:
+        raise ValueError("shared_cover is not supported with predictor='med'")
+    fn = lib().peeb_pee_med_embed_batch if predictor == "med" else lib().peeb_pee_embed_batch
+    check(fn(
         ws.handle, _raw(imgs, "imgs"), src_stride, n, h, w, item, int(bit_depth), Ts.ctypes.data, nb.ctypes.data,
         _raw(payloads, "payloads"), payloads.shape[1], _raw(marked, "marked") if marked is not False else None,
         h * w * item, _raw(lm, "lm") if lm is not False else None, h * lmw, _raw(info, "info"), _stream(dev)),
@@ -70,7 +74,8 @@ def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None,
     return marked, lm, info
 
 
-def pee_extract_device(marked, lm, T, n_bits, bit_depth, payload_out=None, recovered=None, info=None):
+def pee_extract_device(marked, lm, T, n_bits, bit_depth, payload_out=None, recovered=None, info=None,
+                       predictor="rhombus"):
     """-> (payload_out (n, stride) uint8, recovered, info); enqueued only."""
     dev = marked.device
     item = _pixels(marked, "marked")
@@ -85,7 +90,8 @@ def pee_extract_device(marked, lm, T, n_bits, bit_depth, payload_out=None, recov
     if info is None:
         info = torch.empty((n, INFO), dtype=torch.int64, device=dev)
     ws = workspace(dev.index if dev.index is not None else torch.cuda.current_device())
-    check(lib().peeb_pee_extract_batch(
+    fn = lib().peeb_pee_med_extract_batch if predictor == "med" else lib().peeb_pee_extract_batch
+    check(fn(
         ws.handle, _raw(marked, "marked"), h * w * item, n, h, w, item, int(bit_depth), Ts.ctypes.data,
         nb.ctypes.data, _raw(lm, "lm"), h * lmw, _raw(payload_out, "payload_out"), payload_out.shape[1],
         _raw(recovered, "recovered") if recovered is not False else None, h * w * item, _raw(info, "info"),

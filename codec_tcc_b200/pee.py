@@ -68,8 +68,17 @@ def _info_dict(row):
 
 
 # ---------------------------------------------------------------- batches (numpy in / numpy out)
+PREDICTORS = ("rhombus", "med")
+
+
+def _check_predictor(predictor):
+    if predictor not in PREDICTORS:
+        raise ValueError(f"predictor must be one of {PREDICTORS}")
+    return predictor
+
+
 def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=False, shared_payload=False,
-                    want_marked=True, want_lm=True, out_marked=None, out_lm=None, device=None):
+                    want_marked=True, want_lm=True, out_marked=None, out_lm=None, device=None, predictor="rhombus"):
     """Embed into a batch of equally shaped images.
 
     imgs      (n, h, w) uint8/uint16 -- or (h, w) with ``shared_cover=True``,
@@ -80,7 +89,10 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
     -> (marked (n,h,w) or None, lm_packed (n,h,ceil(w/8)) or None, info (n, 8) int64)
     ``info[:, 7]`` is 0 or PEEB_E_CAPACITY (-2): nothing is raised here, the
     embed of an oversize payload is the zero-padded embed of what fits.
+    ``predictor``: "rhombus" (two-pass checkerboard) or "med" (causal MED predictor,
+    one raster pass; no shared cover / payload).
     """
+    _check_predictor(predictor)
     imgs = _cabi.as_image(imgs, "imgs")
     if shared_cover:
         if imgs.ndim != 2:
@@ -116,6 +128,13 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
     info = np.zeros((n, INFO), np.int64)
     ws = workspace(device)
     flags = (1 if shared_cover else 0) | (2 if shared_payload else 0)
+    if predictor == "med":
+        if flags:
+            raise ValueError("shared_cover / shared_payload are not supported with predictor='med'")
+        check(lib().peeb_pee_med_embed_h(ws.handle, ptr(imgs), n, h, w, imgs.dtype.itemsize, bd, ptr(Ts), ptr(nb),
+                                         ptr(payloads) if payloads.size else None, payloads.shape[1], ptr(marked), ptr(lm),
+                                         ptr(info)), "peeb_pee_med_embed_h")
+        return marked, lm, info
     check(lib().peeb_pee_embed_h(ws.handle, ptr(imgs), flags, n, h, w, imgs.dtype.itemsize, bd,
                                  ptr(Ts), ptr(nb), ptr(payloads) if payloads.size else None, payloads.shape[1],
                                  ptr(marked), ptr(lm), ptr(info)), "peeb_pee_embed_h")
@@ -123,11 +142,12 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
 
 
 def pee_extract_batch(marked, lm, T, n_bits, bit_depth=None, *, want_recovered=True, out_recovered=None,
-                      out_payload=None, device=None):
+                      out_payload=None, device=None, predictor="rhombus"):
     """-> (payloads (n, stride) uint8, recovered (n,h,w) or None, info (n,8)).
     ``info[:, 2]`` is the number of carriers found; ``info[:, 7]`` is
     PEEB_E_CAPACITY when n_bits exceeds it (the payload row is then what could
     be read, zero padded)."""
+    _check_predictor(predictor)
     marked = _cabi.as_image(marked, "marked")
     if marked.ndim != 3:
         raise ValueError("marked must be (n, h, w)")
@@ -157,8 +177,9 @@ def pee_extract_batch(marked, lm, T, n_bits, bit_depth=None, *, want_recovered=T
     ws = workspace(device)
     # a zero-width payload array still needs a valid pointer
     pay_ptr = ptr(payload) if payload.size else ptr(np.zeros(4, np.uint8))
-    check(lib().peeb_pee_extract_h(ws.handle, ptr(marked), n, h, w, marked.dtype.itemsize, bd, ptr(Ts), ptr(nb),
-                                   ptr(lm), pay_ptr, stride, ptr(rec), ptr(info)), "peeb_pee_extract_h")
+    fn = lib().peeb_pee_med_extract_h if predictor == "med" else lib().peeb_pee_extract_h
+    check(fn(ws.handle, ptr(marked), n, h, w, marked.dtype.itemsize, bd, ptr(Ts), ptr(nb),
+             ptr(lm), pay_ptr, stride, ptr(rec), ptr(info)), "peeb_pee_extract_h")
     return payload, rec, info
 
 
@@ -189,7 +210,7 @@ def estimate_threshold(hist, n_bits):
 
 
 # ---------------------------------------------------------------- single image
-def pee_embed(img, payload, T=None, bit_depth=None, n_bits=None, device=None):
+def pee_embed(img, payload, T=None, bit_depth=None, n_bits=None, device=None, predictor="rhombus"):
     """-> (marked, lm_packed, info dict).  ``T=None`` picks the smallest
     threshold whose capacity holds the payload (histogram estimate, then
     verify-and-increment).  ``ValueError`` when the payload does not fit."""
@@ -202,11 +223,12 @@ def pee_embed(img, payload, T=None, bit_depth=None, n_bits=None, device=None):
     pay2d = packed.reshape(1, -1)
 
     def run(t):
-        marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], t, bd, device=device)
+        marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], t, bd, device=device, predictor=predictor)
         return marked[0], lm[0], info[0]
 
     if T is None:
-        T = estimate_threshold(pee_histogram(img, bd, device), n_bits)
+        # the histogram estimate belongs to the rhombus predictor; the causal one starts its search at T = 1
+        T = estimate_threshold(pee_histogram(img, bd, device), n_bits) if predictor == "rhombus" else 1
         if T is None:
             raise ValueError("payload exceeds capacity at every threshold")
         while True:
@@ -226,13 +248,14 @@ def pee_embed(img, payload, T=None, bit_depth=None, n_bits=None, device=None):
     return marked, lm, d
 
 
-def pee_extract(marked, lm_packed, T, n_bits, bit_depth=None, device=None):
+def pee_extract(marked, lm_packed, T, n_bits, bit_depth=None, device=None, predictor="rhombus"):
     """-> (payload packed uint8[ceil(n_bits/8)], recovered image)."""
     marked = _cabi.as_image(marked, "marked")
     if marked.ndim != 2:
         raise ValueError("marked must be 2-D")
     lm = np.ascontiguousarray(lm_packed, dtype=np.uint8)
-    payload, rec, info = pee_extract_batch(marked[None], lm[None], T, [int(n_bits)], bit_depth, device=device)
+    payload, rec, info = pee_extract_batch(marked[None], lm[None], T, [int(n_bits)], bit_depth, device=device,
+                                           predictor=predictor)
     if info[0, 7] == PEEB_E_CAPACITY:
         raise ValueError("n_bits exceeds the number of carriers found")
     return payload[0, :(int(n_bits) + 7) // 8], rec[0]

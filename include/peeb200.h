@@ -237,6 +237,29 @@ int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h,
 int peeb_pee_hist_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize,
                     int bit_depth, uint32_t* hist_host);
 
+/* ---- N1: PEE with the causal MED predictor ----------------- *
+ * Not in the reference; specified in DESIGN.md "Appendix A2":
+ * p = clamp(W + N - NW, min(W, N), max(W, N)) (JPEG-LS MED), domain i >= 1, j >= 1,
+ * ONE raster-order pass; classes / flags / carriers / padding as in Appendix A.
+ * The embedder predicts from original pixels (parallel); the extractor from
+ * recovered ones (anti-diagonal wavefront, one CTA per image).  Same argument
+ * lists as peeb_pee_embed_batch / peeb_pee_extract_batch and their host-buffer
+ * forms (src_stride != 0: no shared cover); info: cap0 = capacity, cap1 = 0.   */
+int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w,
+                             int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
+                             const uint8_t* payload, int64_t payload_stride, void* marked, int64_t marked_stride,
+                             uint8_t* lm, int64_t lm_stride, int64_t* info, void* stream);
+int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h,
+                               int w, int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
+                               const uint8_t* lm, int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride,
+                               void* recovered, int64_t recovered_stride, int64_t* info, void* stream);
+int peeb_pee_med_embed_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                         const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host, int64_t payload_stride,
+                         void* marked_host, uint8_t* lm_host, int64_t* info_host);
+int peeb_pee_med_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize,
+                           int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host,
+                           uint8_t* payload_out_host, int64_t payload_stride, void* recovered_host, int64_t* info_host);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
