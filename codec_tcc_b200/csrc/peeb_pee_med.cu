@@ -11,8 +11,8 @@
 // One CTA per image; a warp owns 32 consecutive rows (lane = row) and runs them skewed by one column
 // per lane, so the N / NW neighbours of a lane are what the lane above produced one and two
 // iterations earlier (two shuffles).  Consecutive 32-row groups are pipelined through the warps of
-// the CTA: the last row of a group goes to a shared-memory line buffer with a progress counter that
-// the first lane of the next group polls.  Carrier bits are collected MSB-first per row and
+// the CTA: the last row of a group goes to a shared-memory line buffer whose entries carry a tag that
+// the first lane of the next group polls (value and ready flag in one word: no fence).  Carrier bits are collected MSB-first per row and
 // concatenated at the end by the same CTA.
 #include <algorithm>
 #include <cstdlib>
@@ -211,21 +211,37 @@ struct MedSmem {
 __host__ __device__ inline MedSmem med_layout(const MedGeom& g, int nwarps) {
     MedSmem L{};
     size_t o = 0;
-    L.line = o; o += align_up((size_t)(nwarps + 1) * g.w * sizeof(unsigned short), 16);
-    L.prog = o; o += align_up((size_t)(nwarps + 1) * sizeof(int), 16);
+    L.line = o; o += align_up((size_t)(nwarps + 1) * g.w * sizeof(unsigned), 16);
+    L.prog = o;
     L.rowoff = o; o += align_up((size_t)(g.h + 1) * sizeof(int), 16);
     L.misc = o; o += 64 * sizeof(int);
     L.total = o;
     return L;
 }
 
-template <typename PixT>
+// eight pixels of a row as four words of two 16-bit values (8-bit pixels are widened), and back
+template <typename PixT> __device__ __forceinline__ uint4 ld8q(const PixT* p) {
+    if (sizeof(PixT) == 2) return *reinterpret_cast<const uint4*>(p);
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    return make_uint4(__byte_perm(v.x, 0, 0x4140), __byte_perm(v.x, 0, 0x4342), __byte_perm(v.y, 0, 0x4140), __byte_perm(v.y, 0, 0x4342));
+}
+template <typename PixT> __device__ __forceinline__ void st8q(PixT* p, const uint4& q) {
+    if (sizeof(PixT) == 2) *reinterpret_cast<uint4*>(p) = q;
+    else *reinterpret_cast<uint2*>(p) = make_uint2(__byte_perm(q.x, q.y, 0x6420), __byte_perm(q.z, q.w, 0x6420));
+}
+
+// VEC: rows are 16-byte (8-bit pixels: 8-byte) aligned and w % 8 == 0: a lane streams its row through
+// two register queues (eight pixels in, eight out, the next block and location-map byte prefetched
+// one block ahead), so no memory latency sits on the wavefront's dependency chain.
+template <typename PixT, bool VEC>
 __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const MedSmem L = med_layout(g, nwarps);
-    unsigned short* line = reinterpret_cast<unsigned short*>(smem_raw + L.line);
-    volatile int* prog = reinterpret_cast<volatile int*>(smem_raw + L.prog);
+    // line buffers: one 32-bit entry per column = recovered value | tag << 16.  The tag (group + 2; row 0:
+    // 1; never written: 0) makes an entry its own "ready" flag, so handing a row to the next group needs
+    // neither a fence nor a separate progress counter.
+    unsigned* line = reinterpret_cast<unsigned*>(smem_raw + L.line);
     int* rowoff = reinterpret_cast<int*>(smem_raw + L.rowoff);
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     const int unit = blockIdx.x, h = g.h, w = g.w, nslot = nwarps + 1;
@@ -233,67 +249,90 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
     PixT* rec = bt.dst ? reinterpret_cast<PixT*>(bt.dst + (long long)unit * bt.dst_stride) : nullptr;
     const unsigned char* lm = bt.lm + (long long)unit * bt.lm_stride;
     unsigned* stage = stage_bits + (long long)unit * h * g.rw;
-    const int T = bt.T[unit];
+    const int T = bt.T[unit], T2 = 2 * T, T4 = 4 * T;
     for (int k = threadIdx.x; k <= h; k += blockDim.x) rowoff[k] = 0;
-    for (int k = threadIdx.x; k < nslot; k += blockDim.x) prog[k] = -1;
-    if (rec) for (int j = threadIdx.x; j < w; j += blockDim.x) rec[j] = marked[j];  // row 0 never changes
+    for (int k = threadIdx.x; k < nslot * w; k += blockDim.x) line[k] = 0u;
+    __syncthreads();
+    // row 0 never changes: it is the "group -1" line (slot nslot-1, tag 1) and goes straight to the output
+    for (int j = threadIdx.x; j < w; j += blockDim.x) {
+        const unsigned v = marked[j];
+        line[(size_t)(nslot - 1) * w + j] = v | (1u << 16);
+        if (rec) rec[j] = (PixT)v;
+    }
     __syncthreads();
 
     const int ngroups = (h - 1 + 31) / 32;
     for (int grp = warp; grp < ngroups; grp += nwarps) {
         const int rowi = 1 + 32 * grp + lane;
         const bool valid = rowi < h;
+        const int rowc = valid ? rowi : 1;
         const int lastl = min(31, h - 2 - 32 * grp);  // last lane that owns a row
-        const PixT* mrow = marked + (size_t)(valid ? rowi : 1) * w;
-        PixT* rrow = rec ? rec + (size_t)(valid ? rowi : 1) * w : nullptr;
-        const unsigned char* lrow = lm + (size_t)(valid ? rowi : 1) * g.lmw;
-        unsigned* srow = stage + (size_t)(valid ? rowi : 1) * g.rw;
-        unsigned short* myline = line + (size_t)(grp % nslot) * w;
-        const unsigned short* upline = line + (size_t)((grp + nslot - 1) % nslot) * w;
-        const int upslot = (grp + nslot - 1) % nslot, myslot = grp % nslot;
-        const int upbase = (grp - 1) * (w + 1), mybase = grp * (w + 1);
+        const PixT* mrow = marked + (size_t)rowc * w;
+        PixT* rrow = rec ? rec + (size_t)rowc * w : nullptr;
+        const unsigned char* lrow = lm + (size_t)rowc * g.lmw;
+        unsigned* srow = stage + (size_t)rowc * g.rw;
+        volatile unsigned* myline = line + (size_t)(grp % nslot) * w;
+        const volatile unsigned* upline = line + (size_t)((grp + nslot - 1) % nslot) * w;
+        const unsigned mytag = (unsigned)(grp + 2) << 16, uptag = (unsigned)(grp + 1);
+        const bool writer = lane == lastl;
         int cur1 = 0, cur2 = 0, aprev = 0, bprev0 = 0;
-        unsigned W = 0, lmbyte = 0;
-        int nW = 0, nwords = 0, ncar = 0;
-        for (int t = 0; t < w + 31; ++t) {
-            const int j = t - lane;
+        unsigned W = 0, lmbyte = 0, lmnext = 0;
+        int nW = 0, ncar = 0;
+        uint4 q = make_uint4(0, 0, 0, 0), nx = q, o = q;
+        if (VEC && valid) {
+            q = ld8q<PixT>(mrow);
+            lmbyte = lrow[0];
+            if (w > 8) { nx = ld8q<PixT>(mrow + 8); lmnext = lrow[1]; }
+        }
+        int j = -lane;
+        for (int t = 0; t < w + 31; ++t, ++j) {
             int b = __shfl_up_sync(0xffffffffu, cur1, 1), c = __shfl_up_sync(0xffffffffu, cur2, 1);
             if (lane == 0 && j < w) {
-                int bnew;
-                if (grp == 0) bnew = marked[j];  // row 0
-                else {
-                    while (prog[upslot] < upbase + j + 1) {}
-                    bnew = reinterpret_cast<const volatile unsigned short*>(upline)[j];
-                }
-                c = bprev0; b = bnew; bprev0 = bnew;
+                unsigned v;
+                do { v = upline[j]; } while ((v >> 16) != uptag);
+                c = bprev0; b = (int)(v & 0xffffu); bprev0 = b;
             }
             __syncwarp();
             if (valid && j >= 0 && j < w) {
-                const int x = mrow[j];
+                int x;
+                if (VEC) {
+                    x = (int)(q.x & 0xffffu);
+                    q.x = __funnelshift_r(q.x, q.y, 16); q.y = __funnelshift_r(q.y, q.z, 16);
+                    q.z = __funnelshift_r(q.z, q.w, 16); q.w >>= 16;
+                } else {
+                    x = mrow[j];
+                    if ((j & 7) == 0) lmbyte = lrow[j >> 3];
+                }
                 int val = x;
                 if (j >= 1) {
-                    if ((j & 7) == 0 || j == 1) lmbyte = lrow[j >> 3];
-                    const int Tl = ((lmbyte >> (7 - (j & 7))) & 1u) ? 0 : T;       // flagged pixels were left alone
-                    const int u = x - med3(aprev, b, c) + 2 * Tl;                  // e' + 2T
-                    const int cc = max(min((u + 1) >> 1, 2 * Tl), 0);              // clamp(ceil(e'/2), -T, T) + T
+                    const bool flagged = (lmbyte >> (7 - (j & 7))) & 1u;           // flagged pixels were left alone
+                    const int Tl = flagged ? 0 : T, Tl2 = flagged ? 0 : T2;
+                    const int u = x - med3(aprev, b, c) + Tl2;                     // e' + 2T
+                    const int cc = max(min((u + 1) >> 1, Tl2), 0);                 // clamp(ceil(e'/2), -T, T) + T
                     val = x - cc + Tl;
-                    if ((unsigned)u < (unsigned)(4 * Tl)) {                        // carrier: -2T <= e' < 2T
+                    if ((unsigned)u < (unsigned)(flagged ? 0 : T4)) {              // carrier: -2T <= e' < 2T
                         W = (W << 1) | (unsigned)(u & 1);
                         ++ncar;
-                        if (++nW == 32) { srow[nwords++] = W; nW = 0; W = 0; }
+                        if (++nW == 32) { *srow++ = W; nW = 0; W = 0; }
                     }
                 }
-                if (rrow) rrow[j] = (PixT)val;
                 cur2 = cur1; cur1 = val; aprev = val;
-                if (lane == lastl) {
-                    myline[j] = (unsigned short)val;
-                    __threadfence_block();
-                    prog[myslot] = mybase + j + 1;
+                if (writer) myline[j] = (unsigned)val | mytag;
+                if (VEC) {
+                    o.x = __funnelshift_r(o.x, o.y, 16); o.y = __funnelshift_r(o.y, o.z, 16);
+                    o.z = __funnelshift_r(o.z, o.w, 16); o.w = (o.w >> 16) | ((unsigned)val << 16);
+                    if ((j & 7) == 7) {  // block done: write it, switch to the prefetched one, fetch the one after
+                        if (rrow) st8q<PixT>(rrow + j - 7, o);
+                        q = nx; lmbyte = lmnext;
+                        if (j + 9 < w) { nx = ld8q<PixT>(mrow + j + 9); lmnext = lrow[(j + 9) >> 3]; }
+                    }
+                } else if (rrow) {
+                    rrow[j] = (PixT)val;
                 }
             }
         }
         if (valid) {
-            if (nW) srow[nwords] = W << (32 - nW);
+            if (nW) *srow = W << (32 - nW);
             rowoff[rowi] = ncar;
         }
     }
@@ -422,18 +461,28 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
     bt.payload_out = payload_out; bt.payload_stride = payload_stride;
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
     // warps per CTA: one per 32-row group up to 16; fewer when the line buffers would not fit
-    int nwarps = std::max(1, std::min(16, (h - 1 + 31) / 32));
+    // Groups are pipelined 33 iterations apart, so a CTA with as many warps as groups keeps only about half
+    // of them busy (fill and drain); fewer warps taking the groups round-robin stay busier, and more images
+    // share an SM.  8 measured best for 512-row images (scripts/bench_med.py).
+    int maxw = 8;
+    if (const char* e = getenv("PEEB_MED_WARPS")) maxw = std::max(1, std::min(16, atoi(e)));
+    int nwarps = std::max(1, std::min(maxw, (h - 1 + 31) / 32));
     while (nwarps > 1 && med_layout(g, nwarps).total > (size_t)ws->max_smem_optin) nwarps /= 2;
     const size_t smem = med_layout(g, nwarps).total;
     PEEB_REQUIRE(smem <= (size_t)ws->max_smem_optin, "peeb_pee_med_extract_batch: image %dx%d needs more shared memory than one SM has", h, w);
+    // vector path: every row of every unit starts on a 16-byte (8-bit pixels: 8-byte) boundary
+    const uintptr_t al = 8 * (uintptr_t)itemsize - 1;
+    const bool vec = (w % 8 == 0) && ((((uintptr_t)marked) | (uintptr_t)recovered | (uintptr_t)marked_stride | (uintptr_t)recovered_stride) & al) == 0 &&
+                     !getenv("PEEB_MED_SCALAR");
     ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
-    if (itemsize == 2) {
-        PEEB_CUDA(cudaFuncSetAttribute(med_extract_kernel<unsigned short>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        med_extract_kernel<unsigned short><<<n_units, nwarps * 32, smem, st>>>(g, bt, (unsigned*)ws->pbits[0].ptr);
-    } else {
-        PEEB_CUDA(cudaFuncSetAttribute(med_extract_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        med_extract_kernel<unsigned char><<<n_units, nwarps * 32, smem, st>>>(g, bt, (unsigned*)ws->pbits[0].ptr);
-    }
+#define PEEB_MED_LAUNCH(PIXT, VEC)                                                                                          \
+    do {                                                                                                                    \
+        PEEB_CUDA(cudaFuncSetAttribute(med_extract_kernel<PIXT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        med_extract_kernel<PIXT, VEC><<<n_units, nwarps * 32, smem, st>>>(g, bt, (unsigned*)ws->pbits[0].ptr);                \
+    } while (0)
+    if (itemsize == 2) { if (vec) PEEB_MED_LAUNCH(unsigned short, true); else PEEB_MED_LAUNCH(unsigned short, false); }
+    else { if (vec) PEEB_MED_LAUNCH(unsigned char, true); else PEEB_MED_LAUNCH(unsigned char, false); }
+#undef PEEB_MED_LAUNCH
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }
