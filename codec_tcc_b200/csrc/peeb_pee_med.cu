@@ -219,6 +219,15 @@ __host__ __device__ inline MedSmem med_layout(const MedGeom& g, int nwarps) {
     return L;
 }
 
+__device__ __forceinline__ uint4 lds128_volatile(const unsigned* p) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128_volatile(unsigned* p, const uint4& v) {
+    asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // eight pixels of a row as four words of two 16-bit values (8-bit pixels are widened), and back
 template <typename PixT> __device__ __forceinline__ uint4 ld8q(const PixT* p) {
     if (sizeof(PixT) == 2) return *reinterpret_cast<const uint4*>(p);
@@ -275,6 +284,83 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
         const volatile unsigned* upline = line + (size_t)((grp + nslot - 1) % nslot) * w;
         const unsigned mytag = (unsigned)(grp + 2) << 16, uptag = (unsigned)(grp + 1);
         const bool writer = lane == lastl;
+        if (VEC) {
+            // ---- four columns per lane and step (skew of four columns per lane): the step overhead -- shuffles,
+            // the poll of the line above, queue handling, loop control -- is paid once per four pixels.
+            // A lane holds its last four recovered values packed in two words (curA: columns jb, jb+1;
+            // curB: jb+2, jb+3) and the one before them (plast): exactly what the lane below needs next step.
+            unsigned curA = 0, curB = 0, plast = 0;
+            int a = 0, ulast = 0, ncar = 0, nW = 0;
+            unsigned long long Wq = 0;
+            unsigned lmbyte = 0, lmnext = 0;
+            uint4 q = make_uint4(0, 0, 0, 0), nx = q;
+            unsigned oA = 0, oB = 0;
+            if (valid) {
+                q = ld8q<PixT>(mrow);
+                lmbyte = lrow[0];
+                if (w > 8) { nx = ld8q<PixT>(mrow + 8); lmnext = lrow[1]; }
+            }
+            const int nsteps = w >> 2;
+            int jb = -4 * lane;
+            for (int t = 0; t < nsteps + 31; ++t, jb += 4) {
+                unsigned uA = __shfl_up_sync(0xffffffffu, curA, 1), uB = __shfl_up_sync(0xffffffffu, curB, 1);
+                int um1 = (int)__shfl_up_sync(0xffffffffu, plast, 1);
+                if (lane == 0 && jb < w) {
+                    uint4 v;
+                    do {
+                        v = lds128_volatile(const_cast<const unsigned*>(upline) + jb);
+                    } while (((v.x >> 16) != uptag) | ((v.y >> 16) != uptag) | ((v.z >> 16) != uptag) | ((v.w >> 16) != uptag));
+                    uA = (v.x & 0xffffu) | (v.y << 16); uB = (v.z & 0xffffu) | (v.w << 16);
+                    um1 = ulast; ulast = (int)(v.w & 0xffffu);
+                }
+                __syncwarp();
+                if (valid && jb >= 0 && jb < w) {
+                    const bool second = jb & 4;
+                    const unsigned xa = second ? q.z : q.x, xb = second ? q.w : q.y;
+                    // location-map nibble of these four columns (bit 3 = column jb); column 0 is border: treated as flagged
+                    unsigned fl = (lmbyte >> (second ? 0 : 4)) & 0xfu;
+                    if (jb == 0) fl |= 8u;
+                    const int xs[4] = {(int)(xa & 0xffffu), (int)(xa >> 16), (int)(xb & 0xffffu), (int)(xb >> 16)};
+                    const int us[4] = {(int)(uA & 0xffffu), (int)(uA >> 16), (int)(uB & 0xffffu), (int)(uB >> 16)};
+                    int vals[4];
+                    unsigned wb = 0;
+                    int nb = 0, c = um1;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool flagged = (fl >> (3 - k)) & 1u;
+                        const int Tl = flagged ? 0 : T, Tl2 = flagged ? 0 : T2;
+                        const int u = xs[k] - med3(a, us[k], c) + Tl2;                // e' + 2T
+                        const int cc = max(min((u + 1) >> 1, Tl2), 0);                // clamp(ceil(e'/2), -T, T) + T
+                        const int val = xs[k] - cc + Tl;
+                        if ((unsigned)u < (unsigned)(flagged ? 0 : T4)) { wb = (wb << 1) | (unsigned)(u & 1); ++nb; }
+                        vals[k] = val; a = val; c = us[k];
+                    }
+                    plast = curB >> 16;
+                    curA = (unsigned)vals[0] | ((unsigned)vals[1] << 16);
+                    curB = (unsigned)vals[2] | ((unsigned)vals[3] << 16);
+                    if (nb) {
+                        Wq = (Wq << nb) | wb; nW += nb; ncar += nb;
+                        if (nW >= 32) { *srow++ = (unsigned)(Wq >> (nW - 32)); nW -= 32; }
+                    }
+                    if (writer) {
+                        uint4 e;
+                        e.x = (unsigned)vals[0] | mytag; e.y = (unsigned)vals[1] | mytag; e.z = (unsigned)vals[2] | mytag; e.w = (unsigned)vals[3] | mytag;
+                        sts128_volatile(const_cast<unsigned*>(myline) + jb, e);
+                    }
+                    if (!second) { oA = curA; oB = curB; }
+                    else {  // block of eight done: write it, switch to the prefetched one, fetch the one after
+                        if (rrow) st8q<PixT>(rrow + jb - 4, make_uint4(oA, oB, curA, curB));
+                        q = nx; lmbyte = lmnext;
+                        if (jb + 12 < w) { nx = ld8q<PixT>(mrow + jb + 12); lmnext = lrow[(jb + 12) >> 3]; }
+                    }
+                }
+            }
+            if (valid) {
+                if (nW) *srow = (unsigned)(Wq << (32 - nW));
+                rowoff[rowi] = ncar;
+            }
+            continue;
+        }
         int cur1 = 0, cur2 = 0, aprev = 0, bprev0 = 0;
         unsigned W = 0, lmbyte = 0, lmnext = 0;
         int nW = 0, ncar = 0;
@@ -461,10 +547,11 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
     bt.payload_out = payload_out; bt.payload_stride = payload_stride;
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
     // warps per CTA: one per 32-row group up to 16; fewer when the line buffers would not fit
-    // Groups are pipelined 33 iterations apart, so a CTA with as many warps as groups keeps only about half
-    // of them busy (fill and drain); fewer warps taking the groups round-robin stay busier, and more images
-    // share an SM.  8 measured best for 512-row images (scripts/bench_med.py).
-    int maxw = 8;
+    // Groups are pipelined 33 steps apart, so a CTA with as many warps as groups keeps only about half of
+    // them busy (fill and drain); fewer warps taking the groups round-robin stay busier and more images
+    // share an SM -- but few large images need the warps.  Aim at ~16 wavefront warps per SM over the batch
+    // (measured: 512 slices of 512x512 -> 5 warps, 64 radiographs of 3000x3000 -> 16; scripts/bench_med.py).
+    int maxw = std::max(4, std::min(16, (ws->sm_count * 16 + n_units - 1) / n_units));
     if (const char* e = getenv("PEEB_MED_WARPS")) maxw = std::max(1, std::min(16, atoi(e)));
     int nwarps = std::max(1, std::min(maxw, (h - 1 + 31) / 32));
     while (nwarps > 1 && med_layout(g, nwarps).total > (size_t)ws->max_smem_optin) nwarps /= 2;
