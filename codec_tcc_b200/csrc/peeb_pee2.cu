@@ -1,8 +1,8 @@
-// Row a10, second-generation kernels: the "row pair" layout.
+// Row a10: the PEE kernels, "row pair" layout.
 //
-// The first-generation kernels (peeb_pee.cu) walk 128-column strips downwards and rank carriers
-// with warp ballots; ncu showed them bound by the integer ALU pipe at ~60 executed instructions per
-// colour pixel.  These kernels cut that to about a third:
+// A first generation of these kernels (in the history of this repository; profiles/r01_ncu_full_pee_kernels.md)
+// walked 128-column strips downwards and ranked carriers with warp ballots; ncu showed it bound by the
+// integer ALU pipe at ~60 executed instructions per colour pixel.  This layout needs about a third less:
 //
 //   * a LANE owns two adjacent image rows of a cell (<= 64 columns) and walks them left to right in
 //     16-byte steps, so its carriers come in raster order: the rank of a carrier inside a
