@@ -73,6 +73,9 @@ int peeb_ws_create(int device, peeb_ws** out) {
     ws->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
     PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream2, cudaStreamNonBlocking));
+    PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream3, cudaStreamNonBlocking));
+    for (int i = 0; i < peeb_ws::kPipeEvents; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pipe_ev[i], cudaEventDisableTiming));
+    if (const char* pr = getenv("PEEB_PIPE_ROLES")) ws->pipe_roles = pr[0] != '0';
     for (int i = 0; i < 4; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreate(&ws->prof_ev[i]));
     for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pev[i], cudaEventDisableTiming));
@@ -89,6 +92,7 @@ int peeb_ws_destroy(peeb_ws* ws) {
     cudaSetDevice(ws->device);
     if (ws->stream) cudaStreamSynchronize(ws->stream);
     if (ws->stream2) cudaStreamSynchronize(ws->stream2);
+    if (ws->stream3) cudaStreamSynchronize(ws->stream3);
     scratch_free(ws->tables);
     scratch_free(ws->tables_h, true);
     scratch_free(ws->stage);
@@ -105,6 +109,8 @@ int peeb_ws_destroy(peeb_ws* ws) {
     for (int i = 0; i < 2; ++i) if (ws->prof_ev[i]) cudaEventDestroy(ws->prof_ev[i]);
     if (ws->stream) cudaStreamDestroy(ws->stream);
     if (ws->stream2) cudaStreamDestroy(ws->stream2);
+    if (ws->stream3) cudaStreamDestroy(ws->stream3);
+    for (int i = 0; i < peeb_ws::kPipeEvents; ++i) if (ws->pipe_ev[i]) cudaEventDestroy(ws->pipe_ev[i]);
     delete ws;
     return PEEB_OK;
 }
@@ -114,6 +120,7 @@ int peeb_ws_sync(peeb_ws* ws) {
     PEEB_CUDA(cudaSetDevice(ws->device));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream2));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream3));
     return PEEB_OK;
 }
 

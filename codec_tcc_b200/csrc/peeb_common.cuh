@@ -42,6 +42,10 @@ struct peeb_ws {
     cudaStream_t stream = nullptr;   // used by the *_h (host buffer) entry points
     cudaStream_t stream2 = nullptr;  // second stream for copy/compute overlap
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream3 = nullptr;  // host batches: copy-out stream (stream = copy-in, stream2 = kernels)
+    static constexpr int kPipeEvents = 32;
+    cudaEvent_t pipe_ev[kPipeEvents] = {};  // ring: copy-in done / kernels done, per chunk of a host batch
+    int pipe_roles = 1;              // 1: one stream per direction + one for kernels; 0: chunks alternate between two streams
     peeb::Scratch tables;            // device: per-launch tables (tickets, status, counts)
     peeb::Scratch tables_h;          // pinned host mirror
     peeb::Scratch stage;             // device: staging for *_h entry points

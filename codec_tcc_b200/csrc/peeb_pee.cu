@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <vector>
+
 #include "peeb_common.cuh"
 #include "peeb_pee.cuh"
 
@@ -250,6 +252,28 @@ static int chunk_units(int n_units, size_t unit_bytes) {
     return (int)c;
 }
 
+// Chunk sizes (in units) of a host batch: uniform steady-state chunks.  PEEB_CHUNK_FIRST_MB=k ramps up
+// from k MB chunks (and down again at the end) to shorten the first copy-in and the last copy-out, which
+// overlap nothing; measured on B200 / PCIe gen5 it gains nothing (ct512 round trip 14.02 ms against
+// 13.88 ms uniform, the bidirectional copy floor being 13.1-13.8 ms), so it is off by default.
+static std::vector<int> chunk_plan(int n_units, size_t unit_bytes, int cmax_limit = 1 << 30) {
+    const int cmax = std::min(chunk_units(n_units, unit_bytes), cmax_limit);
+    size_t first = 0;
+    if (const char* e = getenv("PEEB_CHUNK_FIRST_MB")) first = (size_t)atoi(e) << 20;  // 0: uniform chunks
+    std::vector<int> up;
+    if (first > 0) {
+        const long long cmin = std::max<long long>(1, (long long)((first + unit_bytes - 1) / unit_bytes));
+        long long used = 0;
+        for (long long c = cmin; c < cmax && 2 * (used + c) + cmax <= n_units; c *= 2) { up.push_back((int)c); used += c; }
+    }
+    std::vector<int> plan(up);
+    long long rest = n_units;
+    for (int c : up) rest -= 2 * c;
+    while (rest > 0) { const int c = (int)std::min<long long>(rest, cmax); plan.push_back(c); rest -= c; }
+    plan.insert(plan.end(), up.rbegin(), up.rend());
+    return plan;
+}
+
 int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w, int itemsize,
                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
                      int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
@@ -281,35 +305,49 @@ int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_
         PEEB_CUDA(cudaEventRecord(ws->ev[1], streams[0]));
         PEEB_CUDA(cudaStreamWaitEvent(streams[1], ws->ev[1], 0));
     }
-    // chunks alternate between the two streams: copy-in, kernels and copy-out of neighbouring
-    // chunks overlap (PCIe is full duplex, the copy engines run beside the SMs)
-    const int cu = chunk_units(n_units, img);
-    for (int u0 = 0, c = 0; u0 < n_units; u0 += cu, ++c) {
-        const int n = std::min(cu, n_units - u0), slot = c & 1;
-        cudaStream_t st = streams[slot];
+    // Two pipelines.  Roles (default): one stream per PCIe direction and one for the kernels, chained by
+    // events, so the copies of each direction queue back to back.  Alternating: chunks alternate between
+    // two streams, each doing its own copy-in, kernels and copy-out.
+    const bool roles = ws->pipe_roles != 0;
+    const std::vector<int> plan = chunk_plan(n_units, img);
+    for (int u0 = 0, c = 0; c < (int)plan.size(); u0 += plan[c], ++c) {
+        const int n = plan[c], slot = c & 1;
+        cudaStream_t st_in = roles ? ws->stream : streams[slot], st = roles ? ws->stream2 : streams[slot];
+        cudaStream_t st_out = roles ? ws->stream3 : streams[slot];
         if (!shared_src)
             PEEB_CUDA(cudaMemcpy2DAsync(d1 + (size_t)u0 * img_al, img_al, (const char*)src_host + (size_t)u0 * img, img, img, n,
-                                        cudaMemcpyHostToDevice, st));
+                                        cudaMemcpyHostToDevice, st_in));
         if (!shared_pay && payload_stride > 0 && payload_host)
             PEEB_CUDA(cudaMemcpy2DAsync(d2 + (size_t)u0 * pstride, pstride, payload_host + (size_t)u0 * payload_stride,
-                                        (size_t)payload_stride, (size_t)payload_stride, n, cudaMemcpyHostToDevice, st));
+                                        (size_t)payload_stride, (size_t)payload_stride, n, cudaMemcpyHostToDevice, st_in));
+        if (roles) {
+            cudaEvent_t e = ws->pipe_ev[(2 * c) % peeb_ws::kPipeEvents];
+            PEEB_CUDA(cudaEventRecord(e, st_in));
+            PEEB_CUDA(cudaStreamWaitEvent(st, e, 0));
+        }
         rc = embed_batch_impl(ws, shared_src ? d1 : d1 + (size_t)u0 * img_al, shared_src ? 0 : (int64_t)img_al, n, h, w,
                               itemsize, bit_depth, T + u0, n_bits + u0, (const uint8_t*)(shared_pay ? d2 : d2 + (size_t)u0 * pstride),
                               shared_pay ? 0 : (int64_t)pstride, marked_host ? d1 + o_marked + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
                               lm_host ? (uint8_t*)(d2 + o_lm + (size_t)u0 * lm_al) : nullptr, (int64_t)lm_al,
                               (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO, st, slot);
         if (rc) return rc;
+        if (roles) {
+            cudaEvent_t e = ws->pipe_ev[(2 * c + 1) % peeb_ws::kPipeEvents];
+            PEEB_CUDA(cudaEventRecord(e, st));
+            PEEB_CUDA(cudaStreamWaitEvent(st_out, e, 0));
+        }
         if (marked_host)
             PEEB_CUDA(cudaMemcpy2DAsync((char*)marked_host + (size_t)u0 * img, img, d1 + o_marked + (size_t)u0 * img_al, img_al,
-                                        img, n, cudaMemcpyDeviceToHost, st));
+                                        img, n, cudaMemcpyDeviceToHost, st_out));
         if (lm_host)
             PEEB_CUDA(cudaMemcpy2DAsync(lm_host + (size_t)u0 * lmb, lmb, d2 + o_lm + (size_t)u0 * lm_al, lm_al, lmb, n,
-                                        cudaMemcpyDeviceToHost, st));
+                                        cudaMemcpyDeviceToHost, st_out));
         PEEB_CUDA(cudaMemcpyAsync(info_pin + (size_t)u0 * PEEB_INFO, (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO,
-                                  (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+                                  (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st_out));
     }
-    PEEB_CUDA(cudaStreamSynchronize(streams[0]));
-    PEEB_CUDA(cudaStreamSynchronize(streams[1]));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream2));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream3));
     memcpy(info_host, info_pin, (size_t)n_units * PEEB_INFO * 8);
     return PEEB_OK;
 }
@@ -334,31 +372,44 @@ int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h,
     char* d1 = (char*)ws->stage.ptr;
     char* d2 = (char*)ws->stage2.ptr;
     cudaStream_t streams[2] = {ws->stream, ws->stream2};
-    const int cu = std::min(chunk_units(n_units, img), 65535);
-    for (int u0 = 0, c = 0; u0 < n_units; u0 += cu, ++c) {
-        const int n = std::min(cu, n_units - u0), slot = c & 1;
-        cudaStream_t st = streams[slot];
+    const bool roles = ws->pipe_roles != 0;  // see peeb_pee_embed_h
+    const std::vector<int> plan = chunk_plan(n_units, img, 65535);
+    for (int u0 = 0, c = 0; c < (int)plan.size(); u0 += plan[c], ++c) {
+        const int n = plan[c], slot = c & 1;
+        cudaStream_t st_in = roles ? ws->stream : streams[slot], st = roles ? ws->stream2 : streams[slot];
+        cudaStream_t st_out = roles ? ws->stream3 : streams[slot];
         PEEB_CUDA(cudaMemcpy2DAsync(d1 + (size_t)u0 * img_al, img_al, (const char*)marked_host + (size_t)u0 * img, img, img, n,
-                                    cudaMemcpyHostToDevice, st));
+                                    cudaMemcpyHostToDevice, st_in));
         PEEB_CUDA(cudaMemcpy2DAsync(d2 + o_lm + (size_t)u0 * lm_al, lm_al, lm_host + (size_t)u0 * lmb, lmb, lmb, n,
-                                    cudaMemcpyHostToDevice, st));
+                                    cudaMemcpyHostToDevice, st_in));
+        if (roles) {
+            cudaEvent_t e = ws->pipe_ev[(2 * c) % peeb_ws::kPipeEvents];
+            PEEB_CUDA(cudaEventRecord(e, st_in));
+            PEEB_CUDA(cudaStreamWaitEvent(st, e, 0));
+        }
         rc = extract_batch_impl(ws, d1 + (size_t)u0 * img_al, (int64_t)img_al, n, h, w, itemsize, bit_depth, T + u0, n_bits + u0,
                                 (const uint8_t*)(d2 + o_lm + (size_t)u0 * lm_al), (int64_t)lm_al,
                                 (uint8_t*)(d2 + (size_t)u0 * pstride), (int64_t)pstride,
                                 recovered_host ? d1 + o_rec + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
                                 (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO, st, slot);
         if (rc) return rc;
+        if (roles) {
+            cudaEvent_t e = ws->pipe_ev[(2 * c + 1) % peeb_ws::kPipeEvents];
+            PEEB_CUDA(cudaEventRecord(e, st));
+            PEEB_CUDA(cudaStreamWaitEvent(st_out, e, 0));
+        }
         if (recovered_host)
             PEEB_CUDA(cudaMemcpy2DAsync((char*)recovered_host + (size_t)u0 * img, img, d1 + o_rec + (size_t)u0 * img_al, img_al,
-                                        img, n, cudaMemcpyDeviceToHost, st));
+                                        img, n, cudaMemcpyDeviceToHost, st_out));
         if (payload_stride > 0)
             PEEB_CUDA(cudaMemcpy2DAsync(payload_out_host + (size_t)u0 * payload_stride, (size_t)payload_stride,
-                                        d2 + (size_t)u0 * pstride, pstride, (size_t)payload_stride, n, cudaMemcpyDeviceToHost, st));
+                                        d2 + (size_t)u0 * pstride, pstride, (size_t)payload_stride, n, cudaMemcpyDeviceToHost, st_out));
         PEEB_CUDA(cudaMemcpyAsync(info_pin + (size_t)u0 * PEEB_INFO, (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO,
-                                  (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st));
+                                  (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st_out));
     }
-    PEEB_CUDA(cudaStreamSynchronize(streams[0]));
-    PEEB_CUDA(cudaStreamSynchronize(streams[1]));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream2));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream3));
     memcpy(info_host, info_pin, (size_t)n_units * PEEB_INFO * 8);
     return PEEB_OK;
 }

@@ -453,7 +453,7 @@ struct Count2 {
     bool acta, actb;
     __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
         acta = a; actb = b;
-        ka = make_ke(a ? T : 0); kb = make_ke(b ? T : 0);
+        ka = kb = make_ke(T);  // inactive rows compute like the others; nothing of theirs is kept
         na = nb = 0;
         ia = (rowa - row0) * g.ncol + cell;
     }
@@ -488,7 +488,7 @@ struct Count2 {
         if (GLOBAL) {
             if (acta) rowcnt[ia] = (unsigned char)na;
             if (actb) rowcnt[ia + g.ncol] = (unsigned char)nb;
-            total += na + nb;  // inactive rows run with T = 0 and count nothing
+            total += (acta ? na : 0) + (actb ? nb : 0);
         } else {
             if (acta) tab[ia] = na;
             if (actb) tab[ia + g.ncol] = nb;
@@ -526,7 +526,7 @@ struct Apply2 {
     }
     __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
         sta = a; stb = b;
-        ka = make_ke(a ? T : 0); kb = make_ke(b ? T : 0);
+        ka = kb = make_ke(T);
         const int ia = (rowa - row0) * g.ncol + cell;
         Wa = a ? window(tab[ia]) : 0u;
         Wb = b ? window(tab[ia + g.ncol]) : 0u;
@@ -875,7 +875,7 @@ struct Extract2 {
     unsigned long long la, lb;  // location-map bytes of this lane's cell in rows a and b (byte k = columns 8k..8k+7 of the cell)
     __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
         sta = a; stb = b;
-        ka = make_kx(a ? T : 0); kb = make_kx(b ? T : 0);
+        ka = kb = make_kx(T);
         Wa = Wb = 0u; na = nb = 0;
         ia = (rowa - own_lo) * g.ncol + cell;
         reca = a && rowa >= own_lo && rowa < own_hi;

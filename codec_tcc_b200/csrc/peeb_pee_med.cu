@@ -73,91 +73,190 @@ __device__ __forceinline__ void store8(PixT* row, int j0, int w, bool vec, const
     }
 }
 
-// One warp item = (unit, row, chunk); lane -> 8 pixels.  APPLY = false: count carriers of the chunk;
-// APPLY = true: write marked pixels, the location-map byte of every 8 columns, SSE / flag statistics.
+// eight pixels of a row starting at column j0, still packed (16-bit pixels: x..w; 8-bit pixels: x, y); 0 beyond
+// the row end.  Split from the unpacking so that the next row can be in flight while a row is processed.
+template <typename PixT>
+__device__ __forceinline__ uint4 fetch8(const PixT* row, int j0, int w, bool vec) {
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (vec && j0 + 8 <= w) {
+        if (sizeof(PixT) == 2) q = *reinterpret_cast<const uint4*>(row + j0);
+        else { const uint2 t = *reinterpret_cast<const uint2*>(row + j0); q.x = t.x; q.y = t.y; }
+    } else {
+        unsigned v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = j0 + k < w ? (unsigned)row[j0 + k] : 0u;
+        if (sizeof(PixT) == 2) { q.x = v[0] | (v[1] << 16); q.y = v[2] | (v[3] << 16); q.z = v[4] | (v[5] << 16); q.w = v[6] | (v[7] << 16); }
+        else { q.x = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); q.y = v[4] | (v[5] << 8) | (v[6] << 16) | (v[7] << 24); }
+    }
+    return q;
+}
+template <typename PixT>
+__device__ __forceinline__ void unpack8(const uint4& q, int (&v)[8]) {
+    if (sizeof(PixT) == 2) {
+        v[0] = q.x & 0xffff; v[1] = q.x >> 16; v[2] = q.y & 0xffff; v[3] = q.y >> 16;
+        v[4] = q.z & 0xffff; v[5] = q.z >> 16; v[6] = q.w & 0xffff; v[7] = q.w >> 16;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = (q.x >> (8 * k)) & 0xff; v[4 + k] = (q.y >> (8 * k)) & 0xff; }
+    }
+}
+
+// One warp item = (unit, block of `rb` consecutive rows, chunk); lane -> 8 pixels of every row of the block.
+// The warp walks down its rows: the row above a row is the row it has just read (each pixel is
+// loaded once), SSE / flag statistics are reduced once per item.  APPLY = false: count the carriers
+// of every (row, chunk); APPLY = true: write marked pixels, the location-map byte of every 8 columns,
+// SSE / flag statistics.  cnt / off are indexed [(unit * h + row) * nchunk + chunk] (raster order).
+//
+// A row first runs the FAST code: it assumes that no pixel over/underflows (every expandable pixel is
+// a carrier, the location-map byte is 0) and only watches for a value leaving [0, maxval); pixels
+// outside the domain (column 0, row 0, lanes past the row end) run with T = 0, which makes them
+// "shifted by 0".  If any lane of the warp sees a value leave the range, or a lane straddles the row
+// end, the row is redone by the GENERIC code (per-pixel domain test, flags, location map).
+struct MedRow {
+    int ncar;
+    unsigned carmask, lmbyte;
+    int nflag;
+};
+template <bool APPLY>
+__device__ __forceinline__ void med_row_generic(const int (&x)[8], const int (&up)[8], int left, int upleft, unsigned rmask,
+                                                int T, int maxval, int (&nv)[8], MedRow& r) {
+    const int T2 = 2 * T;
+    r.ncar = 0; r.carmask = 0; r.lmbyte = 0; r.nflag = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int a = k ? x[k - 1] : left, c = k ? up[k - 1] : upleft;
+        const int t = x[k] - med3(a, up[k], c) + T;                      // e + T
+        const bool expd = (unsigned)t < (unsigned)T2;                    // -T <= e < T
+        const int nv0 = x[k] + max(min(t, T2), 0) - T;                   // x + e | x + T | x - T
+        const bool ok = (unsigned)nv0 <= (unsigned)maxval - (expd ? 1u : 0u);
+        const bool in = (rmask >> k) & 1u;
+        if (in && expd && ok) { ++r.ncar; r.carmask |= 1u << k; }
+        nv[k] = (in && ok) ? nv0 : x[k];
+        if (APPLY && in && !ok) { r.lmbyte |= 0x80u >> k; ++r.nflag; }
+    }
+}
+// returns true when some value left [0, maxval): the caller falls back to the generic code
+__device__ __forceinline__ bool med_row_fast(const int (&x)[8], const int (&up)[8], int left, int upleft, int T0, int T,
+                                             int maxval, int (&nv)[8], MedRow& r) {
+    unsigned top = 0;
+    r.ncar = 0; r.carmask = 0; r.lmbyte = 0; r.nflag = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int a = k ? x[k - 1] : left, c = k ? up[k - 1] : upleft;
+        const int Tk = k ? T : T0;
+        const int t = x[k] - med3(a, up[k], c) + Tk;
+        nv[k] = x[k] + max(min(t, 2 * Tk), 0) - Tk;
+        top = max(top, (unsigned)nv[k]);
+        if ((unsigned)t < (unsigned)(2 * Tk)) { ++r.ncar; r.carmask |= 1u << k; }
+    }
+    return top >= (unsigned)maxval;
+}
+
 template <typename PixT, bool APPLY>
-__global__ void __launch_bounds__(256) med_embed_kernel(MedGeom g, PeeBatch bt, unsigned short* __restrict__ cnt,
+__global__ void __launch_bounds__(256) med_embed_kernel(MedGeom g, PeeBatch bt, int rb, unsigned short* __restrict__ cnt,
                                                         const unsigned* __restrict__ off) {
     const int lane = threadIdx.x & 31;
     const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long per_unit = (long long)g.h * g.nchunk;
+    const int nblk = (g.h + rb - 1) / rb;
+    const long long per_unit = (long long)nblk * g.nchunk;
     if (item >= per_unit * bt.n_units) return;
     const int unit = (int)(item / per_unit);
     const int rem = (int)(item - (long long)unit * per_unit);
-    const int row = rem / g.nchunk, chunk = rem - row * g.nchunk;
+    const int blk = rem / g.nchunk, chunk = rem - blk * g.nchunk;
+    const int row0 = blk * rb, row1 = min(row0 + rb, g.h);
     const unsigned char* ubase = bt.src + (long long)unit * bt.src_stride;
-    const PixT* cur = reinterpret_cast<const PixT*>(ubase) + (size_t)row * g.w;
     const bool vec_in = ((((uintptr_t)ubase) | ((uintptr_t)g.w * sizeof(PixT))) & (8 * sizeof(PixT) - 1)) == 0;
+    unsigned char* obase = APPLY && bt.dst ? bt.dst + (long long)unit * bt.dst_stride : nullptr;
+    const bool vec_out = ((((uintptr_t)obase) | ((uintptr_t)g.w * sizeof(PixT))) & (8 * sizeof(PixT) - 1)) == 0;
     const int j0 = chunk * MCHUNK + 8 * lane;
     const int T = bt.T[unit];
-    int x[8], nv[8];
-    load8<PixT>(cur, j0, g.w, vec_in, x);
-    int ncar = 0, nflag = 0;
-    unsigned carmask = 0, lmbyte = 0;
-    long long sse = 0;
+    const unsigned n_bits = bt.n_bits[unit];
+    const unsigned* pay = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
+    unsigned vmask = 0;  // pixels of this lane inside the domain 1 <= j < w
 #pragma unroll
-    for (int k = 0; k < 8; ++k) nv[k] = x[k];
-    if (row >= 1) {
-        int up[8];
+    for (int k = 0; k < 8; ++k) vmask |= (j0 + k >= 1 && j0 + k < g.w) ? 1u << k : 0u;
+    // fast code: a lane is either inside the row or past its end (T = 0 there); its first pixel may be column 0
+    const bool straddle = __any_sync(0xffffffffu, j0 < g.w && j0 + 8 > g.w);
+    const int Tl = j0 + 8 <= g.w ? T : 0, Tl0 = j0 >= 1 ? Tl : 0;
+    const PixT* cur = reinterpret_cast<const PixT*>(ubase) + (size_t)row0 * g.w;
+    int up[8], upleft = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) up[k] = 0;
+    if (row0 >= 1) {
         load8<PixT>(cur - g.w, j0, g.w, vec_in, up);
-        // W / NW of the lane's first pixel: the previous lane's last pixel (lane 0: one scalar load each)
-        int left = __shfl_up_sync(0xffffffffu, x[7], 1), upleft = __shfl_up_sync(0xffffffffu, up[7], 1);
-        if (lane == 0 && j0 > 0) { left = cur[j0 - 1]; upleft = cur[j0 - 1 - g.w]; }
+        upleft = __shfl_up_sync(0xffffffffu, up[7], 1);
+        if (lane == 0) upleft = j0 > 0 ? (int)cur[j0 - 1 - g.w] : 0;
+    }
+    long long sse = 0;
+    int nflag = 0;
+    long long e = ((long long)unit * g.h + row0) * g.nchunk + chunk;  // index of (row, chunk) in cnt / off
+    // the next row is fetched while a row is processed (one 16-byte load per lane and row would
+    // otherwise leave the memory system mostly idle)
+    uint4 qc = fetch8<PixT>(cur, j0, g.w, vec_in);
+    int lc = (lane == 0 && j0 > 0) ? (int)cur[j0 - 1] : 0;
+    for (int row = row0; row < row1; ++row, cur += g.w, e += g.nchunk) {
+        int x[8], nv[8];
+        uint4 qn = make_uint4(0u, 0u, 0u, 0u);
+        int ln = 0;
+        if (row + 1 < row1) {
+            qn = fetch8<PixT>(cur + g.w, j0, g.w, vec_in);
+            if (lane == 0 && j0 > 0) ln = (int)cur[g.w + j0 - 1];
+        }
+        unpack8<PixT>(qc, x);
+        // W of the lane's first pixel: the previous lane's last pixel (lane 0: one scalar load)
+        int left = __shfl_up_sync(0xffffffffu, x[7], 1);
+        if (lane == 0) left = lc;
+        MedRow r;
+        bool redo = straddle;
+        if (!redo) {
+            const bool inrow = row >= 1;  // row 0 never changes
+            redo = __any_sync(0xffffffffu, med_row_fast(x, up, left, upleft, inrow ? Tl0 : 0, inrow ? Tl : 0, g.maxval, nv, r));
+        }
+        if (redo) med_row_generic<APPLY>(x, up, left, upleft, row >= 1 ? vmask : 0u, T, g.maxval, nv, r);
+        int ncar = r.ncar;
+        if constexpr (!APPLY) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int j = j0 + k;
-            const int a = k ? x[k - 1] : left, c = k ? up[k - 1] : upleft;
-            if (j >= 1 && j < g.w) {
-                const int t = x[k] - med3(a, up[k], c) + T;                      // e + T
-                const bool expd = (unsigned)t < (unsigned)(2 * T);               // -T <= e < T
-                const int nv0 = x[k] + max(min(t, 2 * T), 0) - T;                // x + e | x + T | x - T
-                const bool ok = (unsigned)nv0 <= (unsigned)g.maxval - (expd ? 1u : 0u);
-                if (expd && ok) { ++ncar; carmask |= 1u << k; }
-                if (ok) nv[k] = nv0; else { lmbyte |= 0x80u >> k; ++nflag; }
+            for (int o = 16; o > 0; o >>= 1) ncar += __shfl_xor_sync(0xffffffffu, ncar, o);
+            if (lane == 0) cnt[e] = (unsigned short)ncar;
+        } else {
+            // rank of the lane's first carrier inside the chunk, then the chunk's offset in the unit's raster order
+            int incl = ncar;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
             }
+            if (ncar) {
+                const unsigned base = off[e] + (unsigned)(incl - ncar);
+                unsigned win = 0;  // bits base .. base+7 on top, zero past n_bits
+                if (base < n_bits) {
+                    const unsigned w0 = __byte_perm(__ldg(pay + (base >> 5)), 0, 0x0123), w1 = __byte_perm(__ldg(pay + (base >> 5) + 1), 0, 0x0123);
+                    win = __funnelshift_l(w1, w0, base & 31);
+                    if (n_bits - base < 32u) win &= ~(0xffffffffu >> (n_bits - base));
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (r.carmask & (1u << k)) { nv[k] += (int)(win >> 31); win <<= 1; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int d = nv[k] - x[k]; sse += (long long)d * d; }
+            nflag += r.nflag;
+            if (obase) store8<PixT>(reinterpret_cast<PixT*>(obase) + (size_t)row * g.w, j0, g.w, vec_out, nv);
+            if (bt.lm && j0 < g.w) bt.lm[(long long)unit * bt.lm_stride + (size_t)row * g.lmw + (j0 >> 3)] = (unsigned char)r.lmbyte;
         }
-    }
-    if (!APPLY) {
+        upleft = left;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ncar += __shfl_xor_sync(0xffffffffu, ncar, o);
-        if (lane == 0) cnt[item] = (unsigned short)ncar;
-        return;
+        for (int k = 0; k < 8; ++k) up[k] = x[k];
+        qc = qn; lc = ln;
     }
-    // rank of the lane's first carrier inside the chunk, then the chunk's offset in the unit's raster order
-    int incl = ncar;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (ncar) {
-        const unsigned n_bits = bt.n_bits[unit];
-        const unsigned* pay = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
-        const unsigned base = off[item] + (unsigned)(incl - ncar);
-        unsigned win = 0;  // bits base .. base+7 on top, zero past n_bits
-        if (base < n_bits) {
-            const unsigned w0 = __byte_perm(__ldg(pay + (base >> 5)), 0, 0x0123), w1 = __byte_perm(__ldg(pay + (base >> 5) + 1), 0, 0x0123);
-            win = __funnelshift_l(w1, w0, base & 31);
-            if (n_bits - base < 32u) win &= ~(0xffffffffu >> (n_bits - base));
+    if constexpr (APPLY) {
+        sse = warp_sum_i64(sse);
+        nflag = (int)warp_sum_i64(nflag);
+        if (lane == 0) {
+            long long* info = bt.info + (long long)unit * PEEB_INFO;
+            if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(info + 6), (unsigned long long)sse);
+            if (nflag) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)nflag);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (carmask & (1u << k)) { nv[k] += (int)(win >> 31); win <<= 1; }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const int d = nv[k] - x[k]; sse += (long long)d * d; }
-    if (bt.dst) {
-        unsigned char* obase = bt.dst + (long long)unit * bt.dst_stride;
-        const bool vec_out = ((((uintptr_t)obase) | ((uintptr_t)g.w * sizeof(PixT))) & (8 * sizeof(PixT) - 1)) == 0;
-        store8<PixT>(reinterpret_cast<PixT*>(obase) + (size_t)row * g.w, j0, g.w, vec_out, nv);
-    }
-    if (bt.lm && j0 < g.w) bt.lm[(long long)unit * bt.lm_stride + (size_t)row * g.lmw + (j0 >> 3)] = (unsigned char)lmbyte;
-    sse = warp_sum_i64(sse);
-    nflag = (int)warp_sum_i64(nflag);
-    if (lane == 0) {
-        long long* info = bt.info + (long long)unit * PEEB_INFO;
-        if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(info + 6), (unsigned long long)sse);
-        if (nflag) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)nflag);
     }
 }
 
@@ -507,14 +606,20 @@ int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, i
     bt.lm = lm; bt.lm_stride = lm_stride;
     bt.payload = payload; bt.payload_stride = payload_stride;
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
-    const unsigned blocks = (unsigned)((ne + 7) / 8);
+    // rows per warp item: long enough to amortise the set-up, short enough to leave ~8 items per
+    // resident warp slot for load balance
+    int rb = 16;
+    while (rb > 1 && (long long)n_units * ((h + rb - 1) / rb) * g.nchunk < (long long)ws->sm_count * 64 * 4) rb >>= 1;
+    if (const char* e = getenv("PEEB_MED_ROWS")) rb = std::max(1, atoi(e));
+    const long long nitems = (long long)n_units * ((h + rb - 1) / rb) * g.nchunk;
+    const unsigned blocks = (unsigned)((nitems + 7) / 8);
     { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-      if (itemsize == 2) med_embed_kernel<unsigned short, false><<<blocks, 256, 0, st>>>(g, bt, cnt, off);
-      else med_embed_kernel<unsigned char, false><<<blocks, 256, 0, st>>>(g, bt, cnt, off); }
+      if (itemsize == 2) med_embed_kernel<unsigned short, false><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off);
+      else med_embed_kernel<unsigned char, false><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off); }
     med_scan_kernel<<<n_units, 1024, 0, st>>>(g, bt, cnt, off);
     { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
-      if (itemsize == 2) med_embed_kernel<unsigned short, true><<<blocks, 256, 0, st>>>(g, bt, cnt, off);
-      else med_embed_kernel<unsigned char, true><<<blocks, 256, 0, st>>>(g, bt, cnt, off); }
+      if (itemsize == 2) med_embed_kernel<unsigned short, true><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off);
+      else med_embed_kernel<unsigned char, true><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off); }
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }
