@@ -413,7 +413,11 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
             pu += 16; pa += 16; pb += 16; pd += 16;
         }
 #else
+#ifdef PEEB_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int s = 0; s < g.cws; ++s) {
             const int c = c0 + s * P::PXS;
             const uint4 U = lds128(pu), D = lds128(pd);

@@ -20,3 +20,15 @@ for f in funcs[1:]:
                     if sum('IDP' in b for b in body)==0: continue
                     # fast part: up to first '@!P0 BRA' after a VOTE following IDPs
                     print(f"  loop {t}->{i} len {i-t+1} IDP {sum('IDP' in b for b in body)} MOV {sum('MOV' in b for b in body)} UMOV {sum('UMOV' in b for b in body)} SEL {sum(b.startswith('SEL') for b in body)}")
+
+
+def dump(pattern, first, last, obj=obj):
+    """print instructions [first, last] of the first function whose name matches `pattern`"""
+    for f in funcs[1:]:
+        name = f.split('\n', 1)[0]
+        if not re.search(pattern, name):
+            continue
+        ls = [re.sub(r'\s*/\*.*$', '', re.sub(r'^\s+/\*[0-9a-f]+\*/\s+', '', l)) for l in f.split('\n') if re.match(r'^\s+/\*[0-9a-f]{4}\*/', l)]
+        for i in range(first, min(last, len(ls) - 1) + 1):
+            print(i, hex(i * 16), ls[i])
+        break
