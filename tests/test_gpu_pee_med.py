@@ -36,6 +36,23 @@ def test_med_gpu_vs_oracle(idx):
         pee.pee_embed(img, pay, T, bd, n_bits=cap + 1, predictor="med")
 
 
+@pytest.mark.parametrize("rows", [3, 16])
+def test_med_embed_multi_row_items(rows, monkeypatch):
+    """The embed kernels walk `rows` consecutive rows per warp item (the library picks 1 for small batches,
+    up to 16 for large ones): same bits for every choice, also when h is not a multiple of it."""
+    monkeypatch.setenv("PEEB_MED_ROWS", str(rows))
+    for idx in (0, 1, 3, 4, 10, 11, 13, 14):
+        img, bd, T = CASES[idx]
+        pay = random_payload(img.size, 300 + idx)
+        cap = pee_c.embed(img, pay, img.size, T, bd, predictor="med")[2]["capacity"]
+        m0, lm0, i0 = pee_c.embed(img, pay, cap, T, bd, predictor="med")
+        m, lm, info = pee.pee_embed(img, pay, T, bd, n_bits=cap, predictor="med")
+        assert np.array_equal(m, m0) and np.array_equal(lm, lm0), (rows, idx)
+        assert {k: info[k] for k in ("capacity", "n_flagged", "sse")} == {k: i0[k] for k in ("capacity", "n_flagged", "sse")}
+        out, rec = pee.pee_extract(m, lm, T, cap, bd, predictor="med")
+        assert np.array_equal(rec, img) and np.array_equal(np.unpackbits(out)[:cap], np.unpackbits(pay)[:cap])
+
+
 def test_med_batch_and_auto_threshold():
     imgs = synth_batch(5, 96, 160, 4095, 31)
     pays = np.stack([random_payload(imgs[0].size, 70 + k) for k in range(5)])
