@@ -255,7 +255,11 @@ def run_gpu_arm(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    rank_ms = [ms_total / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        rank_ms = [float(x.item()) / args.steps for x in every]  # reported beside the max: a straggler shows
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = npx * world / (ms_step * 1e-3) / 1e6
@@ -360,7 +364,7 @@ def run_gpu_arm(args):
             "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
             "capacity_bpp": float(cap.mean() / (h * w)), "images_total": int(stats.shape[0]),
             "bit_exact": "round trip identity on all images; first 2 images == CPU oracle (oracle/pee_ref.c)",
-            "numa_cores_rank0": len(numa_cores),
+            "numa_cores_rank0": len(numa_cores), "ms_per_step_by_rank": [round(x, 4) for x in rank_ms],
             "setup_s": gen_s,
         }
         if cpu_baseline is not None:
