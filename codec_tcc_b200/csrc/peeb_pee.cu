@@ -154,12 +154,13 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
         const size_t pb = peeb_payload_bytes(n_bits[u]);
         PEEB_REQUIRE(n_units == 1 || (int64_t)pb <= payload_stride, "peeb_pee_extract_batch: payload_stride too small for unit %d", u);
     }
-    // zero every unit's output words (the gather kernel ORs the boundary words in)
-    if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
-    else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
+    // every unit's output words start from zero: the extract kernel clears them itself (the gather kernel
+    // ORs the boundary words in); the path for images without an interior uses a memset
     if (h >= 3 && w >= 3)
         return extract_batch_impl2(ws, marked, marked_stride, n_units, h, w, itemsize, bit_depth, T, n_bits, lm, lm_stride,
                                    payload_out, payload_stride, recovered, recovered_stride, info, st, slot);
+    if (n_units == 1) PEEB_CUDA(cudaMemsetAsync(payload_out, 0, peeb_payload_bytes(n_bits[0]), st));
+    else PEEB_CUDA(cudaMemsetAsync(payload_out, 0, (size_t)payload_stride * n_units, st));
     int* dT; unsigned* dN; char* extra;
     int rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, 256, st, &dT, &dN, &extra);
     if (rc) return rc;

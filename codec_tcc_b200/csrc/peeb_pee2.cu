@@ -640,7 +640,9 @@ __device__ __forceinline__ void stage_payload(const unsigned* __restrict__ pay, 
 // ------------------------------------------------------------------ K_A: pass-0 counts
 template <typename PixT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch bt, int* __restrict__ band_cnt,
-                                                              unsigned char* __restrict__ rowcnt) {
+                                                              unsigned char* __restrict__ rowcnt,
+                                                              unsigned* __restrict__ ticket,
+                                                              unsigned long long* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem2 L = layout2(g, 0);
     unsigned char* simg = smem_raw + L.img;
@@ -651,7 +653,15 @@ __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch 
     __syncthreads();
     const int r0 = band * g.R, r_first = r0 - 2;
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
-    load_rows2<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
+    issue_rows2<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
+    // this launch also resets what the embed kernel behind it starts from (no memsets on the stream):
+    // the band's look-back status word, the ticket counter, the unit's summary row
+    if (threadIdx.x == 0) {
+        status[blockIdx.x] = 0ull;
+        if (blockIdx.x == 0) *ticket = 0u;
+    }
+    if (band == 0 && threadIdx.x < PEEB_INFO) bt.info[(long long)unit * PEEB_INFO + threadIdx.x] = 0;
+    wait_rows2(g, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     Count2<PixT, true> body{g, 0, rowcnt + (long long)unit * g.h * g.ncol, nullptr, 0};
     sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, bt.T[unit], body);
@@ -662,8 +672,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch 
     __syncthreads();
     if (threadIdx.x == 0) {
         const int all = misc[0];
-        band_cnt[unit * g.nb + band] = all;
-        if (all) atomicAdd(reinterpret_cast<unsigned long long*>(bt.info + (long long)unit * PEEB_INFO + 3), (unsigned long long)all);
+        band_cnt[unit * g.nb + band] = all;  // cap0 of the unit = their sum (the embed kernel adds them up)
     }
 }
 
@@ -815,7 +824,13 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
             if (lane == 0) {
                 st_relaxed_gpu(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
                 misc[43] = (int)before;
-                if (total) atomicAdd(reinterpret_cast<unsigned long long*>(info + 4), (unsigned long long)total);
+                if (band == g.nb - 1) {
+                    // the last band knows both pass totals: it writes the unit's summary (no separate kernel);
+                    // n_flagged and sse (info[5], info[6]) are summed by every band with atomics
+                    const long long cap0 = misc[42], cap1 = (long long)before + total;
+                    info[0] = T; info[1] = n_bits; info[2] = cap0 + cap1; info[3] = cap0; info[4] = cap1;
+                    info[7] = ((long long)n_bits > cap0 + cap1) ? PEEB_E_CAPACITY : 0;
+                }
             }
         }
         PHASE_MARK(8);  // look-back
@@ -943,7 +958,7 @@ struct Extract2 {
 // 31-(k&31) of word k>>5; stage_cnt: carriers per (unit, pass, band).
 template <typename PixT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatch bt, unsigned* __restrict__ stage_bits,
-                                                                int* __restrict__ stage_cnt) {
+                                                                int* __restrict__ stage_cnt, long long zero_words) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem2 L = layout2(g, 2);
     unsigned char* simg = smem_raw + L.img;
@@ -997,6 +1012,11 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         for (int r = warp; r < g.R + 2; r += nwarps)
             if (lane < padb) slm[(size_t)r * g.lmpitch + g.lmw + lane] = 0;
         for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
+        // the unit's output words start from zero (the gather kernel ORs the boundary words in and skips
+        // zero words): every band clears its share, instead of a memset on the stream
+        unsigned* pout = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
+        const long long z_lo = zero_words * band / g.nb, z_hi = zero_words * (band + 1) / g.nb;
+        for (long long k = z_lo + threadIdx.x; k < z_hi; k += blockDim.x) pout[k] = 0u;
     }
     wait_rows2(g, s_lo, s_hi, bar);
     PHASE_MARK(0);  // load
@@ -1107,16 +1127,6 @@ __global__ void __launch_bounds__(128) pee2_gather_kernel(int nb, int bandwords,
     }
 }
 
-__global__ void pee2_finalize_kernel(PeeBatch bt) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= bt.n_units) return;
-    long long* info = bt.info + (long long)u * PEEB_INFO;
-    info[0] = bt.T[u];
-    info[1] = bt.n_bits[u];
-    info[2] = info[3] + info[4];
-    info[7] = ((long long)bt.n_bits[u] > info[2]) ? PEEB_E_CAPACITY : 0;
-}
-
 // ------------------------------------------------------------------ host side
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 
@@ -1220,18 +1230,18 @@ static int launch_embed2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long l
     int rc = set_smem2(pee2_count_kernel<PixT, NT, MINB>, smem0); if (rc) return rc;
     rc = set_smem2(pee2_embed_kernel<PixT, NT, MINB>, smem1); if (rc) return rc;
     { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-      pee2_count_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem0, st>>>(g, bt, band_cnt, rowcnt); }
+      pee2_count_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem0, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
     { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
       pee2_embed_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem1, st>>>(g, bt, band_cnt, rowcnt, ticket, status); }
     return PEEB_OK;
 }
 template <typename PixT, int NT, int MINB>
 static int launch_extract2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long long nbands, unsigned* stage_bits,
-                           int* stage_cnt, cudaStream_t st) {
+                           int* stage_cnt, long long zero_words, cudaStream_t st) {
     const size_t smem = layout2(g, 2).total;
     int rc = set_smem2(pee2_extract_kernel<PixT, NT, MINB>, smem); if (rc) return rc;
     ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
-    pee2_extract_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem, st>>>(g, bt, stage_bits, stage_cnt);
+    pee2_extract_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem, st>>>(g, bt, stage_bits, stage_cnt, zero_words);
     return PEEB_OK;
 }
 // (CTA size, CTAs per SM) pairs the kernels are compiled for: registers per thread = 64K / (NT * MINB)
@@ -1264,8 +1274,6 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     unsigned long long* status = (unsigned long long*)(extra + cnt_bytes);
     unsigned* ticket = (unsigned*)(extra + cnt_bytes + st_bytes);
     unsigned char* rowcnt = (unsigned char*)(extra + cnt_bytes + st_bytes + 256);
-    PEEB_CUDA(cudaMemsetAsync(status, 0, st_bytes + 256, st));
-    PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
     PeeBatch bt{};
     bt.src = (const unsigned char*)src; bt.src_stride = src_stride;
     bt.dst = (unsigned char*)marked; bt.dst_stride = marked_stride;
@@ -1274,9 +1282,6 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
     rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
     if (rc) return rc;
-    PEEB_CUDA(cudaGetLastError());
-    { ProfScope p(ws, PEEB_K_PEE_FINAL, st);
-      pee2_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt); }
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }
@@ -1306,7 +1311,9 @@ int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, 
     bt.lm = const_cast<uint8_t*>(lm); bt.lm_stride = lm_stride;
     bt.payload = nullptr; bt.payload_stride = payload_stride; bt.payload_out = payload_out;
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
-    rc = PEEB_DISPATCH2(launch_extract2, ws, g, bt, nbands, stage_bits, stage_cnt, st);
+    // bytes of every unit's output that start from zero: the whole row of a batch, the payload's own bytes for one unit
+    const long long zero_words = (long long)(n_units == 1 ? peeb_payload_bytes(n_bits[0]) : (size_t)payload_stride) / 4;
+    rc = PEEB_DISPATCH2(launch_extract2, ws, g, bt, nbands, stage_bits, stage_cnt, zero_words, st);
     if (rc) return rc;
     PEEB_CUDA(cudaGetLastError());
     {
