@@ -122,14 +122,46 @@ def workload_config(name, world):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region.  NVML in process
+    (initialised before the region, a few microseconds per sample); starting an `nvidia-smi -lms`
+    child instead puts its start-up (driver enumeration of every GPU of the box) inside the region,
+    which showed up once as a straggling rank of a multi-GPU run.  nvidia-smi stays as the fallback."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"),
+               (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml = self.handle = None
+        self.samples, self.bits, self.stop_flag = [], 0, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = (pynvml.nvmlDeviceGetHandleByUUID(uuid if isinstance(uuid, bytes) else uuid.encode())
+                           if uuid else pynvml.nvmlDeviceGetHandleByIndex(gpu_index))
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001 - no NVML binding / no permission: nvidia-smi child below
+            self.nvml = None
+
+    def _poll(self):
+        nv, hd = self.nvml, self.handle
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(hd))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -143,6 +175,13 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            sm = self.samples
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax,
+                    "reasons": sorted(name for bit, name in self.REASONS if self.bits & bit), "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -160,7 +199,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ the GPU arm
@@ -247,7 +286,11 @@ def run_gpu_arm(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:  # noqa: BLE001
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid)
     if rank == 0:
         sampler.start()
     barrier()
