@@ -487,8 +487,7 @@ def extract_message_bits(stego_array, metadata, device=None):
         ws = workspace(device)
         check(lib().peeb_lsb_extract_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, int(metadata["s"]), ptr(start),
                                        ptr(length), ptr(off), total, ptr(out)), "peeb_lsb_extract_h")
-    bits = np.unpackbits(out)[:total]
-    return "".join("1" if v else "0" for v in bits.tolist())
+    return (np.unpackbits(out)[:total] + np.uint8(48)).tobytes().decode("ascii")  # 0 / 1 -> "0" / "1"
 
 
 def extract_message(stego_array, metadata, device=None):

@@ -149,6 +149,21 @@ assert all(np.array_equal(a, b) for a, b in zip(ref[0] + ref[1], got[0] + got[1]
 rows[-1].update(api_ms=t_api * 1e3, api_mpixel_s=npx / t_api / 1e6, cpu_oracle_ms=t_cpu * 1e3, cpu_oracle_mpixel_s=npx / t_cpu / 1e6,
                 api="lsb_embed_block_then_multiplane (numpy planes in/out, '0'/'1' string payload); outputs equal the restatement")
 
+# ---- a5-a8 chained: the reference's encode flow (decompose -> hybrid embed -> merge), device resident
+t_api = wall(lambda: codec.embed_pipeline(imgs[0], bits, beta=0.8, search_block_size=16), reps=2)
+t0 = time.perf_counter()
+g0, l0 = OC.adaptive_modalities_decomposition(imgs[0], beta=0.8)
+r_e = OC.lsb_embed_block_then_multiplane(l0, bits, search_block_size=16)
+r_m = OC.merge_modalities(g0, r_e[0])
+t_cpu = time.perf_counter() - t0
+p_st, p_bm, p_meta = codec.embed_pipeline(imgs[0], bits, beta=0.8, search_block_size=16)
+assert np.array_equal(p_st, r_m) and all(np.array_equal(a, b) for a, b in zip(p_bm, r_e[1])) and p_meta["segments_indices"] == r_e[4]
+rows.append({"row": "a5-a8", "kernel": "hist + planes_unpack + tile_moments + lsb_embed + planes_pack (one upload, one download)",
+             "workload": f"3000x3000 u16 (12-bit), {pay_bits / 1e6:.1f} Mbit payload, s={s}", "api_ms": t_api * 1e3,
+             "api_mpixel_s": npx / t_api / 1e6, "cpu_oracle_ms": t_cpu * 1e3, "cpu_oracle_mpixel_s": npx / t_cpu / 1e6,
+             "api": "codec.embed_pipeline (numpy image + '0'/'1' string in, stego image + uint8 bitmaps out) against the chained "
+                    "restatements of adaptive_modalities_decomposition, lsb_embed_block_then_multiplane, merge_modalities; outputs equal"})
+
 # ---- a9: decode_message
 meta = {"s": s, "segments_indices": got[4], "segments_lengths": got[3]}
 t_api = wall(lambda: codec.decode_message(got[0], got[1], meta), reps=1)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Development aid: device-resident step time and per-kernel times of the PEE round trip for one workload
 (the timed part of bench.py without its CPU legs), to compare library variants quickly.
-    python scripts/kernel_ab.py [ct512|dx3000|slice] [steps]"""
+    python scripts/kernel_ab.py [ct512|dx3000|slice|custom:n,h,w,bit_depth,T] [steps]"""
 import os
 import sys
 
@@ -15,7 +15,11 @@ from codec_tcc_b200.synth import synth_batch  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "ct512"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-n, h, w, maxval, bd, T = WORKLOADS[name]
+if name.startswith("custom:"):  # custom:n,h,w,bit_depth,T
+    n, h, w, bd, T = (int(x) for x in name[7:].split(","))
+    maxval = (1 << bd) - 1
+else:
+    n, h, w, maxval, bd, T = WORKLOADS[name]
 dev = torch.device("cuda:0")
 imgs = synth_batch(n, h, w, maxval, 2)
 d_imgs = torch.from_numpy(imgs.view(np.int16) if imgs.dtype == np.uint16 else imgs).to(dev)
