@@ -6,6 +6,8 @@
 //   compact_bits  : decode_message's "LSBs where the bitmap is set" gather
 // All of it is streaming byte/integer work: 128-bit coalesced accesses, grids
 // sized in multiples of the SM count, no tensor cores.
+#include <algorithm>
+
 #include "peeb_common.cuh"
 
 namespace peeb {
@@ -54,6 +56,76 @@ __global__ void __launch_bounds__(256) hist_kernel(const unsigned char* __restri
     }
 }
 
+// 16-bit data: one CTA of 1024 threads per SM with 128 KB of shared counters, used in one of two ways that
+// the CTA picks from a strided sample of its own part of the image (no host round trip, exact either way):
+//   window  32-bit counters for the bins [0, 32768) -- 8..15-bit data in uint16 containers; a value above
+//           the window (the sample missed it) goes to the global histogram with an atomic;
+//   packed  all 65 536 bins as packed 16-bit counters.  The CTA counts at most 57 344 pixels (7 x 8 per
+//           thread) between two flushes to the global histogram, so no 16-bit counter can wrap and no
+//           carry can reach its neighbour.
+__global__ void __launch_bounds__(1024) hist16_kernel(const unsigned char* __restrict__ img, long long n,
+                                                      unsigned* __restrict__ hist, int force_window) {
+    extern __shared__ unsigned sh[];
+    constexpr int ROUNDS = 7;  // 7 * 1024 threads * 8 pixels < 65 536
+    const unsigned short* px = reinterpret_cast<const unsigned short*>(img);
+    const bool aligned = (((uintptr_t)img) & 15) == 0;
+    const long long nvec = aligned ? n / 8 : 0;
+    const int4* q = reinterpret_cast<const int4*>(img);
+    const long long chunk = (long long)ROUNDS * blockDim.x;
+    // sample: one pixel per thread out of each of the first chunks this CTA will read
+    unsigned top = 0;
+    if (!force_window) {
+        const long long first = (long long)blockIdx.x * chunk * 8, step = (long long)gridDim.x * chunk * 8;
+        for (int k = 0; k < 4; ++k) {
+            const long long e = first + k * step + (long long)threadIdx.x * (ROUNDS * 8) + 5;
+            if (e < n) top = max(top, (unsigned)px[e]);
+        }
+    }
+    for (int k = threadIdx.x; k < 32768; k += blockDim.x) sh[k] = 0;
+    const bool packed = __syncthreads_or(top >= 32768u) != 0;  // also orders the zeroing before the counting
+    auto flush = [&]() {
+        __syncthreads();
+        for (int k = threadIdx.x; k < 32768; k += blockDim.x) {
+            const unsigned c = sh[k];
+            if (c) {
+                if (packed) {
+                    if (c & 0xffffu) atomicAdd(hist + 2 * k, c & 0xffffu);
+                    if (c >> 16) atomicAdd(hist + 2 * k + 1, c >> 16);
+                } else {
+                    atomicAdd(hist + k, c);
+                }
+                sh[k] = 0;
+            }
+        }
+        __syncthreads();
+    };
+    auto put = [&](unsigned v) {
+        if (packed) atomicAdd(sh + (v >> 1), (v & 1u) ? 0x10000u : 1u);
+        else if (v < 32768u) atomicAdd(sh + v, 1u);
+        else atomicAdd(hist + v, 1u);
+    };
+    for (long long base = (long long)blockIdx.x * chunk; base < nvec; base += (long long)gridDim.x * chunk) {
+#pragma unroll
+        for (int r = 0; r < ROUNDS; ++r) {
+            const long long i = base + (long long)r * blockDim.x + threadIdx.x;
+            if (i < nvec) {
+                const int4 v = ldg_stream(q + i);
+                const unsigned wv[4] = {(unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { put(wv[k] & 0xffffu); put(wv[k] >> 16); }
+            }
+        }
+        if (packed) flush();  // 32-bit window counters cannot wrap (n < 2^32): they are flushed once, at the end
+    }
+    // what the vector loop left (unaligned image: everything), in slices of 57 344 pixels per CTA
+    const long long rest0 = nvec * 8, slice = chunk * 8;
+    for (long long base = rest0 + (long long)blockIdx.x * slice; base < n; base += (long long)gridDim.x * slice) {
+        for (long long e = base + threadIdx.x; e < min(base + slice, n); e += blockDim.x) put((unsigned)px[e]);
+        if (packed) flush();
+    }
+    if (!packed) flush();
+}
+
 // plane_ones[b] = sum over values v with bit b set of hist[v]  (one block)
 __global__ void __launch_bounds__(256) hist_to_planes_kernel(const unsigned* __restrict__ hist, int nbins,
                                                              unsigned long long* __restrict__ plane_ones) {
@@ -89,7 +161,12 @@ static int launch_hist(peeb_ws* ws, const void* img, int64_t n, int itemsize, ui
         ProfScope p(ws, PEEB_K_HIST_PLANES, st);
         if (n > 0) {
             const unsigned grid = grid_for(ws, n, 256 * (16 / itemsize) * 8, 3);
-            if (itemsize == 2) {
+            if (itemsize == 2 && (size_t)ws->max_smem_optin >= 131072) {
+                PEEB_CUDA(cudaFuncSetAttribute(hist16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+                const long long per_cta = 7 * 1024 * 8;
+                const unsigned g16 = (unsigned)std::max<long long>(1, std::min<long long>(ws->sm_count, (n + per_cta - 1) / per_cta));
+                hist16_kernel<<<g16, 1024, 131072, st>>>((const unsigned char*)img, n, hist, getenv("PEEB_HIST_WINDOW_ONLY") ? 1 : 0);
+            } else if (itemsize == 2) {
                 PEEB_CUDA(cudaFuncSetAttribute(hist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 hist_kernel<2><<<grid, 256, smem, st>>>((const unsigned char*)img, n, win, hist);
             } else {

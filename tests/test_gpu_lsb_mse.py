@@ -77,6 +77,31 @@ def _same(r, o):
         assert a.dtype == b.dtype == np.uint8 and np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("shape,hi", [((257, 301), 65536), ((64, 64), 65536), ((1000, 1003), 65536), ((300, 331), 20000),
+                                      ((129, 77), 4096), ((1, 5), 65536), ((2100, 2050), 65536)])
+def test_histogram_full_range_16bit(shape, hi, monkeypatch):
+    """Row a5's histogram on 16-bit data that leaves the 16 K-bin window (packed full-range counters) and on
+    data inside it (window kernel), forced both ways: exact counts and plane population counts."""
+    from codec_tcc_b200 import codec
+    rng = np.random.default_rng(shape[0] * 7 + hi)
+    img = rng.integers(0, hi, shape, dtype=np.uint16)
+    img[0, 0] = hi - 1
+    flat = np.concatenate([np.zeros(1, np.uint16), img.reshape(-1)])[1:].reshape(shape)  # a view that is only 2-byte aligned
+    ref = np.bincount(img.reshape(-1), minlength=65536)
+    ones = np.array([int(((img >> b) & 1).sum()) for b in range(16)])
+    for force_window in (False, True):
+        if force_window:
+            monkeypatch.setenv("PEEB_HIST_WINDOW_ONLY", "1")
+        for a in (img, flat):
+            hist, po = codec._image_histogram(a)
+            assert np.array_equal(hist, ref) and np.array_equal(po, ones)
+    # many hits on one bin: more than a 16-bit counter holds
+    big = np.full((700, 700), 60001, np.uint16)
+    big[::7, ::3] = 60000
+    hist, _ = codec._image_histogram(big)
+    assert np.array_equal(hist, np.bincount(big.reshape(-1), minlength=65536))
+
+
 def test_metrics_scalars(golden):
     an = mse.AnalisadorMSE()
     sc = golden["scalars"]
