@@ -72,6 +72,14 @@ int peeb_ws_create(int device, peeb_ws** out) {
     ws->sm_count = prop.multiProcessorCount;
     ws->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+    {   // peeb_dev_alloc / peeb_dev_free: keep freed blocks in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream2, cudaStreamNonBlocking));
     PEEB_CUDA(cudaStreamCreateWithFlags(&ws->stream3, cudaStreamNonBlocking));
     for (int i = 0; i < peeb_ws::kPipeEvents; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pipe_ev[i], cudaEventDisableTiming));
@@ -148,14 +156,17 @@ int peeb_host_free(void* ptr) {
 int peeb_dev_alloc(peeb_ws* ws, size_t bytes, void** ptr) {
     PEEB_REQUIRE(ws && ptr, "peeb_dev_alloc: null pointer");
     PEEB_CUDA(cudaSetDevice(ws->device));
-    PEEB_CUDA(cudaMalloc(ptr, bytes ? bytes : 1));
+    // stream-ordered allocation from the device's pool (kept resident, see peeb_ws_create): a chain of calls
+    // that allocates its intermediates every time does not pay cudaMalloc / cudaFree (and their device-wide
+    // synchronisation) per buffer.  Every use of these buffers goes through the workspace stream.
+    PEEB_CUDA(cudaMallocAsync(ptr, bytes ? bytes : 1, ws->stream));
     return PEEB_OK;
 }
 
 int peeb_dev_free(peeb_ws* ws, void* ptr) {
     PEEB_REQUIRE(ws != nullptr, "peeb_dev_free: null workspace");
     PEEB_CUDA(cudaSetDevice(ws->device));
-    if (ptr) PEEB_CUDA(cudaFree(ptr));
+    if (ptr) PEEB_CUDA(cudaFreeAsync(ptr, ws->stream));
     return PEEB_OK;
 }
 

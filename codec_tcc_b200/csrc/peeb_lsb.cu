@@ -333,8 +333,29 @@ __global__ void __launch_bounds__(256) lsb_embed_kernel(const unsigned char* __r
 #pragma unroll
             for (int j = 0; j < 4; ++j) { px[j] = (v.x >> (8 * j)) & 0xffu; px[4 + j] = (v.y >> (8 * j)) & 0xffu; }
         }
+        // a group that lies entirely inside the plane's segment (or entirely outside) needs one position
+        // test and one 8-bit payload window; groups on a segment boundary take the per-pixel code
+        long long rel0 = gi * 8 - sg.start;
+        if (rel0 < 0) rel0 += n;
+        if (rel0 + 7 < sg.len) {
+            const long long bp = sg.bit_off + rel0;
+            const int sh = (int)(bp & 7);
+            unsigned two = (unsigned)__ldg(payload + (bp >> 3)) << 8;
+            if (sh) two |= (unsigned)__ldg(payload + (bp >> 3) + 1);
+            const unsigned bits8 = (two >> (8 - sh)) & 0xffu;  // bit of pixel j at position 7 - j
 #pragma unroll
-        for (int j = 0; j < 8; ++j) one(gi * 8 + j, px[j], nv[j], xr[j]);
+            for (int j = 0; j < 8; ++j) {
+                const unsigned bit = (bits8 >> (7 - j)) & 1u;
+                nv[j] = (px[j] & 0xFEu) | bit;
+                xr[j] = (px[j] ^ nv[j]) & 0xffu;
+            }
+        } else if (rel0 >= sg.len && rel0 + 7 < n) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { nv[j] = px[j]; xr[j] = 0; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) one(gi * 8 + j, px[j], nv[j], xr[j]);
+        }
         if (ITEM == 2) {
             int4 o;
             o.x = (int)(nv[0] | (nv[1] << 16)); o.y = (int)(nv[2] | (nv[3] << 16));
