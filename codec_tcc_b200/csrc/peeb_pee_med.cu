@@ -399,6 +399,11 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
                 lmbyte = lrow[0];
                 if (w > 8) { nx = ld8q<PixT>(mrow + 8); lmnext = lrow[1]; }
             }
+            // running pointers of the block to fetch next, its location-map byte and the block to write next
+            // (kept in registers: the addresses are not rebuilt from the row index at every block)
+            const PixT* mnx = mrow + 16;
+            const unsigned char* lnx = lrow + 2;
+            PixT* rout = rrow;
             const int nsteps = w >> 2;
             int jb = -4 * lane;
             for (int t = 0; t < nsteps + 31; ++t, jb += 4) {
@@ -406,9 +411,13 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
                 int um1 = (int)__shfl_up_sync(0xffffffffu, plast, 1);
                 if (lane == 0 && jb < w) {
                     uint4 v;
-                    do {
+                    const unsigned tg = uptag << 16;
+                    for (;;) {
                         v = lds128_volatile(const_cast<const unsigned*>(upline) + jb);
-                    } while (((v.x >> 16) != uptag) | ((v.y >> 16) != uptag) | ((v.z >> 16) != uptag) | ((v.w >> 16) != uptag));
+                        // all four tags equal uptag <=> no bit differs in any upper half
+                        if (((((v.x ^ tg) | (v.y ^ tg)) | ((v.z ^ tg) | (v.w ^ tg))) & 0xffff0000u) == 0u) break;
+                        __nanosleep(20);  // the group above is about one step away: do not burn issue slots on the poll
+                    }
                     uA = (v.x & 0xffffu) | (v.y << 16); uB = (v.z & 0xffffu) | (v.w << 16);
                     um1 = ulast; ulast = (int)(v.w & 0xffffu);
                 }
@@ -448,9 +457,11 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
                     }
                     if (!second) { oA = curA; oB = curB; }
                     else {  // block of eight done: write it, switch to the prefetched one, fetch the one after
-                        if (rrow) st8q<PixT>(rrow + jb - 4, make_uint4(oA, oB, curA, curB));
+                        if (rrow) st8q<PixT>(rout, make_uint4(oA, oB, curA, curB));
+                        rout += 8;
                         q = nx; lmbyte = lmnext;
-                        if (jb + 12 < w) { nx = ld8q<PixT>(mrow + jb + 12); lmnext = lrow[(jb + 12) >> 3]; }
+                        if (jb + 12 < w) { nx = ld8q<PixT>(mnx); lmnext = *lnx; }
+                        mnx += 8; ++lnx;
                     }
                 }
             }
