@@ -902,10 +902,20 @@ struct Extract2 {
         // fetched once per cell, ahead of use: the common all-zero case then costs one test per step
         const unsigned char* lmpa = slm + (size_t)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3);
         la = lb = 0ull;
-        const int nbytes = g.cws * (P::PXS >> 3);
-        for (int k = 0; k < nbytes; ++k) {
-            la |= (unsigned long long)lmpa[k] << (8 * k);
-            lb |= (unsigned long long)lmpa[g.lmpitch + k] << (8 * k);
+        const int nbytes = g.cws * (P::PXS >> 3);  // <= 8
+        if ((g.CW & 31) == 0) {
+            // cells start on a 4-byte boundary of the (4-byte aligned) map rows: two word loads per row; bytes
+            // past the cell belong to the next cell or to the row padding and are masked off
+            const unsigned* wa = reinterpret_cast<const unsigned*>(lmpa);
+            const unsigned* wb = reinterpret_cast<const unsigned*>(lmpa + g.lmpitch);
+            la = wa[0]; lb = wb[0];
+            if (nbytes > 4) { la |= (unsigned long long)wa[1] << 32; lb |= (unsigned long long)wb[1] << 32; }
+            if (nbytes < 8) { const unsigned long long m = (1ull << (8 * nbytes)) - 1ull; la &= m; lb &= m; }
+        } else {
+            for (int k = 0; k < nbytes; ++k) {
+                la |= (unsigned long long)lmpa[k] << (8 * k);
+                lb |= (unsigned long long)lmpa[g.lmpitch + k] << (8 * k);
+            }
         }
     }
     __device__ __forceinline__ unsigned lmbits(unsigned long long v, int s) const {
