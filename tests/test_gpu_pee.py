@@ -165,6 +165,38 @@ def test_batch_matches_oracle_per_unit():
     assert np.array_equal(xinfo[:, 2], info[:, 2])
 
 
+def test_large_batch_of_small_images_matches_oracle_per_unit():
+    """Many units with several bands each: the payload assembly takes several pieces per block, the units'
+    summaries come from their last bands, the output rows are cleared by the kernel (dirty buffers passed in)."""
+    n, h, w, bd = 320, 130, 72, 12
+    imgs = synth_batch(n, h, w, 4095, 90)
+    rng = np.random.default_rng(5)
+    Ts = rng.integers(1, 9, n).astype(np.int32)
+    caps = np.array([PC.embed(imgs[u], np.zeros(h * w // 8 + 8, np.uint8), 0, int(Ts[u]), bd)[2]["capacity"] for u in range(n)])
+    # (the capacity of pass 1 depends on the payload: stay a little under the zero-payload capacity)
+    nb = np.where(rng.integers(0, 4, n) == 0, (caps * 0.93).astype(np.int64), (caps * 0.9 * rng.random(n)).astype(np.int64)).astype(np.int64)
+    nb[::17] = 0
+    stride = int(((nb + 7) // 8).max()) + 3
+    pays = np.zeros((n, stride), np.uint8)
+    for u in range(n):
+        p = random_payload(int(nb[u]), 1000 + u)
+        pays[u, :p.size] = p
+    marked, lm, info = pee.pee_embed_batch(imgs, pays, nb, Ts, bd)
+    for u in range(n):
+        m0, lm0, i0 = PC.embed(imgs[u], pays[u], int(nb[u]), int(Ts[u]), bd)
+        assert int(info[u, 7]) == i0["status"] == 0, u
+        assert np.array_equal(marked[u], m0) and np.array_equal(lm[u], lm0), u
+        assert [int(v) for v in info[u, :7]] == [i0[k] for k in ("T", "n_bits", "capacity", "cap0", "cap1", "n_flagged", "sse")], u
+    out = np.full((n, stride), 0xA5, np.uint8)
+    rec = np.full_like(imgs, 7)
+    out, rec, xinfo = pee.pee_extract_batch(marked, lm, Ts, nb, bd, out_payload=out, out_recovered=rec)
+    assert np.array_equal(rec, imgs) and (xinfo[:, 7] == 0).all() and np.array_equal(xinfo[:, 2], info[:, 2])
+    for u in range(n):
+        k = int(nb[u])
+        assert np.array_equal(np.unpackbits(out[u])[:k], np.unpackbits(pays[u])[:k]), u
+        assert not np.unpackbits(out[u])[k:((k + 7) // 8) * 8].any(), u
+
+
 @pytest.mark.parametrize("cfg", [
     dict(name="ct512", n=24, h=512, w=512, maxval=65535, bd=16, T=96),      # BASELINE configs[1]/[2] slice shape
     dict(name="dx3000", n=3, h=3000, w=3000, maxval=4095, bd=12, T=12),     # BASELINE configs[3] image shape
