@@ -157,6 +157,19 @@ class ClockSampler:
                 pass
             time.sleep(0.001)
 
+    def sample_now(self):
+        """A few samples taken from the calling thread (used while the timed steps are still queued on the GPU)."""
+        if self.nvml is None:
+            return
+        nv, hd = self.nvml, self.handle
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        for _ in range(3):
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(hd, nv.NVML_CLOCK_SM)))
+                self.bits |= int(reasons(hd))
+            except Exception:  # noqa: BLE001
+                pass
+
     def start(self):
         if self.nvml is not None:
             self.thread = threading.Thread(target=self._poll, daemon=True)
@@ -270,7 +283,7 @@ def run_gpu_arm(args):
         D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm, info=d_info_e)
         D.pee_extract_device(d_marked, d_lm, T, cap, bd, payload_out=d_out, recovered=d_rec, info=d_info_x)
 
-    def timed_steps(k):
+    def timed_steps(k, while_busy=None):
         """K steps, CUDA events on the launching stream; with a small workload the
         L2 is flushed between steps and only the steps are timed."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
@@ -280,6 +293,8 @@ def run_gpu_arm(args):
             a.record()
             step()
             b.record()
+        if while_busy is not None:  # the host is ahead of the GPU here: the queued steps are still running
+            while_busy()
         torch.cuda.synchronize(dev)
         return sum(a.elapsed_time(b) for a, b in ev)
 
@@ -294,7 +309,7 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     barrier()
-    ms_total = timed_steps(args.steps)
+    ms_total = timed_steps(args.steps, sampler.sample_now if rank == 0 else None)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
