@@ -37,6 +37,20 @@ __device__ __forceinline__ void op(unsigned& x, unsigned a, unsigned b, unsigned
     if (OP == 19) asm volatile("shl.b32 %0, %0, 1; add.s32 %0, %0, %1;" : "+r"(x) : "r"(a));  // LEA?
     if (OP == 20) asm volatile("bfe.u32 %0, %0, 16, 16;" : "+r"(x));
     if (OP == 21) asm volatile("vadd2.u32.u32.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+    // packed 16-bit pairs (sm_90+): VIADD.16x2, VIMNMX.U16x2 / .S16x2[.RELU]
+    if (OP == 22) asm volatile("add.u16x2 %0, %0, %1;" : "+r"(x) : "r"(a));
+    if (OP == 23) asm volatile("min.u16x2 %0, %0, %1;" : "+r"(x) : "r"(a));
+    if (OP == 24) asm volatile("max.s16x2.relu %0, %0, %1;" : "+r"(x) : "r"(a));
+    if (OP == 25) {  // unsigned clamp of two pixels: max then min
+        asm volatile("max.u16x2 %0, %0, %1;" : "+r"(x) : "r"(a));
+        asm volatile("min.u16x2 %0, %0, %1;" : "+r"(x) : "r"(b));
+    }
+    if (OP == 26) {  // packed op next to an fma-pipe op
+        asm volatile("dp2a.lo.u32.s32 %0, %1, %2, %0;" : "+r"(x) : "r"(a), "r"(b));
+        asm volatile("add.u16x2 %0, %0, %1;" : "+r"(x) : "r"(a));
+    }
+    if (OP == 27) asm volatile("mad.hi.u32 %0, %1, 2, %0;" : "+r"(x) : "r"(a));            // IMAD.HI: x + (a >> 31)
+    if (OP == 28) asm volatile("min.s32 %0, %0, %1; max.s32 %0, %0, %2;" : "+r"(x) : "r"(a), "r"(b));  // VIMNMX3?
 }
 
 template <int OP>
@@ -105,6 +119,13 @@ int main() {
         run<13>("IDP + LOP3 pair", 2, out, cyc, warps);
         run<14>("IMAD + LOP3 pair", 2, out, cyc, warps);
         run<21>("vadd2", 1, out, cyc, warps);
+        run<22>("VIADD.16x2 (add.u16x2)", 1, out, cyc, warps);
+        run<23>("VIMNMX.U16x2 (min.u16x2)", 1, out, cyc, warps);
+        run<24>("VIMNMX.S16x2.RELU", 1, out, cyc, warps);
+        run<25>("max.u16x2 + min.u16x2", 2, out, cyc, warps);
+        run<26>("IDP + VIADD.16x2 pair", 2, out, cyc, warps);
+        run<27>("IMAD.HI.U32", 1, out, cyc, warps);
+        run<28>("min.s32 + max.s32", 2, out, cyc, warps);
     }
     return 0;
 }
