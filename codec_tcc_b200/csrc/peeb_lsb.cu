@@ -274,12 +274,25 @@ __global__ void __launch_bounds__(256) tile_moments_kernel(const unsigned char* 
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int lane = threadIdx.x & 31;
+    const bool fast16 = sbs == 16 && (w & 7) == 0 && (((uintptr_t)plane) & 15) == 0;
     for (long long t = warp0; t < ntiles; t += nwarps) {
         const int ty = (int)(t / tiles_x), tx = (int)(t % tiles_x);
         const int y0 = ty * sbs, x0 = tx * sbs;
         const int th = min(sbs, h - y0), tw = min(sbs, w - x0);
         unsigned long long s1 = 0, s2 = 0;
         const long long npx = (long long)th * tw;
+        if (ITEM == 2 && fast16 && th == 16 && tw == 16) {
+            // full 16x16 tile of 16-bit pixels: one 16-byte load per lane (row = lane / 2, half a row each)
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned short*>(plane) +
+                                                                  (long long)(y0 + (lane >> 1)) * w + x0 + 8 * (lane & 1)));
+            const unsigned wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned lo = wv[k] & 0xffffu, hi = wv[k] >> 16;
+                s1 += lo + hi;
+                s2 += (unsigned long long)lo * lo + (unsigned long long)hi * hi;
+            }
+        } else
         for (long long k = lane; k < npx; k += 32) {
             const int yy = (int)(k / tw), xx = (int)(k % tw);
             const long long at = (long long)(y0 + yy) * w + x0 + xx;
