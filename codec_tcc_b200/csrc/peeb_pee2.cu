@@ -34,12 +34,18 @@ namespace peeb {
 
 #ifdef PEEB_PHASE_TIMING
 // development aid: per-phase clock64 totals of thread 0 of every embed CTA (see scripts/phase_timing.py)
-__device__ unsigned long long g_phase[16];
+__device__ unsigned long long g_phase[32];
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
 #define PHASE_INIT long long _t0 = clock64()
 #else
 #define PHASE_MARK(i) do {} while (0)
 #define PHASE_INIT do {} while (0)
+#endif
+
+#ifdef PEEB_COUNT_REDO
+// development aid: warp-steps of the embed kernel that took the generic code [0] at a border column, [1] after the
+// fast code saw a value leave the range; [2] all warp-steps (peeb_debug_redo)
+__device__ unsigned long long g_redo[4];
 #endif
 
 struct Geom2 {
@@ -51,6 +57,8 @@ struct Geom2 {
     int CW;                 // cell width in pixels (<= 64, so a cell holds <= 32 carriers of one colour)
     int ncol;               // cells per row
     int rpw, rpw_log2;      // row pairs per warp item (power of two); 32/rpw cells side by side
+    int nic;                // warp items of a sweep: ceil(ncol / (32/rpw)) -- a sweep has at most rpw row pairs
+    int tpitch;             // bytes per row of the carrier-count tables (one byte per cell, multiple of 16)
     int lmw, lmpitch;       // location map: global row bytes, shared row pitch (bytes, multiple of 4)
     int bandwords;          // extract staging: 32-bit words per (unit, pass, band)
     int threads;
@@ -59,7 +67,7 @@ struct Geom2 {
 };
 
 struct Smem2 {
-    size_t img, lm, tab, misc, bar, pw, tn0, tw0, tw1, stream, total;
+    size_t img, lm, tab, misc, bar, tn0, tn1, tw0, tw1, stream, total;
 };
 __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 embed, 2 extract*/) {
     Smem2 L{};
@@ -68,15 +76,14 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 e
     L.lm = o;
     if (kind == 2 || (kind == 1 && !g.lm_direct)) o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
     L.tab = o;
-    if (kind != 0) o += align_up((size_t)(g.R + 2) * g.ncol * sizeof(int), 16);
+    if (kind == 1) o += (size_t)(g.R + 2) * g.tpitch;   // pass-1 carriers per (row, cell), one byte each
     L.misc = o; o += 64 * sizeof(int);
     L.bar = o; o += 16;
-    L.pw = L.tn0 = L.tw0 = L.tw1 = L.stream = o;
-    if (kind == 1) {
-        L.pw = o; o += align_up(((size_t)(g.R + 2) * ((g.w + 1) / 2) / 32 + 8) * sizeof(unsigned), 16);
-    } else if (kind == 2) {
+    L.tn0 = L.tn1 = L.tw0 = L.tw1 = L.stream = o;
+    if (kind == 2) {
         const size_t cells = (size_t)g.R * g.ncol;
-        L.tn0 = o; o += align_up(cells * sizeof(int), 16);
+        L.tn0 = o; o += (size_t)g.R * g.tpitch;
+        L.tn1 = o; o += (size_t)g.R * g.tpitch;
         L.tw0 = o; o += align_up(cells * sizeof(unsigned), 16);
         L.tw1 = o; o += align_up(cells * sizeof(unsigned), 16);
         L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
@@ -116,6 +123,7 @@ __device__ __forceinline__ void wait_rows2(const Geom2& g, int lo, int hi, uint6
     if (g.bulk && hi > lo) mbar_wait(bar, 0);
     __syncthreads();
 }
+#define WAIT_ROWS2_MARKED(g, lo, hi, bar, slot) do { if ((g).bulk && (hi) > (lo)) mbar_wait(bar, 0); PHASE_MARK(slot); __syncthreads(); } while (0)
 template <typename PixT>
 __device__ __forceinline__ void load_rows2(const Geom2& g, const unsigned char* usrc, unsigned char* simg, int r_first,
                                            int lo, int hi, uint64_t* bar) {
@@ -123,36 +131,109 @@ __device__ __forceinline__ void load_rows2(const Geom2& g, const unsigned char* 
     wait_rows2(g, lo, hi, bar);
 }
 
-// Exclusive scan of data[0..n) in place by the whole block with ONE internal barrier: every thread
-// owns a run of consecutive entries.  Callers synchronise before (data complete) and after (offsets
-// visible).  Returns the total to every thread.  warp_sums: >= 33 ints of shared memory.
-__device__ __forceinline__ int block_scan_runs(int* data, int n, int* warp_sums) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int lo = min(tid * per, n), hi = min(lo + per, n);
-    int sum = 0;
-    for (int k = lo; k < hi; ++k) sum += data[k];
-    int incl = sum;
+// ------------------------------------------------------------------ payload order without block scans
+// Carrier counts live in byte tables, one byte per (row, cell), rows `tpitch` bytes apart (bytes past ncol are 0).
+// A lane of the row-pair layout owns the cells (rowa, cell) and (rowa + 1, cell) of a sweep over rows
+// [row_lo, row_hi); the stream position of its first carrier is
+//     (carriers of the rows above, all cells)  +  (carriers of the cells to its left in its own row).
+// Both terms come from the lane's own two table rows: IDP.4A sums the bytes (all of them / those left of
+// the cell), a warp scan over the row pairs adds the rows above.  No block-wide scan, no barrier beyond the
+// one that completes the table.  Every lane of the warp must call this (shuffles); lanes whose rows or
+// cell are outside the sweep pass acta / actb = false and get offsets they never use.
+__device__ __forceinline__ int idp4_sum(unsigned a, unsigned wsel, int c) {
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(wsel), "r"(c));
+    return d;
+}
+struct CellPrefix {
+    int offa, offb;   // carriers before (rowa, cell) / (rowa + 1, cell) in the sweep's raster order
+    int row0_total;   // carriers of the first row of the sweep (the halo row above a band, when there is one)
+    int total;        // carriers of the whole sweep
+};
+template <bool GLOBAL>
+__device__ __forceinline__ CellPrefix cell_prefix(const Geom2& g, const unsigned char* ta, bool rowa_in, bool rowb_in,
+                                                  int cell) {
+    // ta: table row of rowa (row of rowa + 1 follows at ta + tpitch); shared or global memory
+    const int lane = threadIdx.x & 31, rp = lane & (g.rpw - 1);
+    const int jc = cell >> 2;
+    const unsigned partial = 0x01010101u & ((1u << (8 * (cell & 3))) - 1u);
+    int tota = 0, totb = 0, prea = 0, preb = 0;
+    for (int j4 = 0; j4 < g.tpitch; j4 += 16) {
+        uint4 va = make_uint4(0, 0, 0, 0), vb = va;
+        if (GLOBAL) {
+            if (rowa_in) va = __ldg(reinterpret_cast<const uint4*>(ta + j4));
+            if (rowb_in) vb = __ldg(reinterpret_cast<const uint4*>(ta + g.tpitch + j4));
+        } else {
+            if (rowa_in) va = *reinterpret_cast<const uint4*>(ta + j4);
+            if (rowb_in) vb = *reinterpret_cast<const uint4*>(ta + g.tpitch + j4);
+        }
+        const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int k = 0; k < 4; ++k) {
+            const int j = (j4 >> 2) + k;
+            const int sa = idp4_sum(wa[k], 0x01010101u, 0), sb = idp4_sum(wb[k], 0x01010101u, 0);
+            tota += sa; totb += sb;
+            if (j < jc) { prea += sa; preb += sb; }
+            if (j == jc) { prea = idp4_sum(wa[k], partial, prea); preb = idp4_sum(wb[k], partial, preb); }
+        }
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    int before = 0, total = 0;
-    for (int k = 0; k < nwarps; ++k) {
-        const int ws = warp_sums[k];
-        if (k < warp) before += ws;
-        total += ws;
+    const int v = tota + totb;
+    int incl = v;
+    for (int o = 1; o < g.rpw; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o, g.rpw);
+        if (rp >= o) incl += t;
     }
-    int run = before + incl - sum;
-    for (int k = lo; k < hi; ++k) {
-        const int v = data[k];
-        data[k] = run;
-        run += v;
+    CellPrefix r;
+    r.offa = incl - v + prea;
+    r.offb = incl - totb + preb;
+    r.row0_total = __shfl_sync(0xffffffffu, tota, 0, g.rpw);
+    r.total = __shfl_sync(0xffffffffu, incl, g.rpw - 1, g.rpw);
+    return r;
+}
+
+// Decoupled look-back over the bands of a unit, run by a whole warp (every warp of the CTA may run it: all of
+// them get the same answer, only `publish` = true writes this band's words).  Aggregates are summed back to the
+// nearest band that already knows its inclusive prefix; returns the carriers of the earlier bands.
+// look-back status words: the value is the whole message, so relaxed gpu-scope accesses suffice
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned warp_lookback(unsigned long long* stt, int band, unsigned total, bool publish) {
+    const int lane = threadIdx.x & 31;
+    if (publish && lane == 0) st_relaxed_gpu(stt + band, ST_AGG | total);
+    unsigned before = 0;
+    for (int k0 = band - 1; k0 >= 0; k0 -= 32) {
+        const int k = k0 - lane;
+        unsigned long long v = ST_PFX;  // lanes before band 0: prefix 0
+        if (k >= 0) do { v = ld_relaxed_gpu(stt + k); } while ((v & ST_MASK) == 0);
+        const unsigned pfx = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_PFX);
+        const int first = __ffs(pfx) - 1;  // nearest band with a prefix (-1: none in this window)
+        unsigned val = (first < 0 || lane <= first) ? (unsigned)(v & 0xffffffffu) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        before += val;
+        if (first >= 0) break;
     }
-    return total;
+    if (publish && lane == 0) st_relaxed_gpu(stt + band, ST_PFX | (unsigned long long)(before + total));
+    return before;
+}
+
+// 32 payload bits starting at stream bit p (bit p on top), straight from the packed MSB-first payload in
+// global memory; bits at or past n_bits read as 0 (zero padding), words past the payload are never loaded.
+__device__ __forceinline__ unsigned payload_window(const unsigned* __restrict__ pay, unsigned p, unsigned n_bits) {
+    const unsigned wi = p >> 5;
+    unsigned w0 = 0u, w1 = 0u;
+    if ((wi << 5) < n_bits) w0 = __byte_perm(__ldg(pay + wi), 0, 0x0123);
+    if (((wi + 1u) << 5) < n_bits) w1 = __byte_perm(__ldg(pay + wi + 1), 0, 0x0123);
+    const unsigned r0 = n_bits - (wi << 5);             // valid bits from the start of w0 (when w0 was loaded)
+    if (r0 < 32u) w0 &= ~(0xffffffffu >> r0);
+    else if (r0 < 64u) w1 &= ~(0xffffffffu >> (r0 - 32u));
+    return __funnelshift_l(w1, w0, p & 31u);
 }
 
 // Write-back of band rows, split so that the tail work of a kernel overlaps it.  Callers synchronise
@@ -180,36 +261,6 @@ __device__ __forceinline__ void store_rows2_issue(const Geom2& g, unsigned char*
 }
 __device__ __forceinline__ void store_rows2_wait(const Geom2& g) {
     if (g.bulk && (threadIdx.x & 31) < 4) bulk_wait_read0();
-}
-
-// Two tables scanned at once (same contract as block_scan_runs; warp_sums: >= 64 ints).
-__device__ __forceinline__ void block_scan_runs2(int* da, int* db, int n, int* warp_sums, int& tota, int& totb) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-    const int lo = min(tid * per, n), hi = min(lo + per, n);
-    int sa = 0, sb = 0;
-    for (int k = lo; k < hi; ++k) { sa += da[k]; sb += db[k]; }
-    int ia = sa, ib = sb;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-        if (lane >= o) { ia += ta; ib += tb; }
-    }
-    if (lane == 31) { warp_sums[warp] = ia; warp_sums[32 + warp] = ib; }
-    __syncthreads();
-    int ba = 0, bb = 0;
-    tota = totb = 0;
-    for (int k = 0; k < nwarps; ++k) {
-        const int wa = warp_sums[k], wb = warp_sums[32 + k];
-        if (k < warp) { ba += wa; bb += wb; }
-        tota += wa; totb += wb;
-    }
-    int ra = ba + ia - sa, rb = bb + ib - sb;
-    for (int k = lo; k < hi; ++k) {
-        const int va = da[k], vb = db[k];
-        da[k] = ra; db[k] = rb;
-        ra += va; rb += vb;
-    }
 }
 
 // ------------------------------------------------------------------ packed-pixel arithmetic
@@ -264,6 +315,20 @@ template <> struct PixOps<unsigned short> {
     template <int Q, int S> static __device__ __forceinline__ int add4x(const uint4& M, int acc) {  // acc + 4x
         return idp2(comp<S>(M), Q == 0 ? 0x0004u : 0x0400u, acc);
     }
+    template <int Q, int S> static __device__ __forceinline__ int addx(const uint4& M, int acc) {   // acc + x
+        return idp2(comp<S>(M), Q == 0 ? 0x0001u : 0x0100u, acc);
+    }
+    // pixel += d inside the packed word (exact while the new value stays inside the pixel's range)
+    template <int Q, int S> static __device__ __forceinline__ void addpacked(uint4& M, int d) {
+        unsigned& wv = compr<S>(M);
+        wv += Q == 0 ? (unsigned)d : ((unsigned)d << 16);
+    }
+    // pixel = (pixel + d) mod 2^16, the neighbour in the word untouched whatever the value (extract: any input)
+    template <int Q, int S> static __device__ __forceinline__ void addwrap(uint4& M, int d) {
+        unsigned& wv = compr<S>(M);
+        if constexpr (Q == 0) wv = __byte_perm(wv + (unsigned)d, wv, 0x7610);
+        else wv += (unsigned)d << 16;
+    }
 };
 template <> struct PixOps<unsigned char> {
     static constexpr int ITEM = 1, NS = 8, PXS = 16;
@@ -298,6 +363,22 @@ template <> struct PixOps<unsigned char> {
         constexpr int J = S / 2, B = 2 * (S % 2) + Q;
         return idp4(comp<J>(M), 4u << (8 * B), acc);
     }
+    template <int Q, int S> static __device__ __forceinline__ int addx(const uint4& M, int acc) {   // acc + x
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;
+        return idp4(comp<J>(M), 1u << (8 * B), acc);
+    }
+    template <int Q, int S> static __device__ __forceinline__ void addpacked(uint4& M, int d) {
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;
+        unsigned& wv = compr<J>(M);
+        wv += (unsigned)d << (8 * B);
+    }
+    template <int Q, int S> static __device__ __forceinline__ void addwrap(uint4& M, int d) {  // (pixel + d) mod 2^8
+        constexpr int J = S / 2, B = 2 * (S % 2) + Q;
+        constexpr unsigned sel = B == 0 ? 0x7650u : B == 1 ? 0x7610u : B == 2 ? 0x7210u : 0x3210u;
+        unsigned& wv = compr<J>(M);
+        const unsigned sum = wv + ((unsigned)d << (8 * B));
+        wv = B == 3 ? sum : __byte_perm(sum, wv, sel);
+    }
 };
 
 template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& f) {
@@ -305,16 +386,6 @@ template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& 
         f(std::integral_constant<int, I>{});
         static_for<I + 1, N>(f);
     }
-}
-
-// look-back status words: the value is the whole message, so relaxed gpu-scope accesses suffice
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ uint4 lds128(const unsigned char* p) { return *reinterpret_cast<const uint4*>(p); }
@@ -337,12 +408,13 @@ struct Stats2 {
 };
 
 // ---- predicated tails (explicit PTX: the compiler turns these into select chains otherwise) ----
-// embed: a carrier (q < 8T unsigned, i.e. -T <= e < T; range already checked) takes the next payload bit
+// embed: a carrier (q < 8T unsigned, i.e. -T <= e < T; range already checked) takes the next payload bit,
+// the top bit of W (tested as the sign: one predicated add, no 64-bit multiply-high and its register pair)
 __device__ __forceinline__ void take_bit(int& nv, unsigned& W, int q, int T8) {
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 b;\n\t"
+    asm("{\n\t.reg .pred p, pb;\n\t"
         "setp.lt.u32 p, %2, %3;\n\t"
-        "shr.u32 b, %1, 31;\n\t"
-        "@p add.s32 %0, %0, b;\n\t"
+        "setp.lt.and.s32 pb, %1, 0, p;\n\t"
+        "@pb add.s32 %0, %0, 1;\n\t"
         "@p shl.b32 %1, %1, 1;\n\t}"
         : "+r"(nv), "+r"(W) : "r"(q), "r"(T8));
 }
@@ -365,59 +437,57 @@ __device__ __forceinline__ void collect_bit(unsigned& W, int& n, int q, int T16)
 }
 
 // ------------------------------------------------------------------ the sweep
-// Rows [row_lo, row_hi) of the staged band, colour with column parity QA in row row_lo.  A warp
-// item = (group of rpw row pairs) x (32/rpw neighbouring cells); lane -> (row pair, cell).
+// Rows [row_lo, row_hi) of the staged band (at most 2 * rpw of them: make_geom2 sizes the bands so), colour
+// with column parity QA in row row_lo.  A warp item = (the sweep's row pairs) x (32/rpw neighbouring cells);
+// lane -> (row pair, cell).
+// lane -> (row pair, cell of warp item `item`) of a sweep over rows [row_lo, row_hi)
+struct Lane2 {
+    int rowa, cell;
+    bool rowa_in, rowb_in, acta, actb;
+};
+__device__ __forceinline__ Lane2 lane_of(const Geom2& g, int row_lo, int row_hi, int item) {
+    const int lane = threadIdx.x & 31;
+    const int rp = lane & (g.rpw - 1), part = lane >> g.rpw_log2, parts = 32 >> g.rpw_log2;
+    Lane2 l;
+    l.rowa = row_lo + 2 * rp;
+    l.rowa_in = l.rowa < row_hi; l.rowb_in = l.rowa + 1 < row_hi;
+    if (!l.rowa_in) l.rowa = row_lo;  // idle lane: any staged row will do, nothing is written
+    l.cell = item * parts + part;
+    const bool colv = l.cell < g.ncol;
+    l.acta = colv && l.rowa_in; l.actb = colv && l.rowb_in;
+    if (!colv) l.cell = g.ncol - 1;
+    return l;
+}
+// What a body needs before its first item (payload order, payload bits: global loads) can be fetched ahead of the
+// sweep, e.g. while the band's rows are still on their way; sweep2 then skips begin() for that item.
+template <class Body>
+__device__ __forceinline__ void sweep2_prime(const Geom2& g, int row_lo, int row_hi, int T, Body& body) {
+    const int warp = threadIdx.x >> 5;
+    if (row_hi <= row_lo || warp >= g.nic) return;
+    const Lane2 l = lane_of(g, row_lo, row_hi, warp);
+    body.begin(l.rowa, l.cell, l.acta, l.actb, l.rowa_in, l.rowb_in, T);
+    body.primed = true;
+}
 template <typename PixT, int QA, class Body>
 __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int r_first, int row_lo, int row_hi, int T,
                                        Body& body) {
     using P = PixOps<PixT>;
     if (row_hi <= row_lo) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int rp = lane & (g.rpw - 1), part = lane >> g.rpw_log2, parts = 32 >> g.rpw_log2;
-    const int npairs = (row_hi - row_lo + 1) >> 1;
-    const int ngroups = (npairs + g.rpw - 1) >> g.rpw_log2;
-    const int nic = (g.ncol + parts - 1) / parts;
-    const int nitems = ngroups * nic;
-    for (int item = warp; item < nitems; item += nwarps) {
-        int grp = 0, ic = item;
-        if (ngroups > 1) { grp = item / nic; ic = item - grp * nic; }
-        int rowa = row_lo + 2 * (grp * g.rpw + rp);
-        int cell = ic * parts + part;
-        const bool colv = cell < g.ncol;
-        const bool acta = colv && rowa < row_hi, actb = colv && rowa + 1 < row_hi;
-        if (rowa >= row_hi) rowa = row_lo;  // idle lane: any staged row will do, nothing is written
-        if (!colv) cell = g.ncol - 1;
-        const int c0 = cell * g.CW;
-        const int rs = rowa - r_first;
-        const unsigned char* pu = simg + row_off(g, rs - 1) + c0 * P::ITEM;
-        unsigned char* pa = simg + row_off(g, rs) + c0 * P::ITEM;
-        unsigned char* pb = simg + row_off(g, rs + 1) + c0 * P::ITEM;
-        const unsigned char* pd = simg + row_off(g, rs + 2) + c0 * P::ITEM;
-        body.begin(rowa, cell, acta, actb, T);
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int item = warp; item < g.nic; item += nwarps) {
+        const Lane2 l = lane_of(g, row_lo, row_hi, item);
+        const int rs = l.rowa - r_first;
+        const int oa = row_off(g, rs);
+        unsigned char* pa = simg + oa + l.cell * g.CW * P::ITEM;
+        const unsigned char* pu = pa + (row_off(g, rs - 1) - oa);
+        unsigned char* pb = pa + (row_off(g, rs + 1) - oa);
+        const unsigned char* pd = pa + (row_off(g, rs + 2) - oa);
+        const int c0 = l.cell * g.CW;
+        if (!body.primed) body.begin(l.rowa, l.cell, l.acta, l.actb, l.rowa_in, l.rowb_in, T);
+        body.primed = false;
         // the row whose colour sits on even columns looks one word back, the other one word ahead
         unsigned prev = *reinterpret_cast<const unsigned*>((QA == 0 ? pa : pb) - 4);
-#ifdef PEEB_PREFETCH  // measured slower on B200 at 3 CTAs/SM (register pressure); kept for experiments
-        // the words of step s+1 are fetched while step s computes (reads run at most one step past the
-        // cell; the staging buffer has slack for that)
-        uint4 U = lds128(pu), D = lds128(pd), A = lds128(pa), B = lds128(pb);
-        unsigned next = *reinterpret_cast<const unsigned*>((QA == 0 ? pb : pa) + 16);
-        for (int s = 0; s < g.cws; ++s) {
-            const int c = c0 + s * P::PXS;
-            const uint4 nU = lds128(pu + 16), nD = lds128(pd + 16), nA = lds128(pa + 16), nB = lds128(pb + 16);
-            const unsigned nnext = *reinterpret_cast<const unsigned*>((QA == 0 ? pb : pa) + 32);
-            const unsigned newprev = QA == 0 ? A.w : B.w;
-            const bool special = __any_sync(0xffffffffu, body.special(c, s));
-            body.template step<QA>(c, s, special, U, A, B, D, prev, next, pa, pb);
-            prev = newprev;
-            U = nU; D = nD; A = nA; B = nB; next = nnext;
-            pu += 16; pa += 16; pb += 16; pd += 16;
-        }
-#else
-#ifdef PEEB_UNROLL2
-#pragma unroll 2
-#else
 #pragma unroll 1
-#endif
         for (int s = 0; s < g.cws; ++s) {
             const int c = c0 + s * P::PXS;
             const uint4 U = lds128(pu), D = lds128(pd);
@@ -430,7 +500,6 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
             prev = newprev;
             pu += 16; pa += 16; pb += 16; pd += 16;
         }
-#endif
         body.end();
     }
 }
@@ -449,17 +518,16 @@ struct Count2 {
     using P = PixOps<PixT>;
     const Geom2& g;
     int row0;               // image row of table row 0
-    unsigned char* rowcnt;  // GLOBAL: bytes in global memory, [row * ncol + cell]
-    int* tab;               // !GLOBAL: shared table
+    unsigned char* tab;     // byte table, [(row - row0) * tpitch + cell]: global (GLOBAL) or shared memory
     int total;              // GLOBAL: carriers seen by this lane
     KE ka, kb;
     int na, nb, ia;
-    bool acta, actb;
-    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
+    bool acta, actb, primed;
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool, bool, int T) {
         acta = a; actb = b;
         ka = kb = make_ke(T);  // inactive rows compute like the others; nothing of theirs is kept
         na = nb = 0;
-        ia = (rowa - row0) * g.ncol + cell;
+        ia = (rowa - row0) * g.tpitch + cell;
     }
     __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
     template <int Q, bool EDGE>
@@ -489,32 +557,30 @@ struct Count2 {
         }
     }
     __device__ __forceinline__ void end() {
-        if (GLOBAL) {
-            if (acta) rowcnt[ia] = (unsigned char)na;
-            if (actb) rowcnt[ia + g.ncol] = (unsigned char)nb;
-            total += (acta ? na : 0) + (actb ? nb : 0);
-        } else {
-            if (acta) tab[ia] = na;
-            if (actb) tab[ia + g.ncol] = nb;
-        }
+        if (acta) tab[ia] = (unsigned char)na;
+        if (actb) tab[ia + g.tpitch] = (unsigned char)nb;
+        if (GLOBAL) total += (acta ? na : 0) + (actb ? nb : 0);
     }
 };
 
 // ---- full apply of one colour ---------------------------------------------------------------------
-// tab[(row-row0)*ncol + cell] = offset of the cell's first carrier in the band's bit window `pw`
-// (32-bit words, stream bit k at bit 31-(k&31) of word k>>5), counted from bit `bitbase`.
+// The stream position of a lane's first carrier comes from the byte table of the pass (cell_prefix: pass 0 reads
+// the count kernel's table in global memory, pass 1 the shared table of the band), its 32 payload bits straight
+// from global memory (payload_window).
 // A step first runs the fast code, which assumes that no pixel over/underflows (every expandable
 // pixel is a carrier, nothing goes to the location map) and only watches for a value leaving
 // [0, maxval); if any lane of the warp sees one, or the step touches a border column, the step is
 // redone from the saved words by the generic code.
-template <typename PixT>
+template <typename PixT, bool GTAB>
 struct Apply2 {
     using P = PixOps<PixT>;
     const Geom2& g;
     int row0, own_lo, own_hi;
-    const int* tab;
-    const unsigned* pw;
-    int bitbase;
+    const unsigned char* tab;   // byte table, row `row0` first
+    const unsigned* pay;        // the unit's packed payload
+    unsigned n_bits;
+    unsigned B;                 // stream index of the first carrier of the sweep's first own row
+    bool halo;                  // the sweep starts one row above the band: that row's carriers precede B
     unsigned* slm;  // location-map rows (row lm_row0 first), lmwords words apart: shared copy of the band, or
                     // the unit's rows in global memory (null: the caller wants no map)
     int lm_row0, lmwords;
@@ -522,26 +588,24 @@ struct Apply2 {
     KE ka, kb;
     unsigned Wa, Wb;
     long long ssea, sseb;
-    bool sta, stb, owna, ownb;
+    bool sta, stb, owna, ownb, primed;
     unsigned* lma;
-    __device__ __forceinline__ unsigned window(int o) const {
-        const int p = bitbase + o;
-        return __funnelshift_l(pw[(p >> 5) + 1], pw[p >> 5], p & 31);
-    }
-    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool rowa_in, bool rowb_in, int T) {
         sta = a; stb = b;
         ka = kb = make_ke(T);
-        const int ia = (rowa - row0) * g.ncol + cell;
-        Wa = a ? window(tab[ia]) : 0u;
-        Wb = b ? window(tab[ia + g.ncol]) : 0u;
+        const CellPrefix cp = cell_prefix<GTAB>(g, tab + (long long)(rowa - row0) * g.tpitch, rowa_in, rowb_in, cell);
+        const unsigned base = B - (halo ? (unsigned)cp.row0_total : 0u);
+        Wa = a ? payload_window(pay, base + (unsigned)cp.offa, n_bits) : 0u;
+        Wb = b ? payload_window(pay, base + (unsigned)cp.offb, n_bits) : 0u;
         owna = a && rowa >= own_lo && rowa < own_hi;
         ownb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
         ssea = sseb = 0;
         lma = slm ? slm + (long long)(rowa - lm_row0) * lmwords : nullptr;
     }
     __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
-    // All predictions read the words as loaded (M); results go to a separate copy (O), so the pixels
-    // of a step form independent dependency chains that the scheduler can interleave.
+    // All predictions read the words as loaded (M); the differences are added to a separate copy (O) inside the
+    // packed words: O += d << (position of the pixel) is exact as long as the new value stays in range, which is
+    // what `bad` watches -- no pixel is unpacked or re-inserted.
     template <int Q>
     __device__ __forceinline__ bool fast(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
                                          const uint4& D, const KE& k, unsigned& W, long long& sse) {
@@ -549,14 +613,13 @@ struct Apply2 {
         static_for<0, P::NS>([&](auto Sc) {
             constexpr int S = decltype(Sc)::value;
             const int q = P::template qsum<Q, S>(M, prev, next, U, D, k.init);
-            const int x = P::template getx<Q, S>(M);
             const int cc = max(min(q >> 2, k.T2), 0);               // clamp(e + T, 0, 2T)
-            int nv = x + cc + k.negT;                               // x + e | x + T | x - T
-            bad |= (unsigned)nv >= (unsigned)g.maxval;              // (maxval itself is fine for a shift: rare, generic code sorts it out)
-            take_bit(nv, W, q, k.T8);
-            const int d = nv - x;
+            int d = cc + k.negT;                                    // e | +T | -T
+            const int nv0 = P::template addx<Q, S>(M, d);           // x + e | x + T | x - T
+            bad |= (unsigned)nv0 >= (unsigned)g.maxval;             // (maxval itself is fine for a shift: rare, generic code sorts it out)
+            take_bit(d, W, q, k.T8);
             sse += (long long)d * (long long)d;
-            P::template setx<Q, S>(O, nv);
+            P::template addpacked<Q, S>(O, d);
         });
         return bad;
     }
@@ -605,7 +668,13 @@ struct Apply2 {
             A = A0; B = B0; Wa = Wa0; Wb = Wb0; ssea = sa0; sseb = sb0;
             generic<QA>(A0, A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
             generic<1 - QA>(B0, B, prev, next, A0, D, kb, c, Wb, sseb, ownb, lma ? lma + lmwords : nullptr);
+#ifdef PEEB_COUNT_REDO
+            if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo[special ? 0 : 1], 1ull);
+#endif
         }
+#ifdef PEEB_COUNT_REDO
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo[2], 1ull);
+#endif
         if (c < g.w) {
             if (sta) sts128(pa, A);
             if (stb) sts128(pb, B);
@@ -617,27 +686,18 @@ struct Apply2 {
     }
 };
 
-// Copies the payload words covering stream bits [B0, B0 + total] into shared memory, byte-swapped
-// so that stream bit k is bit 31-(k&31) of its word; bits at or past n_bits read as 0 (zero padding).
-__device__ __forceinline__ unsigned payload_word(const unsigned* __restrict__ pay, unsigned B0, int j, int nw,
-                                                unsigned n_bits) {
-    const unsigned wi = (B0 >> 5) + (unsigned)j;
-    const unsigned long long bit0 = (unsigned long long)wi << 5;
-    unsigned v = 0;
-    if (j < nw && bit0 < n_bits) {
-        v = __byte_perm(__ldg(pay + wi), 0, 0x0123);
-        const unsigned rem = n_bits - (unsigned)bit0;
-        if (rem < 32u) v &= ~(0xffffffffu >> rem);
-    }
-    return v;
-}
-__device__ __forceinline__ void stage_payload(const unsigned* __restrict__ pay, unsigned B0, int total, unsigned n_bits,
-                                              unsigned* pw) {
-    const int nw = (int)(((B0 & 31u) + (unsigned)total + 31u) >> 5) + 2;
-    for (int j = threadIdx.x; j < nw; j += blockDim.x) pw[j] = payload_word(pay, B0, j, nw, n_bits);
+// carriers of a whole byte table of `nrows` rows, summed by one warp (every lane gets the total)
+__device__ __forceinline__ int table_total(const Geom2& g, const unsigned char* tab, int nrows) {
+    int sum = 0;
+    const int wpr = g.tpitch >> 2;
+    for (int k = threadIdx.x & 31; k < nrows * wpr; k += 32) sum = idp4_sum(reinterpret_cast<const unsigned*>(tab)[k], 0x01010101u, sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    return sum;
 }
 
 // ------------------------------------------------------------------ K_A: pass-0 counts
+// rowcnt: one byte per (row, cell) of every unit, rows `tpitch` bytes apart.
 template <typename PixT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch bt, int* __restrict__ band_cnt,
                                                               unsigned char* __restrict__ rowcnt,
@@ -663,7 +723,12 @@ __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch 
     if (band == 0 && threadIdx.x < PEEB_INFO) bt.info[(long long)unit * PEEB_INFO + threadIdx.x] = 0;
     wait_rows2(g, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
-    Count2<PixT, true> body{g, 0, rowcnt + (long long)unit * g.h * g.ncol, nullptr, 0};
+    {   // bytes past ncol of this band's table rows are summed with the rest by the embed kernel: they are 0
+        const int padn = g.tpitch - g.ncol;
+        unsigned char* rt = rowcnt + ((long long)unit * g.h + own_lo) * g.tpitch + g.ncol;
+        for (int k = threadIdx.x; k < (own_hi - own_lo) * padn; k += blockDim.x) rt[(k / padn) * g.tpitch + (k % padn)] = 0;
+    }
+    Count2<PixT, true> body{g, 0, rowcnt + (long long)unit * g.h * g.tpitch, 0};
     sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, bt.T[unit], body);
     int tot = body.total;
 #pragma unroll
@@ -677,6 +742,9 @@ __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch 
 }
 
 // ------------------------------------------------------------------ K_B: fused two-pass embed
+// Barriers per band: ticket, rows staged, pass 0 applied, pass-1 table complete, pass 1 applied.  Everything
+// between them is per warp: payload order (cell_prefix), look-back (every warp runs it, warp 0 publishes),
+// payload bits (payload_window).
 template <typename PixT, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch bt, const int* __restrict__ band_cnt,
                                                               const unsigned char* __restrict__ rowcnt,
@@ -686,16 +754,18 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     const Smem2 L = layout2(g, 1);
     unsigned char* simg = smem_raw + L.img;
     unsigned* slm = reinterpret_cast<unsigned*>(smem_raw + L.lm);
-    int* tab = reinterpret_cast<int*>(smem_raw + L.tab);
+    unsigned char* tab = smem_raw + L.tab;
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
-    unsigned* pw = reinterpret_cast<unsigned*>(smem_raw + L.pw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // in-order ticket: a band only ever waits on bands with smaller tickets
     if (threadIdx.x == 0) {
         misc[40] = (int)atomicAdd(ticket, 1u);
         if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
     }
+    // bytes of the pass-1 table past ncol are summed with the rest: keep them 0
+    for (int k = threadIdx.x; k < ((g.R + 2) * g.tpitch) >> 2; k += blockDim.x) reinterpret_cast<unsigned*>(tab)[k] = 0u;
     __syncthreads();
     // Tickets run band-major over the batch (band 0 of every unit, then band 1, ...): with more units
     // than resident CTAs the earlier bands of a unit have finished when a band looks back, so the
@@ -710,52 +780,32 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     long long* info = bt.info + (long long)unit * PEEB_INFO;
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
-    const int n0 = max(p0_hi - p0_lo, 0) * g.ncol, n1 = max(own_hi - own_lo, 0) * g.ncol;
-
-    // Small reads first: issued after the band's own bulk copies they would queue behind ~64 KB of
-    // traffic on this SM's path to L2.  Order: tables -> payload words of pass 0 -> band copy.
     const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
     PHASE_INIT;
-    {
-        const unsigned char* rc = rowcnt + ((long long)unit * g.h + p0_lo) * g.ncol;
-        int rcv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = threadIdx.x + i * blockDim.x;
-            rcv[i] = k < n0 ? rc[k] : 0;
-        }
-        if (threadIdx.x >= 32 && threadIdx.x < 64) {  // warp 1: pass-0 prefix of this band, cap0 of the unit
-            const int lane = threadIdx.x & 31;
-            int before = 0, all = 0;
-            for (int k = lane; k < g.nb; k += 32) {
-                const int cc = band_cnt[unit * g.nb + k];
-                all += cc;
-                if (k < band) before += cc;
-            }
-            // carriers of the halo row above precede this band in raster order
-            if (p0_lo < own_lo)
-                for (int k = lane; k < g.ncol; k += 32) before -= rc[k];
-            before = (int)warp_sum_i64(before);
-            all = (int)warp_sum_i64(all);
-            if (lane == 0) { misc[41] = before; misc[42] = all; }
-        }
-        if (!g.lm_direct) {
-            for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
-        } else if (bt.lm) {
-            // flagged pixels are rare: their bits are OR-ed straight into the (zeroed) global rows of this band
-            const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
-            unsigned* glm = reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw);
-            for (int k = threadIdx.x; k < (b_hi - b_lo) * (g.lmw >> 2); k += blockDim.x) glm[k] = 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int k = threadIdx.x + i * blockDim.x;
-            if (k < n0) tab[k] = rcv[i];
-        }
-        for (int k = threadIdx.x + 4 * blockDim.x; k < n0; k += blockDim.x) tab[k] = rc[k];
+    issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+    PHASE_MARK(16);  // copies issued
+    // every warp: carriers of pass 0 in the earlier bands, and in the whole unit (cap0), from the count kernel
+    int before0 = 0, cap0 = 0;
+    for (int k = lane; k < g.nb; k += 32) {
+        const int cc = __ldg(band_cnt + unit * g.nb + k);
+        cap0 += cc;
+        if (k < band) before0 += cc;
     }
-    __syncthreads();
-    PHASE_MARK(0);  // tables
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        before0 += __shfl_xor_sync(0xffffffffu, before0, o);
+        cap0 += __shfl_xor_sync(0xffffffffu, cap0, o);
+    }
+    PHASE_MARK(17);  // band counts
+    if (!g.lm_direct) {
+        for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
+    } else if (bt.lm) {
+        // flagged pixels are rare: their bits are OR-ed straight into the (zeroed) global rows of this band
+        const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
+        unsigned* glm = reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw);
+        for (int k = threadIdx.x; k < (b_hi - b_lo) * (g.lmw >> 2); k += blockDim.x) glm[k] = 0u;
+    }
+    PHASE_MARK(0);  // set-up
     Stats2 st;
     unsigned* lmbase = slm;
     int lmrow0 = r0, lmwords = g.lmpitch >> 2;
@@ -763,90 +813,51 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         lmbase = bt.lm ? reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride) : nullptr;
         lmrow0 = 0; lmwords = g.lmw >> 2;
     }
-
-    // ---- pass 0 (colour 0): band rows and one halo row on each side
+    // ---- pass 0 (colour 0): band rows and one halo row on each side; order from the count kernel's table.
+    // The table rows and the payload bits of a warp's first item are fetched while the band's rows arrive.
     {
-        const unsigned B0 = (unsigned)misc[41];  // stream index of the first carrier of row p0_lo
-        // payload window: an upper bound of the band's carriers, so that it need not wait for the scan
-        const int maxbits = max(p0_hi - p0_lo, 0) * ((g.w + 1) >> 1);
-        const int nw = (int)(((B0 & 31u) + (unsigned)maxbits + 31u) >> 5) + 2;
-        unsigned pv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pv[i] = payload_word(payload, B0, threadIdx.x + i * blockDim.x, nw, n_bits);
-        issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int j = threadIdx.x + i * blockDim.x;
-            if (j < nw) pw[j] = pv[i];
-        }
-        for (int j = threadIdx.x + 4 * blockDim.x; j < nw; j += blockDim.x) pw[j] = payload_word(payload, B0, j, nw, n_bits);
-        block_scan_runs(tab, n0, misc);
-        PHASE_MARK(1);  // payload staging + scan
-        wait_rows2(g, s_lo, s_hi, bar);
-        PHASE_MARK(2);  // band copy wait
-        Apply2<PixT> body{g, p0_lo, own_lo, own_hi, tab, pw, (int)(B0 & 31u), lmbase, lmrow0, lmwords, &st};
+        Apply2<PixT, true> body{g, 0, own_lo, own_hi, rowcnt + (long long)unit * g.h * g.tpitch, payload, n_bits,
+                                (unsigned)before0, p0_lo < own_lo, lmbase, lmrow0, lmwords, &st};
+        sweep2_prime(g, p0_lo, p0_hi, T, body);
+        PHASE_MARK(18);  // pass-0 order and bits of the first item
+        WAIT_ROWS2_MARKED(g, s_lo, s_hi, bar, 19);
+        PHASE_MARK(1);  // band copy wait
         sweep2_colour<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
-        PHASE_MARK(3);  // apply 0 (own warp)
+        PHASE_MARK(2);  // apply 0
     }
     __syncthreads();
-    PHASE_MARK(4);  // barrier
+    PHASE_MARK(3);  // barrier
 
     // ---- pass 1 (colour 1) over the band rows: count, order (look-back over earlier bands), apply
     {
-        Count2<PixT, false> body{g, own_lo, nullptr, tab, 0};
+        Count2<PixT, false> body{g, own_lo, tab, 0};
         sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
     }
-    PHASE_MARK(5);  // count 1
+    PHASE_MARK(4);  // count 1
     __syncthreads();
-    PHASE_MARK(6);  // barrier
+    PHASE_MARK(5);  // barrier
     {
-        const int total = block_scan_runs(tab, n1, misc);
-        PHASE_MARK(7);  // scan
-        if (threadIdx.x < 32) {
-            // decoupled look-back, one predecessor per lane: aggregates are summed back to the nearest
-            // band that already knows its inclusive prefix
-            const int lane = threadIdx.x;
-            unsigned long long* stt = status + (long long)unit * g.nb;
-            if (lane == 0) st_relaxed_gpu(stt + band, ST_AGG | (unsigned)total);
-            unsigned before = 0;
-            for (int k0 = band - 1; k0 >= 0; k0 -= 32) {
-                const int k = k0 - lane;
-                unsigned long long v = ST_PFX;  // lanes before band 0: prefix 0
-                if (k >= 0) do { v = ld_relaxed_gpu(stt + k); } while ((v & ST_MASK) == 0);
-                const unsigned pfx = __ballot_sync(0xffffffffu, (v & ST_MASK) == ST_PFX);
-                const int first = __ffs(pfx) - 1;  // nearest band with a prefix (-1: none in this window)
-                unsigned val = (first < 0 || lane <= first) ? (unsigned)(v & 0xffffffffu) : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-                before += val;
-                if (first >= 0) break;
-            }
-            if (lane == 0) {
-                st_relaxed_gpu(stt + band, ST_PFX | (unsigned long long)(before + (unsigned)total));
-                misc[43] = (int)before;
-                if (band == g.nb - 1) {
-                    // the last band knows both pass totals: it writes the unit's summary (no separate kernel);
-                    // n_flagged and sse (info[5], info[6]) are summed by every band with atomics
-                    const long long cap0 = misc[42], cap1 = (long long)before + total;
-                    info[0] = T; info[1] = n_bits; info[2] = cap0 + cap1; info[3] = cap0; info[4] = cap1;
-                    info[7] = ((long long)n_bits > cap0 + cap1) ? PEEB_E_CAPACITY : 0;
-                }
-            }
+        const unsigned total = (unsigned)table_total(g, tab, max(own_hi - own_lo, 0));
+        const unsigned before1 = warp_lookback(status + (long long)unit * g.nb, band, total, warp == 0);
+        if (warp == 0 && lane == 0 && band == g.nb - 1) {
+            // the last band knows both pass totals: it writes the unit's summary (no separate kernel);
+            // n_flagged and sse (info[5], info[6]) are summed by every band with atomics
+            const long long cap1 = (long long)before1 + total;
+            info[0] = T; info[1] = n_bits; info[2] = cap0 + cap1; info[3] = cap0; info[4] = cap1;
+            info[7] = ((long long)n_bits > cap0 + cap1) ? PEEB_E_CAPACITY : 0;
         }
-        PHASE_MARK(8);  // look-back
-        __syncthreads();
-        const unsigned B1 = (unsigned)(misc[42] + misc[43]);  // cap0 + earlier bands' pass-1 carriers
-        stage_payload(payload, B1, total, n_bits, pw);
-        __syncthreads();
-        PHASE_MARK(9);  // payload staging
-        Apply2<PixT> body{g, own_lo, own_lo, own_hi, tab, pw, (int)(B1 & 31u), lmbase, lmrow0, lmwords, &st};
+        PHASE_MARK(6);  // look-back
+        Apply2<PixT, false> body{g, own_lo, own_lo, own_hi, tab, payload, n_bits, (unsigned)cap0 + before1, false,
+                                 lmbase, lmrow0, lmwords, &st};
         sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
-        PHASE_MARK(10);  // apply 1
+        PHASE_MARK(7);  // apply 1
     }
 
     __syncthreads();
+    PHASE_MARK(20);  // barrier after pass 1
     const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
     if (bt.dst) store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, b_lo, b_hi);
+    PHASE_MARK(21);  // stores issued
     {   // statistics and the location map go out while the rows drain
         const long long sse = warp_sum_i64(st.sse);
         const long long fl = warp_sum_i64((long long)st.flagged);
@@ -855,11 +866,11 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
             if (fl) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)fl);
         }
     }
-    PHASE_MARK(11);  // stats
+    PHASE_MARK(8);  // stats
     if (bt.lm && !g.lm_direct) {
         unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw;
         const int nrows = b_hi - b_lo;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const int nwarps = blockDim.x >> 5;
         if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
             const int wpr = g.lmw >> 2;
             for (int r = warp; r < nrows; r += nwarps)
@@ -872,7 +883,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         }
     }
     store_rows2_wait(g);
-    PHASE_MARK(12);  // location map + store drain
+    PHASE_MARK(9);  // location map + store drain
 }
 
 // ------------------------------------------------------------------ K_X: extract
@@ -885,18 +896,19 @@ struct Extract2 {
     int own_lo, own_hi;
     const unsigned char* slm;  // location-map rows, row lm_row0 first
     int lm_row0;
-    int* tn;
-    unsigned* tw;
+    unsigned char* tn;         // carriers per (own row, cell), one byte each, rows tpitch apart
+    unsigned* tw;              // their bits, rows ncol words apart
     KX ka, kb;
     unsigned Wa, Wb;
-    int na, nb, ia;
-    bool sta, stb, reca, recb;
+    int na, nb, ia, in;
+    bool sta, stb, reca, recb, primed;
     unsigned long long la, lb;  // location-map bytes of this lane's cell in rows a and b (byte k = columns 8k..8k+7 of the cell)
-    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, int T) {
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool, bool, int T) {
         sta = a; stb = b;
         ka = kb = make_kx(T);
         Wa = Wb = 0u; na = nb = 0;
         ia = (rowa - own_lo) * g.ncol + cell;
+        in = (rowa - own_lo) * g.tpitch + cell;
         reca = a && rowa >= own_lo && rowa < own_hi;
         recb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
         // fetched once per cell, ahead of use: the common all-zero case then costs one test per step
@@ -936,10 +948,11 @@ struct Extract2 {
                 kk = make_kx((col >= 1 && col <= g.w - 2 && !flag) ? k.T : 0);
             }
             const int q = P::template qsum<Q, S>(M, prev, next, U, D, kk.init);  // 4(e' + 2T) + r, e' = x' - p
-            const int x = P::template getx<Q, S>(M);
             const int cc = max(min((q + 4) >> 3, kk.T2), 0);                       // clamp(ceil(e'/2), -T, T) + T
             collect_bit(W, n, q, kk.T16);
-            P::template setx<Q, S>(O, x - cc + kk.T);
+            // the original pixel is x' - (cc - T): subtracted inside the packed word (modulo the pixel width, like the
+            // specification's cast to the pixel type, so that a tampered image cannot disturb the neighbour in the word)
+            P::template addwrap<Q, S>(O, kk.T - cc);
         });
     }
     template <int QA>
@@ -959,10 +972,38 @@ struct Extract2 {
         }
     }
     __device__ __forceinline__ void end() {
-        if (reca) { tn[ia] = na; tw[ia] = Wa; }
-        if (recb) { tn[ia + g.ncol] = nb; tw[ia + g.ncol] = Wb; }
+        if (reca) { tn[in] = (unsigned char)na; tw[ia] = Wa; }
+        if (recb) { tn[in + g.tpitch] = (unsigned char)nb; tw[ia + g.ncol] = Wb; }
     }
 };
+
+// The carrier bits of the band, in payload order: every lane places the bits of its cells (count in tn, bits in
+// tw) at the offset cell_prefix gives it, with shared-memory atomics; same lane -> (row pair, cell) mapping
+// as a sweep over the own rows.  Returns the carriers of the band (every lane).
+__device__ __forceinline__ int assemble_stream(const Geom2& g, int nrows, const unsigned char* tn, const unsigned* tw,
+                                               unsigned* out) {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int total = 0;
+    for (int item = warp; item < g.nic; item += nwarps) {
+        const Lane2 l = lane_of(g, 0, nrows, item);
+        const unsigned char* ta = tn + l.rowa * g.tpitch;
+        const CellPrefix cp = cell_prefix<false>(g, ta, l.rowa_in, l.rowb_in, l.cell);
+        total = cp.total;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!(r ? l.actb : l.acta)) continue;
+            const int cc = ta[r * g.tpitch + l.cell];
+            if (cc > 0) {
+                const int o = r ? cp.offb : cp.offa, sh = o & 31;
+                const unsigned long long v = (unsigned long long)tw[(l.rowa + r) * g.ncol + l.cell] << (64 - cc - sh);
+                atomicOr(out + (o >> 5), (unsigned)(v >> 32));
+                if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
+            }
+        }
+    }
+    if (warp >= g.nic) total = table_total(g, tn, nrows);  // warps without an item still report the total
+    return total;
+}
 
 // grid = n_units * nb.  stage_bits: per (unit, pass, band) `bandwords` words, stream bit k at bit
 // 31-(k&31) of word k>>5; stage_cnt: carriers per (unit, pass, band).
@@ -973,10 +1014,9 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     const Smem2 L = layout2(g, 2);
     unsigned char* simg = smem_raw + L.img;
     unsigned char* slm = smem_raw + L.lm;
-    int* tn1 = reinterpret_cast<int*>(smem_raw + L.tab);
-    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
-    int* tn0 = reinterpret_cast<int*>(smem_raw + L.tn0);
+    unsigned char* tn0 = smem_raw + L.tn0;
+    unsigned char* tn1 = smem_raw + L.tn1;
     unsigned* tw0 = reinterpret_cast<unsigned*>(smem_raw + L.tw0);
     unsigned* tw1 = reinterpret_cast<unsigned*>(smem_raw + L.tw1);
     unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + L.stream);  // [2][bandwords]: pass 0, pass 1
@@ -1017,22 +1057,26 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
             for (int r = l_lo + warp; r < l_hi; r += nwarps)
                 for (int k = lane; k < g.lmw; k += 32) slm[(size_t)(r - (r0 - 1)) * g.lmpitch + k] = glm[(size_t)r * g.lmw + k];
         }
+        PHASE_MARK(24);  // location map + copies issued
         // bytes between lmw and the pitch are read by steps past the row end: keep them defined
         const int padb = g.lmpitch - g.lmw;
         for (int r = warp; r < g.R + 2; r += nwarps)
             if (lane < padb) slm[(size_t)r * g.lmpitch + g.lmw + lane] = 0;
         for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
+        // count tables: the bytes past ncol are summed with the rest (tn0 and tn1 are adjacent)
+        for (int k = threadIdx.x; k < (2 * g.R * g.tpitch) >> 2; k += blockDim.x) reinterpret_cast<unsigned*>(tn0)[k] = 0u;
         // the unit's output words start from zero (the gather kernel ORs the boundary words in and skips
         // zero words): every band clears its share, instead of a memset on the stream
         unsigned* pout = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
         const long long z_lo = zero_words * band / g.nb, z_hi = zero_words * (band + 1) / g.nb;
         for (long long k = z_lo + threadIdx.x; k < z_hi; k += blockDim.x) pout[k] = 0u;
     }
-    wait_rows2(g, s_lo, s_hi, bar);
+    PHASE_MARK(25);  // tables cleared
+    WAIT_ROWS2_MARKED(g, s_lo, s_hi, bar, 26);
     PHASE_MARK(0);  // load
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
-    const int n = max(own_hi - own_lo, 0) * g.ncol;
+    const int nrows = max(own_hi - own_lo, 0);
     {   // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
         Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn1, tw1};
         sweep2_colour<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
@@ -1051,24 +1095,12 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     // the recovered rows leave while the carrier bits are assembled
     if (bt.dst)
         store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
-    // the scans turn counts into bit offsets; a piece's size is the next offset minus its own
-    int total0, total1;
-    block_scan_runs2(tn0, tn1, n, misc, total0, total1);
+    PHASE_MARK(27);  // stores issued
+    const int total0 = assemble_stream(g, nrows, tn0, tw0, stream);
+    const int total1 = assemble_stream(g, nrows, tn1, tw1, stream + g.bandwords);
+    PHASE_MARK(28);  // assembled
     __syncthreads();
-    for (int k2 = threadIdx.x; k2 < 2 * n; k2 += blockDim.x) {
-        const int pass = k2 >= n, k = k2 - pass * n;
-        const int* cnt = pass ? tn1 : tn0;
-        const int o = cnt[k];
-        const int cc = (k + 1 < n ? cnt[k + 1] : (pass ? total1 : total0)) - o;
-        if (cc > 0) {
-            unsigned* out = stream + (size_t)pass * g.bandwords;
-            const int sh = o & 31;
-            const unsigned long long v = (unsigned long long)(pass ? tw1 : tw0)[k] << (64 - cc - sh);
-            atomicOr(out + (o >> 5), (unsigned)(v >> 32));
-            if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
-        }
-    }
-    __syncthreads();
+    PHASE_MARK(29);  // barrier
     for (int pass = 0; pass < 2; ++pass) {
         const int total = pass ? total1 : total0;
         const long long slot = ((long long)unit * 2 + pass) * g.nb + band;
@@ -1078,7 +1110,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         const int nw = (total + 31) >> 5;
         for (int k = threadIdx.x; k < nw; k += blockDim.x) gout[k] = out[k];
     }
-    PHASE_MARK(5);  // scans + stream assembly + staging writes
+    PHASE_MARK(5);  // stream assembly + staging writes
     store_rows2_wait(g);
     PHASE_MARK(6);  // store
 }
@@ -1185,12 +1217,14 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
             t.cws = cws; t.CW = cws * pxs;
             if (forceCW && t.CW != forceCW) continue;
             t.ncol = (nsteps + cws - 1) / cws;
+            t.tpitch = (int)align_up((size_t)t.ncol, 16);
+            t.nic = (t.ncol + parts - 1) / parts;
             t.bandwords = (R * ((w + 1) / 2) + 31) / 32 + 2;
             const size_t smem = layout2(t, kind).total;
             if (smem > (size_t)ws->max_smem_optin) continue;
-            const int nic = (t.ncol + parts - 1) / parts;  // warp items of a one-group pass
-            for (int threads : {256, 512, 1024}) {
-                if (forceT && threads != forceT) continue;
+            const int nic = t.nic;  // warp items of a sweep
+            for (int threads : {128, 256, 512, 1024}) {
+                if (forceT ? threads != forceT : threads == 128) continue;  // 128-thread CTAs: experiments only (PEEB_CTA_THREADS)
                 const int nwarps = threads / 32;
                 int cps = (int)(sm_total / (smem + 1024));
                 cps = std::min(cps, 2048 / threads);
@@ -1265,7 +1299,9 @@ static int launch_extract2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long
 }
 // (CTA size, CTAs per SM) pairs the kernels are compiled for: registers per thread = 64K / (NT * MINB)
 #define PEEB_DISPATCH2_T(FN, PIXT, ...)                                                     \
-    (g.threads == 256 ? (g.minb >= 3 ? FN<PIXT, 256, 3>(__VA_ARGS__) : g.minb == 2 ? FN<PIXT, 256, 2>(__VA_ARGS__) \
+    (g.threads == 128 ? (g.minb >= 6 ? FN<PIXT, 128, 6>(__VA_ARGS__) : g.minb == 5 ? FN<PIXT, 128, 5>(__VA_ARGS__) \
+                                                                    : FN<PIXT, 128, 4>(__VA_ARGS__))               \
+     : g.threads == 256 ? (g.minb >= 3 ? FN<PIXT, 256, 3>(__VA_ARGS__) : g.minb == 2 ? FN<PIXT, 256, 2>(__VA_ARGS__) \
                                                                     : FN<PIXT, 256, 1>(__VA_ARGS__))               \
      : g.threads == 512 ? (g.minb >= 2 ? FN<PIXT, 512, 2>(__VA_ARGS__) : FN<PIXT, 512, 1>(__VA_ARGS__))           \
                         : FN<PIXT, 1024, 1>(__VA_ARGS__))
@@ -1286,7 +1322,7 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     int* dT; unsigned* dN; char* extra;
     const size_t cnt_bytes = align_up((size_t)nbands * sizeof(int), 256);
     const size_t st_bytes = align_up((size_t)nbands * sizeof(unsigned long long), 256);
-    const size_t rc_bytes = align_up((size_t)n_units * h * g.ncol, 256);
+    const size_t rc_bytes = align_up((size_t)n_units * h * g.tpitch, 256);
     rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256 + rc_bytes, st, &dT, &dN, &extra);
     if (rc) return rc;
     int* band_cnt = (int*)extra;
@@ -1354,8 +1390,8 @@ int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, 
 #ifdef PEEB_PHASE_TIMING
 extern "C" __attribute__((visibility("default"))) int peeb_debug_phases(unsigned long long* out16, int reset) {
     cudaDeviceSynchronize();
-    if (out16) cudaMemcpyFromSymbol(out16, peeb::g_phase, sizeof(unsigned long long) * 16);
-    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(peeb::g_phase, z, sizeof(z)); }
+    if (out16) cudaMemcpyFromSymbol(out16, peeb::g_phase, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(peeb::g_phase, z, sizeof(z)); }
     return 0;
 }
 #endif

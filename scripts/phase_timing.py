@@ -12,8 +12,8 @@ import torch
 from codec_tcc_b200 import _cabi, device as D
 from codec_tcc_b200.synth import synth_batch
 
-NAMES = ["tables", "payload+scan0", "band copy wait", "apply0", "barrier", "count1", "barrier", "scan1", "look-back",
-         "stage payload 1", "apply1", "stats+barrier", "store"]
+NAMES = ["set-up + pass-0 order/bits", "band copy wait", "apply0", "barrier", "count1", "barrier", "total + look-back",
+         "apply1", "barrier + store issue + stats", "location map + store drain"]
 
 
 def main():
@@ -35,7 +35,7 @@ def main():
     d_lm = torch.empty((n, h, (w + 7) // 8), dtype=torch.uint8, device=dev)
     for _ in range(3):
         D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm)
-    buf = (C.c_ulonglong * 16)()
+    buf = (C.c_ulonglong * 32)()
     fn(buf, 1)
     reps = 5
     for _ in range(reps):
@@ -48,16 +48,22 @@ def main():
         for _ in range(reps):
             D.pee_extract_device(d_marked, d_lm, T, cap, bd, payload_out=d_out, recovered=d_rec)
         fn(buf, 0)
-        names = ["load", "sweep colour 1", "barrier", "sweep colour 0", "barrier", "scan+assemble+stage", "store"]
-        tot = sum(buf[i] for i in range(7))
+        names = ["load", "sweep colour 1", "barrier", "sweep colour 0", "barrier", "assemble+stage", "store"]
+        names += [""] * 17 + ["  location map + copies issued", "  tables cleared", "  mbarrier wait", "  stores issued", "  assembled", "  barrier"]
+        tot = sum(buf[i] for i in range(32))
         print("extract kernel phases")
         for i, nm in enumerate(names):
+            if not nm:
+                continue
             print(f"  {nm:22s} {buf[i] / reps:14.0f} total  {100.0 * buf[i] / max(tot, 1):5.1f}%")
         return
-    tot = sum(buf[i] for i in range(13))
-    print(f"embed kernel phases, {n}x{h}x{w} bd={bd} T={T}: mean cycles per CTA (thread 0), share")
-    for i, nm in enumerate(NAMES):
-        print(f"  {nm:18s} {buf[i] / reps:14.0f} total  {100.0 * buf[i] / max(tot, 1):5.1f}%")
+    names = NAMES + [""] * 6 + ["  copies issued", "  band counts", "  pass-0 order + bits (first item)", "  mbarrier wait", "  barrier after pass 1", "  stores issued"]
+    tot = sum(buf[i] for i in range(32))
+    print(f"embed kernel phases, {n}x{h}x{w} bd={bd} T={T}: cycles of thread 0 summed over the CTAs, share")
+    for i, nm in enumerate(names):
+        if not nm:
+            continue
+        print(f"  {nm:30s} {buf[i] / reps:14.0f} total  {100.0 * buf[i] / max(tot, 1):5.1f}%")
 
 
 if __name__ == "__main__":
