@@ -321,7 +321,8 @@ template <> struct PixOps<unsigned short> {
     // pixel += d inside the packed word (exact while the new value stays inside the pixel's range)
     template <int Q, int S> static __device__ __forceinline__ void addpacked(uint4& M, int d) {
         unsigned& wv = compr<S>(M);
-        wv += Q == 0 ? (unsigned)d : ((unsigned)d << 16);
+        // (add and shift kept off the FMA pipe: VIADDMNMX with a neutral max, PRMT as the 16-bit shift)
+        wv = __viaddmax_u32(wv, Q == 0 ? (unsigned)d : __byte_perm((unsigned)d, 0u, 0x1044), 0u);
     }
     // pixel = (pixel + d) mod 2^16, the neighbour in the word untouched whatever the value (extract: any input)
     template <int Q, int S> static __device__ __forceinline__ void addwrap(uint4& M, int d) {
@@ -415,7 +416,7 @@ __device__ __forceinline__ void take_bit(int& nv, unsigned& W, int q, int T8) {
         "setp.lt.u32 p, %2, %3;\n\t"
         "setp.lt.and.s32 pb, %1, 0, p;\n\t"
         "@pb add.s32 %0, %0, 1;\n\t"
-        "@p shl.b32 %1, %1, 1;\n\t}"
+        "@p shf.l.wrap.b32 %1, 0, %1, 1;\n\t}"
         : "+r"(nv), "+r"(W) : "r"(q), "r"(T8));
 }
 // count: carrier <=> q < 8T and 0 <= v < maxval (v = x + e)
@@ -485,18 +486,27 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
         const int c0 = l.cell * g.CW;
         if (!body.primed) body.begin(l.rowa, l.cell, l.acta, l.actb, l.rowa_in, l.rowb_in, T);
         body.primed = false;
+        // Steps that touch a border column (or, for extract, cells with location-map bits) take the generic code:
+        // one warp-uniform bit per step, worked out once per item.
+        unsigned spm;
+        {
+            constexpr int PXL = P::PXS == 8 ? 3 : 4;
+            const int t = g.w - 1 - c0 - P::PXS;                 // step s is at the right border iff s * PXS > t
+            const int s_edge = t < 0 ? 0 : (t >> PXL) + 1;
+            unsigned m = s_edge >= 32 ? 0u : (0xffffffffu << s_edge);
+            if (c0 == 0) m |= 1u;
+            if (body.item_special()) m = 0xffffffffu;
+            spm = __reduce_or_sync(0xffffffffu, m);
+        }
         // the row whose colour sits on even columns looks one word back, the other one word ahead
         unsigned prev = *reinterpret_cast<const unsigned*>((QA == 0 ? pa : pb) - 4);
 #pragma unroll 1
         for (int s = 0; s < g.cws; ++s) {
-            const int c = c0 + s * P::PXS;
             const uint4 U = lds128(pu), D = lds128(pd);
             uint4 A = lds128(pa), B = lds128(pb);
             const unsigned next = *reinterpret_cast<const unsigned*>((QA == 0 ? pb : pa) + 16);
             const unsigned newprev = QA == 0 ? A.w : B.w;
-            // steps that touch a border column (or, for extract, location-map bits) take the generic code
-            const bool special = __any_sync(0xffffffffu, body.special(c, s));
-            body.template step<QA>(c, s, special, U, A, B, D, prev, next, pa, pb);
+            body.template step<QA>(c0 + s * P::PXS, s, (spm >> s) & 1u, U, A, B, D, prev, next, pa, pb);
             prev = newprev;
             pu += 16; pa += 16; pb += 16; pd += 16;
         }
@@ -510,7 +520,6 @@ __device__ __forceinline__ void sweep2_colour(const Geom2& g, unsigned char* sim
     else sweep2<PixT, 0>(g, simg, r_first, row_lo, row_hi, T, body);
 }
 
-__device__ __forceinline__ bool edge_step(const Geom2& g, int c, int pxs) { return c == 0 || c + pxs > g.w - 1; }
 
 // ---- count carriers of one colour per (row, cell) ----------------------------------------------
 template <typename PixT, bool GLOBAL>
@@ -529,7 +538,7 @@ struct Count2 {
         na = nb = 0;
         ia = (rowa - row0) * g.tpitch + cell;
     }
-    __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
+    __device__ __forceinline__ bool item_special() const { return false; }
     template <int Q, bool EDGE>
     __device__ __forceinline__ void row(const uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
                                         const KE& k, int c, int& n) {
@@ -602,26 +611,36 @@ struct Apply2 {
         ssea = sseb = 0;
         lma = slm ? slm + (long long)(rowa - lm_row0) * lmwords : nullptr;
     }
-    __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS); }
-    // All predictions read the words as loaded (M); the differences are added to a separate copy (O) inside the
-    // packed words: O += d << (position of the pixel) is exact as long as the new value stays in range, which is
-    // what `bad` watches -- no pixel is unpacked or re-inserted.
+    __device__ __forceinline__ bool item_special() const { return false; }
+    // The fast code of a step has two halves.  probe: predictions and differences of all colour pixels of the two
+    // rows from the words as loaded, nothing modified, and the watch for a value leaving [0, maxval) -- the warp
+    // votes on that before any state changes, so the generic code needs no saved copies to start over from.
+    // commit: payload bits, SSE, and the differences added inside the packed words (O += d << position of the
+    // pixel is exact because the new value stays in range) -- no pixel is unpacked or re-inserted.
     template <int Q>
-    __device__ __forceinline__ bool fast(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
-                                         const uint4& D, const KE& k, unsigned& W, long long& sse) {
+    __device__ __forceinline__ bool probe(const uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
+                                          const KE& k, int (&q)[P::NS], int (&d)[P::NS]) {
         bool bad = false;
         static_for<0, P::NS>([&](auto Sc) {
             constexpr int S = decltype(Sc)::value;
-            const int q = P::template qsum<Q, S>(M, prev, next, U, D, k.init);
-            const int cc = max(min(q >> 2, k.T2), 0);               // clamp(e + T, 0, 2T)
-            int d = cc + k.negT;                                    // e | +T | -T
-            const int nv0 = P::template addx<Q, S>(M, d);           // x + e | x + T | x - T
+            q[S] = P::template qsum<Q, S>(M, prev, next, U, D, k.init);
+            // clamp(e, -T, T) = e | +T | -T, with the add inside the min (VIADDMNMX, ALU pipe: the FMA pipe is
+            // where the IDPs of the predictor run, the busiest unit of this kernel)
+            d[S] = max(__viaddmin_s32(q[S] >> 2, k.negT, k.T), k.negT);
+            const int nv0 = P::template addx<Q, S>(M, d[S]);        // x + e | x + T | x - T
             bad |= (unsigned)nv0 >= (unsigned)g.maxval;             // (maxval itself is fine for a shift: rare, generic code sorts it out)
-            take_bit(d, W, q, k.T8);
-            sse += (long long)d * (long long)d;
-            P::template addpacked<Q, S>(O, d);
         });
         return bad;
+    }
+    template <int Q>
+    __device__ __forceinline__ void commit(uint4& O, const KE& k, const int (&q)[P::NS], int (&d)[P::NS], unsigned& W,
+                                           long long& sse) {
+        static_for<0, P::NS>([&](auto Sc) {
+            constexpr int S = decltype(Sc)::value;
+            take_bit(d[S], W, q[S], k.T8);
+            sse += (long long)d[S] * (long long)d[S];
+            P::template addpacked<Q, S>(O, d[S]);
+        });
     }
     template <int Q>
     __device__ __forceinline__ void generic(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
@@ -655,17 +674,18 @@ struct Apply2 {
     template <int QA>
     __device__ __forceinline__ void step(int c, int, bool special, const uint4& U, uint4& A, uint4& B, const uint4& D,
                                          unsigned prev, unsigned next, unsigned char* pa, unsigned char* pb) {
-        const uint4 A0 = A, B0 = B;
-        const unsigned Wa0 = Wa, Wb0 = Wb;
-        const long long sa0 = ssea, sb0 = sseb;
+        int qa[P::NS], da[P::NS], qb[P::NS], db[P::NS];
         bool redo = special;
         if (!special) {
-            bool bad = fast<QA>(A0, A, prev, next, U, B0, ka, Wa, ssea);
-            bad |= fast<1 - QA>(B0, B, prev, next, A0, D, kb, Wb, sseb);
+            bool bad = probe<QA>(A, prev, next, U, B, ka, qa, da);
+            bad |= probe<1 - QA>(B, prev, next, A, D, kb, qb, db);
             redo = __any_sync(0xffffffffu, bad);
         }
-        if (redo) {
-            A = A0; B = B0; Wa = Wa0; Wb = Wb0; ssea = sa0; sseb = sb0;
+        if (!redo) {
+            commit<QA>(A, ka, qa, da, Wa, ssea);
+            commit<1 - QA>(B, kb, qb, db, Wb, sseb);
+        } else {
+            const uint4 A0 = A, B0 = B;
             generic<QA>(A0, A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
             generic<1 - QA>(B0, B, prev, next, A0, D, kb, c, Wb, sseb, ownb, lma ? lma + lmwords : nullptr);
 #ifdef PEEB_COUNT_REDO
@@ -675,10 +695,10 @@ struct Apply2 {
 #ifdef PEEB_COUNT_REDO
         if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo[2], 1ull);
 #endif
-        if (c < g.w) {
-            if (sta) sts128(pa, A);
-            if (stb) sts128(pb, B);
-        }
+        // (steps past the end of the row run the generic code with T = 0 everywhere: they store back what they read,
+        // into the padding of the shared rows)
+        if (sta) sts128(pa, A);
+        if (stb) sts128(pb, B);
     }
     __device__ __forceinline__ void end() {
         if (owna) st->sse += ssea;
@@ -933,7 +953,7 @@ struct Extract2 {
     __device__ __forceinline__ unsigned lmbits(unsigned long long v, int s) const {
         return (unsigned)(v >> (s * P::PXS)) & (P::PXS == 8 ? 0xffu : 0xffffu);
     }
-    __device__ __forceinline__ bool special(int c, int) const { return edge_step(g, c, P::PXS) || (la | lb) != 0ull; }
+    __device__ __forceinline__ bool item_special() const { return (la | lb) != 0ull; }
     template <int Q, bool SPECIAL>
     __device__ __forceinline__ void row(const uint4& M, uint4& O, unsigned prev, unsigned next, const uint4& U,
                                         const uint4& D, const KX& k, int c, unsigned lmb, unsigned& W, int& n) {
@@ -966,10 +986,8 @@ struct Extract2 {
             row<QA, false>(A0, A, prev, next, U, B0, ka, c, 0u, Wa, na);
             row<1 - QA, false>(B0, B, prev, next, A0, D, kb, c, 0u, Wb, nb);
         }
-        if (c < g.w) {
-            if (sta) sts128(pa, A);
-            if (stb) sts128(pb, B);
-        }
+        if (sta) sts128(pa, A);
+        if (stb) sts128(pb, B);
     }
     __device__ __forceinline__ void end() {
         if (reca) { tn[in] = (unsigned char)na; tw[ia] = Wa; }
@@ -1217,6 +1235,9 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
             t.cws = cws; t.CW = cws * pxs;
             if (forceCW && t.CW != forceCW) continue;
             t.ncol = (nsteps + cws - 1) / cws;
+            // a shared row holds whole cells: the steps of the last cell that lie past the end of the image row
+            // read and store back padding of their own row, never the start of the next one
+            t.pitch = (int)align_up((size_t)std::max(g.rowbytes, t.ncol * t.CW * itemsize), 128) + 16;
             t.tpitch = (int)align_up((size_t)t.ncol, 16);
             t.nic = (t.ncol + parts - 1) / parts;
             t.bandwords = (R * ((w + 1) / 2) + 31) / 32 + 2;
@@ -1305,8 +1326,14 @@ static int launch_extract2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long
                                                                     : FN<PIXT, 256, 1>(__VA_ARGS__))               \
      : g.threads == 512 ? (g.minb >= 2 ? FN<PIXT, 512, 2>(__VA_ARGS__) : FN<PIXT, 512, 1>(__VA_ARGS__))           \
                         : FN<PIXT, 1024, 1>(__VA_ARGS__))
+#ifdef PEEB_DEV_ONE_VARIANT  // development builds (SASS inspection): only the 16-bit, 256-thread, 3-CTA kernels
+#undef PEEB_DISPATCH2_T
+#define PEEB_DISPATCH2_T(FN, PIXT, ...) FN<PIXT, 256, 3>(__VA_ARGS__)
+#define PEEB_DISPATCH2(FN, ...) PEEB_DISPATCH2_T(FN, unsigned short, __VA_ARGS__)
+#else
 #define PEEB_DISPATCH2(FN, ...) \
     (g.itemsize == 2 ? PEEB_DISPATCH2_T(FN, unsigned short, __VA_ARGS__) : PEEB_DISPATCH2_T(FN, unsigned char, __VA_ARGS__))
+#endif
 
 int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
                       int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,

@@ -15,7 +15,7 @@ def functions(obj):
     return out
 
 
-if len(sys.argv) > 1 and sys.argv[1] == 'dump':
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dump":
     obj, pattern, first, last = sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
     for name, ls in functions(obj):
         if re.search(pattern, name):
@@ -24,19 +24,20 @@ if len(sys.argv) > 1 and sys.argv[1] == 'dump':
             break
     sys.exit(0)
 
-obj = sys.argv[1] if len(sys.argv) > 1 else '/root/repo/codec_tcc_b200/lib/peeb_pee2.o'
-flt = sys.argv[2] if len(sys.argv) > 2 else r'ItLi256ELi3E'
-for name, lines in functions(obj):
-    if not re.search(flt, name):
-        continue
-    print(name[:60], 'total', len(lines))
-    for i, l in enumerate(lines):
-        if 'BRA' in l:
-            m = re.search(r'0x([0-9a-f]+)', l)
-            if m:
-                t = int(m.group(1), 16) // 16
-                if t < i and i - t > 60:
-                    body = lines[t:i + 1]
-                    if sum('IDP' in b for b in body) == 0:
-                        continue
-                    print(f"  loop {t}->{i} len {i-t+1} IDP {sum('IDP' in b for b in body)} MOV {sum('MOV' in b for b in body)} SEL {sum(b.startswith('SEL') for b in body)}")
+if __name__ == '__main__':
+    obj = sys.argv[1] if len(sys.argv) > 1 else '/root/repo/codec_tcc_b200/lib/peeb_pee2.o'
+    flt = sys.argv[2] if len(sys.argv) > 2 else r'ItLi256ELi3E'
+    for name, lines in functions(obj):
+        if not re.search(flt, name):
+            continue
+        print(name[:60], 'total', len(lines))
+        for i, l in enumerate(lines):
+            if 'BRA' in l:
+                m = re.search(r'0x([0-9a-f]+)', l)
+                if m:
+                    t = int(m.group(1), 16) // 16
+                    if t < i and i - t > 60:
+                        body = lines[t:i + 1]
+                        if sum('IDP' in b for b in body) == 0:
+                            continue
+                        print(f"  loop {t}->{i} len {i-t+1} IDP {sum('IDP' in b for b in body)} MOV {sum('MOV' in b for b in body)} SEL {sum(b.startswith('SEL') for b in body)}")
