@@ -154,8 +154,8 @@ class Workspace:
         return lib().peeb_ws_stream(self.handle) or 0
 
     def set_option(self, name: str, value: bool):
-        """'bulk' (TMA bulk band staging) / 'cluster' (cluster-resident small images)."""
-        opt = {"bulk": 0, "cluster": 1}[name]
+        """'bulk': TMA bulk copies for band staging (default on)."""
+        opt = {"bulk": 0}[name]
         check(lib().peeb_ws_set_option(self.handle, opt, 1 if value else 0), "peeb_ws_set_option")
 
     # profiling counters (bench.py's roofline leg)

@@ -89,8 +89,6 @@ int peeb_ws_create(int device, peeb_ws** out) {
     for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pev[i], cudaEventDisableTiming));
     const char* nb = getenv("PEEB_NO_BULK");
     ws->use_bulk = !(nb && nb[0] == '1');
-    const char* nc = getenv("PEEB_NO_CLUSTER");
-    ws->use_cluster = !(nc && nc[0] == '1');
     *out = ws;
     return PEEB_OK;
 }
@@ -137,7 +135,6 @@ void* peeb_ws_stream(peeb_ws* ws) { return ws ? (void*)ws->stream : nullptr; }
 int peeb_ws_set_option(peeb_ws* ws, int option, int value) {
     PEEB_REQUIRE(ws != nullptr, "peeb_ws_set_option: null workspace");
     if (option == PEEB_OPT_BULK) ws->use_bulk = value ? 1 : 0;
-    else if (option == PEEB_OPT_CLUSTER) ws->use_cluster = value ? 1 : 0;
     else { set_error("peeb_ws_set_option: unknown option %d", option); return PEEB_E_INVALID; }
     return PEEB_OK;
 }

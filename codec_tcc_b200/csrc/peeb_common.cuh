@@ -60,7 +60,6 @@ struct peeb_ws {
     peeb::Scratch info_h;            // pinned landing zone for per-unit info rows (keeps every copy of a
                                      // host batch asynchronous even when the caller's info array is pageable)
     int use_bulk = 1;                // TMA bulk copies (PEEB_NO_BULK=1 disables)
-    int use_cluster = 1;             // cluster-resident path for small images (PEEB_NO_CLUSTER=1 disables)
     // profiling: accumulate per-kernel device time with events when enabled
     int prof_on = 0;
     float prof_ms[PEEB_PROF_SLOTS] = {0};

@@ -13,7 +13,7 @@
 namespace peeb {
 
 
-__global__ void pee_finalize_kernel(PeeBatch bt, int extract) {
+__global__ void pee_finalize_kernel(PeeBatch bt) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= bt.n_units) return;
     long long* info = bt.info + (long long)u * PEEB_INFO;
@@ -21,7 +21,6 @@ __global__ void pee_finalize_kernel(PeeBatch bt, int extract) {
     info[1] = bt.n_bits[u];
     info[2] = info[3] + info[4];
     info[7] = ((long long)bt.n_bits[u] > info[2]) ? PEEB_E_CAPACITY : 0;
-    (void)extract;
 }
 
 // ------------------------------------------------------------------ prediction-error histogram
@@ -133,7 +132,7 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
     }
     PeeBatch bt{};
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
-    pee_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt, 0);
+    pee_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt);
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }
@@ -170,7 +169,7 @@ static int extract_batch_impl(peeb_ws* ws, const void* marked, int64_t marked_st
                                                  (size_t)h * w * itemsize, cudaMemcpyDeviceToDevice, st));
     PeeBatch bt{};
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
-    pee_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt, 1);
+    pee_finalize_kernel<<<(n_units + 127) / 128, 128, 0, st>>>(bt);
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }
@@ -275,7 +274,7 @@ static std::vector<int> chunk_plan(int n_units, size_t unit_bytes, int cmax_limi
     return plan;
 }
 
-int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w, int itemsize,
+static int peeb_pee_embed_h_impl(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w, int itemsize,
                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
                      int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
     PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_embed_h: null pointer");
@@ -353,7 +352,19 @@ int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_
     return PEEB_OK;
 }
 
-int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
+int peeb_pee_embed_h(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w, int itemsize,
+                     int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
+                     int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
+    // a failed call returns only after the copies of earlier chunks have stopped touching the caller's buffers
+    const int rc = peeb_pee_embed_h_impl(ws, src_host, shared_flags, n_units, h, w, itemsize, bit_depth, T, n_bits, payload_host, payload_stride, marked_host, lm_host, info_host);
+    if (rc != PEEB_OK && ws) {
+        cudaStreamSynchronize(ws->stream); cudaStreamSynchronize(ws->stream2); cudaStreamSynchronize(ws->stream3);
+    }
+    return rc;
+}
+
+
+static int peeb_pee_extract_h_impl(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
                        const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host, uint8_t* payload_out_host,
                        int64_t payload_stride, void* recovered_host, int64_t* info_host) {
     PEEB_REQUIRE(ws && marked_host && T && n_bits && lm_host && payload_out_host && info_host, "peeb_pee_extract_h: null pointer");
@@ -414,6 +425,18 @@ int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h,
     memcpy(info_host, info_pin, (size_t)n_units * PEEB_INFO * 8);
     return PEEB_OK;
 }
+
+int peeb_pee_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                       const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host, uint8_t* payload_out_host,
+                       int64_t payload_stride, void* recovered_host, int64_t* info_host) {
+    // a failed call returns only after the copies of earlier chunks have stopped touching the caller's buffers
+    const int rc = peeb_pee_extract_h_impl(ws, marked_host, n_units, h, w, itemsize, bit_depth, T, n_bits, lm_host, payload_out_host, payload_stride, recovered_host, info_host);
+    if (rc != PEEB_OK && ws) {
+        cudaStreamSynchronize(ws->stream); cudaStreamSynchronize(ws->stream2); cudaStreamSynchronize(ws->stream3);
+    }
+    return rc;
+}
+
 
 int peeb_pee_hist_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
                     uint32_t* hist_host) {

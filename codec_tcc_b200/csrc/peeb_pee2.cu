@@ -150,33 +150,9 @@ struct CellPrefix {
     int row0_total;   // carriers of the first row of the sweep (the halo row above a band, when there is one)
     int total;        // carriers of the whole sweep
 };
-template <bool GLOBAL>
-__device__ __forceinline__ CellPrefix cell_prefix(const Geom2& g, const unsigned char* ta, bool rowa_in, bool rowb_in,
-                                                  int cell) {
-    // ta: table row of rowa (row of rowa + 1 follows at ta + tpitch); shared or global memory
-    const int lane = threadIdx.x & 31, rp = lane & (g.rpw - 1);
-    const int jc = cell >> 2;
-    const unsigned partial = 0x01010101u & ((1u << (8 * (cell & 3))) - 1u);
-    int tota = 0, totb = 0, prea = 0, preb = 0;
-    for (int j4 = 0; j4 < g.tpitch; j4 += 16) {
-        uint4 va = make_uint4(0, 0, 0, 0), vb = va;
-        if (GLOBAL) {
-            if (rowa_in) va = __ldg(reinterpret_cast<const uint4*>(ta + j4));
-            if (rowb_in) vb = __ldg(reinterpret_cast<const uint4*>(ta + g.tpitch + j4));
-        } else {
-            if (rowa_in) va = *reinterpret_cast<const uint4*>(ta + j4);
-            if (rowb_in) vb = *reinterpret_cast<const uint4*>(ta + g.tpitch + j4);
-        }
-        const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = (j4 >> 2) + k;
-            const int sa = idp4_sum(wa[k], 0x01010101u, 0), sb = idp4_sum(wb[k], 0x01010101u, 0);
-            tota += sa; totb += sb;
-            if (j < jc) { prea += sa; preb += sb; }
-            if (j == jc) { prea = idp4_sum(wa[k], partial, prea); preb = idp4_sum(wb[k], partial, preb); }
-        }
-    }
+// warp scan over the row pairs: (carriers of row a, row b, cells left of the cell in a, in b) -> offsets
+__device__ __forceinline__ CellPrefix prefix_scan(const Geom2& g, int tota, int totb, int prea, int preb) {
+    const int rp = threadIdx.x & (g.rpw - 1);
     const int v = tota + totb;
     int incl = v;
     for (int o = 1; o < g.rpw; o <<= 1) {
@@ -189,6 +165,56 @@ __device__ __forceinline__ CellPrefix cell_prefix(const Geom2& g, const unsigned
     r.row0_total = __shfl_sync(0xffffffffu, tota, 0, g.rpw);
     r.total = __shfl_sync(0xffffffffu, incl, g.rpw - 1, g.rpw);
     return r;
+}
+// tables of at most 16 cells per row (one 16-byte word per row): the two rows of the lane, already loaded
+__device__ __forceinline__ CellPrefix cell_prefix16(const Geom2& g, const uint4& va, const uint4& vb, int cell) {
+    const int jc = cell >> 2;
+    const unsigned partial = 0x01010101u & ((1u << (8 * (cell & 3))) - 1u);
+    const unsigned one = 0x01010101u;
+    const unsigned m0 = jc > 0 ? one : partial, m1 = jc > 1 ? one : jc == 1 ? partial : 0u,
+                   m2 = jc > 2 ? one : jc == 2 ? partial : 0u, m3 = jc == 3 ? partial : 0u;
+    const int tota = idp4_sum(va.w, one, idp4_sum(va.z, one, idp4_sum(va.y, one, idp4_sum(va.x, one, 0))));
+    const int totb = idp4_sum(vb.w, one, idp4_sum(vb.z, one, idp4_sum(vb.y, one, idp4_sum(vb.x, one, 0))));
+    const int prea = idp4_sum(va.w, m3, idp4_sum(va.z, m2, idp4_sum(va.y, m1, idp4_sum(va.x, m0, 0))));
+    const int preb = idp4_sum(vb.w, m3, idp4_sum(vb.z, m2, idp4_sum(vb.y, m1, idp4_sum(vb.x, m0, 0))));
+    return prefix_scan(g, tota, totb, prea, preb);
+}
+template <bool GLOBAL>
+__device__ __forceinline__ uint4 table_row16(const unsigned char* t, bool in) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (in) v = GLOBAL ? __ldg(reinterpret_cast<const uint4*>(t)) : *reinterpret_cast<const uint4*>(t);
+    return v;
+}
+template <bool GLOBAL>
+__device__ __forceinline__ CellPrefix cell_prefix_inl(const Geom2& g, const unsigned char* ta, bool rowa_in, bool rowb_in,
+                                                      int cell) {
+    // ta: table row of rowa (row of rowa + 1 follows at ta + tpitch); shared or global memory
+    if (g.tpitch == 16)
+        return cell_prefix16(g, table_row16<GLOBAL>(ta, rowa_in), table_row16<GLOBAL>(ta + 16, rowb_in), cell);
+    const int jc = cell >> 2;
+    const unsigned partial = 0x01010101u & ((1u << (8 * (cell & 3))) - 1u);
+    int tota = 0, totb = 0, prea = 0, preb = 0;
+    for (int j4 = 0; j4 < g.tpitch; j4 += 16) {
+        const uint4 va = table_row16<GLOBAL>(ta + j4, rowa_in), vb = table_row16<GLOBAL>(ta + g.tpitch + j4, rowb_in);
+        const unsigned wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = (j4 >> 2) + k;
+            const int sa = idp4_sum(wa[k], 0x01010101u, 0), sb = idp4_sum(wb[k], 0x01010101u, 0);
+            tota += sa; totb += sb;
+            if (j < jc) { prea += sa; preb += sb; }
+            if (j == jc) { prea = idp4_sum(wa[k], partial, prea); preb = idp4_sum(wb[k], partial, preb); }
+        }
+    }
+    return prefix_scan(g, tota, totb, prea, preb);
+}
+
+// (not inlined in the embed kernel: called once per warp item from four sweeps; keeps the kernel's code, and its
+// instruction-cache footprint, small)
+template <bool GLOBAL>
+__device__ __noinline__ CellPrefix cell_prefix(const Geom2& g, const unsigned char* ta, bool rowa_in, bool rowb_in,
+                                               int cell) {
+    return cell_prefix_inl<GLOBAL>(g, ta, rowa_in, rowb_in, cell);
 }
 
 // Decoupled look-back over the bands of a unit, run by a whole warp (every warp of the CTA may run it: all of
@@ -460,13 +486,14 @@ __device__ __forceinline__ Lane2 lane_of(const Geom2& g, int row_lo, int row_hi,
     return l;
 }
 // What a body needs before its first item (payload order, payload bits: global loads) can be fetched ahead of the
-// sweep, e.g. while the band's rows are still on their way; sweep2 then skips begin() for that item.
+// sweep, e.g. while the band's rows are still on their way: sweep2_prime_order, then body.begin_bits() once the
+// body knows its base B; sweep2 then skips begin() for that item.
 template <class Body>
-__device__ __forceinline__ void sweep2_prime(const Geom2& g, int row_lo, int row_hi, int T, Body& body) {
+__device__ __forceinline__ void sweep2_prime_order(const Geom2& g, int row_lo, int row_hi, int T, Body& body) {
     const int warp = threadIdx.x >> 5;
     if (row_hi <= row_lo || warp >= g.nic) return;
     const Lane2 l = lane_of(g, row_lo, row_hi, warp);
-    body.begin(l.rowa, l.cell, l.acta, l.actb, l.rowa_in, l.rowb_in, T);
+    body.begin_order(l.rowa, l.cell, l.acta, l.actb, l.rowa_in, l.rowb_in, T);
     body.primed = true;
 }
 template <typename PixT, int QA, class Body>
@@ -500,7 +527,11 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
         }
         // the row whose colour sits on even columns looks one word back, the other one word ahead
         unsigned prev = *reinterpret_cast<const unsigned*>((QA == 0 ? pa : pb) - 4);
+#ifdef PEEB_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int s = 0; s < g.cws; ++s) {
             const uint4 U = lds128(pu), D = lds128(pd);
             uint4 A = lds128(pa), B = lds128(pb);
@@ -598,18 +629,28 @@ struct Apply2 {
     unsigned Wa, Wb;
     long long ssea, sseb;
     bool sta, stb, owna, ownb, primed;
+    int offa, offb;
     unsigned* lma;
-    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool rowa_in, bool rowb_in, int T) {
+    // begin = begin_order (where the lane's carriers sit in the pass: table rows -> offsets) + begin_bits (their
+    // payload bits); a caller that primes the first item may set B between the two
+    __device__ __forceinline__ void begin_order(int rowa, int cell, bool a, bool b, bool rowa_in, bool rowb_in, int T) {
         sta = a; stb = b;
         ka = kb = make_ke(T);
         const CellPrefix cp = cell_prefix<GTAB>(g, tab + (long long)(rowa - row0) * g.tpitch, rowa_in, rowb_in, cell);
-        const unsigned base = B - (halo ? (unsigned)cp.row0_total : 0u);
-        Wa = a ? payload_window(pay, base + (unsigned)cp.offa, n_bits) : 0u;
-        Wb = b ? payload_window(pay, base + (unsigned)cp.offb, n_bits) : 0u;
+        offa = cp.offa - (halo ? cp.row0_total : 0);
+        offb = cp.offb - (halo ? cp.row0_total : 0);
         owna = a && rowa >= own_lo && rowa < own_hi;
         ownb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
         ssea = sseb = 0;
         lma = slm ? slm + (long long)(rowa - lm_row0) * lmwords : nullptr;
+    }
+    __device__ __forceinline__ void begin_bits() {
+        Wa = sta ? payload_window(pay, B + (unsigned)offa, n_bits) : 0u;
+        Wb = stb ? payload_window(pay, B + (unsigned)offb, n_bits) : 0u;
+    }
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool rowa_in, bool rowb_in, int T) {
+        begin_order(rowa, cell, a, b, rowa_in, rowb_in, T);
+        begin_bits();
     }
     __device__ __forceinline__ bool item_special() const { return false; }
     // The fast code of a step has two halves.  probe: predictions and differences of all colour pixels of the two
@@ -804,19 +845,12 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     PHASE_INIT;
     issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
     PHASE_MARK(16);  // copies issued
-    // every warp: carriers of pass 0 in the earlier bands, and in the whole unit (cap0), from the count kernel
-    int before0 = 0, cap0 = 0;
-    for (int k = lane; k < g.nb; k += 32) {
-        const int cc = __ldg(band_cnt + unit * g.nb + k);
-        cap0 += cc;
-        if (k < band) before0 += cc;
-    }
+    // every warp: carriers of pass 0 in the earlier bands, and in the whole unit (cap0), from the count kernel's band
+    // totals.  Their loads are in flight together with the table rows of the warp's first item (sweep2_prime_order),
+    // the payload bits follow: two global round trips while the band's rows arrive, not three.
+    int ccv[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        before0 += __shfl_xor_sync(0xffffffffu, before0, o);
-        cap0 += __shfl_xor_sync(0xffffffffu, cap0, o);
-    }
-    PHASE_MARK(17);  // band counts
+    for (int i = 0; i < 4; ++i) ccv[i] = lane + 32 * i < g.nb ? __ldg(band_cnt + unit * g.nb + lane + 32 * i) : 0;
     if (!g.lm_direct) {
         for (int k = threadIdx.x; k < ((g.R + 1) * g.lmpitch) >> 2; k += blockDim.x) slm[k] = 0;
     } else if (bt.lm) {
@@ -833,12 +867,31 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         lmbase = bt.lm ? reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride) : nullptr;
         lmrow0 = 0; lmwords = g.lmw >> 2;
     }
+    int cap0 = 0;
     // ---- pass 0 (colour 0): band rows and one halo row on each side; order from the count kernel's table.
-    // The table rows and the payload bits of a warp's first item are fetched while the band's rows arrive.
     {
         Apply2<PixT, true> body{g, 0, own_lo, own_hi, rowcnt + (long long)unit * g.h * g.tpitch, payload, n_bits,
-                                (unsigned)before0, p0_lo < own_lo, lmbase, lmrow0, lmwords, &st};
-        sweep2_prime(g, p0_lo, p0_hi, T, body);
+                                0u, p0_lo < own_lo, lmbase, lmrow0, lmwords, &st};
+        sweep2_prime_order(g, p0_lo, p0_hi, T, body);
+        PHASE_MARK(17);  // pass-0 order of the first item
+        int before0 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            cap0 += ccv[i];
+            if (lane + 32 * i < band) before0 += ccv[i];
+        }
+        for (int k = lane + 128; k < g.nb; k += 32) {
+            const int cc = __ldg(band_cnt + unit * g.nb + k);
+            cap0 += cc;
+            if (k < band) before0 += cc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            before0 += __shfl_xor_sync(0xffffffffu, before0, o);
+            cap0 += __shfl_xor_sync(0xffffffffu, cap0, o);
+        }
+        body.B = (unsigned)before0;
+        if (body.primed) body.begin_bits();
         PHASE_MARK(18);  // pass-0 order and bits of the first item
         WAIT_ROWS2_MARKED(g, s_lo, s_hi, bar, 19);
         PHASE_MARK(1);  // band copy wait
@@ -1005,7 +1058,7 @@ __device__ __forceinline__ int assemble_stream(const Geom2& g, int nrows, const 
     for (int item = warp; item < g.nic; item += nwarps) {
         const Lane2 l = lane_of(g, 0, nrows, item);
         const unsigned char* ta = tn + l.rowa * g.tpitch;
-        const CellPrefix cp = cell_prefix<false>(g, ta, l.rowa_in, l.rowb_in, l.cell);
+        const CellPrefix cp = cell_prefix_inl<false>(g, ta, l.rowa_in, l.rowb_in, l.cell);
         total = cp.total;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -1056,6 +1109,14 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
             const int wpr = g.lmw >> 2, nwords = (l_hi - l_lo) * wpr;
             const unsigned* gw = reinterpret_cast<const unsigned*>(glm + (size_t)l_lo * g.lmw);
             unsigned* sw = reinterpret_cast<unsigned*>(slm);
+            // word k of the copy -> (row, word in row); rows are usually a power of two words long.  (The shared rows
+            // keep their 12-byte pad: lanes are rows, a pitch of a multiple of 128 bytes would put the map bytes of
+            // every lane in the same bank.)
+            const int wsh = (wpr & (wpr - 1)) == 0 ? 31 - __clz(wpr) : -1;
+            auto slot = [&](int k) {
+                const int r = wsh >= 0 ? k >> wsh : k / wpr;
+                return (size_t)(l_lo - (r0 - 1) + r) * (g.lmpitch >> 2) + (k - r * wpr);
+            };
             unsigned v[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -1066,10 +1127,10 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int k = threadIdx.x + i * blockDim.x;
-                if (k < nwords) sw[(size_t)(l_lo - (r0 - 1) + k / wpr) * (g.lmpitch >> 2) + (k % wpr)] = v[i];
+                if (k < nwords) sw[slot(k)] = v[i];
             }
             for (int k = threadIdx.x + 4 * blockDim.x; k < nwords; k += blockDim.x)
-                sw[(size_t)(l_lo - (r0 - 1) + k / wpr) * (g.lmpitch >> 2) + (k % wpr)] = __ldg(gw + k);
+                sw[slot(k)] = __ldg(gw + k);
         } else {
             issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
             for (int r = l_lo + warp; r < l_hi; r += nwarps)
@@ -1078,8 +1139,9 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         PHASE_MARK(24);  // location map + copies issued
         // bytes between lmw and the pitch are read by steps past the row end: keep them defined
         const int padb = g.lmpitch - g.lmw;
-        for (int r = warp; r < g.R + 2; r += nwarps)
-            if (lane < padb) slm[(size_t)r * g.lmpitch + g.lmw + lane] = 0;
+        if (padb > 0)
+            for (int r = warp; r < g.R + 2; r += nwarps)
+                if (lane < padb) slm[(size_t)r * g.lmpitch + g.lmw + lane] = 0;
         for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
         // count tables: the bytes past ncol are summed with the rest (tn0 and tn1 are adjacent)
         for (int k = threadIdx.x; k < (2 * g.R * g.tpitch) >> 2; k += blockDim.x) reinterpret_cast<unsigned*>(tn0)[k] = 0u;
@@ -1393,8 +1455,10 @@ int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, 
     bt.lm = const_cast<uint8_t*>(lm); bt.lm_stride = lm_stride;
     bt.payload = nullptr; bt.payload_stride = payload_stride; bt.payload_out = payload_out;
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
-    // bytes of every unit's output that start from zero: the whole row of a batch, the payload's own bytes for one unit
-    const long long zero_words = (long long)(n_units == 1 ? peeb_payload_bytes(n_bits[0]) : (size_t)payload_stride) / 4;
+    // bytes of every unit's output that start from zero: the whole row (the documented zero padding); a single unit
+    // may come with a buffer that is only as long as its own payload (stride unused)
+    const size_t pb0 = peeb_payload_bytes(n_bits[0]);
+    const long long zero_words = (long long)((n_units == 1 && (size_t)payload_stride < pb0) ? pb0 : (size_t)payload_stride) / 4;
     rc = PEEB_DISPATCH2(launch_extract2, ws, g, bt, nbands, stage_bits, stage_cnt, zero_words, st);
     if (rc) return rc;
     PEEB_CUDA(cudaGetLastError());

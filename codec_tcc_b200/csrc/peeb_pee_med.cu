@@ -691,7 +691,7 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
 }
 
 // ---- host-buffer variants: the whole batch is staged at once on the workspace stream (synchronous)
-int peeb_pee_med_embed_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
+static int peeb_pee_med_embed_h_impl(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
                          const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host, int64_t payload_stride,
                          void* marked_host, uint8_t* lm_host, int64_t* info_host) {
     PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_med_embed_h: null pointer");
@@ -724,7 +724,19 @@ int peeb_pee_med_embed_h(peeb_ws* ws, const void* src_host, int n_units, int h, 
     return PEEB_OK;
 }
 
-int peeb_pee_med_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
+int peeb_pee_med_embed_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                         const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host, int64_t payload_stride,
+                         void* marked_host, uint8_t* lm_host, int64_t* info_host) {
+    // a failed call returns only after the copies of earlier chunks have stopped touching the caller's buffers
+    const int rc = peeb_pee_med_embed_h_impl(ws, src_host, n_units, h, w, itemsize, bit_depth, T, n_bits, payload_host, payload_stride, marked_host, lm_host, info_host);
+    if (rc != PEEB_OK && ws) {
+        cudaStreamSynchronize(ws->stream); cudaStreamSynchronize(ws->stream2); cudaStreamSynchronize(ws->stream3);
+    }
+    return rc;
+}
+
+
+static int peeb_pee_med_extract_h_impl(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
                            const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host, uint8_t* payload_out_host,
                            int64_t payload_stride, void* recovered_host, int64_t* info_host) {
     PEEB_REQUIRE(ws && marked_host && T && n_bits && lm_host && payload_out_host && info_host, "peeb_pee_med_extract_h: null pointer");
@@ -755,5 +767,17 @@ int peeb_pee_med_extract_h(peeb_ws* ws, const void* marked_host, int n_units, in
     PEEB_CUDA(cudaStreamSynchronize(st));
     return PEEB_OK;
 }
+
+int peeb_pee_med_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize, int bit_depth,
+                           const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host, uint8_t* payload_out_host,
+                           int64_t payload_stride, void* recovered_host, int64_t* info_host) {
+    // a failed call returns only after the copies of earlier chunks have stopped touching the caller's buffers
+    const int rc = peeb_pee_med_extract_h_impl(ws, marked_host, n_units, h, w, itemsize, bit_depth, T, n_bits, lm_host, payload_out_host, payload_stride, recovered_host, info_host);
+    if (rc != PEEB_OK && ws) {
+        cudaStreamSynchronize(ws->stream); cudaStreamSynchronize(ws->stream2); cudaStreamSynchronize(ws->stream3);
+    }
+    return rc;
+}
+
 
 }  // extern "C"

@@ -71,6 +71,18 @@ def _info_dict(row):
 PREDICTORS = ("rhombus", "med")
 
 
+def _check_out(arr, name, shape, dtype):
+    """A caller-supplied output array goes to the C ABI as a raw pointer: it must be exactly what the copy back
+    writes (shape, dtype, C order, writable), or the call is refused."""
+    if not isinstance(arr, np.ndarray):
+        raise ValueError(f"{name} must be a numpy array")
+    if arr.dtype != np.dtype(dtype) or arr.shape != tuple(shape):
+        raise ValueError(f"{name} must have shape {tuple(shape)} and dtype {np.dtype(dtype)}, got {arr.shape} {arr.dtype}")
+    if not arr.flags.c_contiguous or not arr.flags.writeable:
+        raise ValueError(f"{name} must be C-contiguous and writable")
+    return arr
+
+
 def _check_predictor(predictor):
     if predictor not in PREDICTORS:
         raise ValueError(f"predictor must be one of {PREDICTORS}")
@@ -121,10 +133,12 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
         return (np.empty((0, h, w), imgs.dtype), np.empty((0, h, (w + 7) // 8), np.uint8), np.empty((0, INFO), np.int64))
     marked = None
     if want_marked:
-        marked = out_marked if out_marked is not None else np.empty((n, h, w), imgs.dtype)
+        marked = (_check_out(out_marked, "out_marked", (n, h, w), imgs.dtype) if out_marked is not None
+                  else np.empty((n, h, w), imgs.dtype))
     lm = None
     if want_lm:
-        lm = out_lm if out_lm is not None else np.empty((n, h, (w + 7) // 8), np.uint8)
+        lm = (_check_out(out_lm, "out_lm", (n, h, (w + 7) // 8), np.uint8) if out_lm is not None
+              else np.empty((n, h, (w + 7) // 8), np.uint8))
     info = np.zeros((n, INFO), np.int64)
     ws = workspace(device)
     flags = (1 if shared_cover else 0) | (2 if shared_payload else 0)
@@ -164,7 +178,10 @@ def pee_extract_batch(marked, lm, T, n_bits, bit_depth=None, *, want_recovered=T
         _check_T(t, bd)
     stride = int(((nb + 7) // 8).max()) if n else 0
     if out_payload is not None:
-        payload = out_payload
+        if not isinstance(out_payload, np.ndarray) or out_payload.ndim != 2 or out_payload.shape[0] != n \
+                or out_payload.shape[1] < stride:
+            raise ValueError(f"out_payload must be a ({n}, >= {stride}) uint8 array")
+        payload = _check_out(out_payload, "out_payload", out_payload.shape, np.uint8)
         stride = payload.shape[1]
     else:
         payload = np.zeros((n, stride), np.uint8)
@@ -172,7 +189,8 @@ def pee_extract_batch(marked, lm, T, n_bits, bit_depth=None, *, want_recovered=T
         return payload, np.empty((0, h, w), marked.dtype), np.empty((0, INFO), np.int64)
     rec = None
     if want_recovered:
-        rec = out_recovered if out_recovered is not None else np.empty((n, h, w), marked.dtype)
+        rec = (_check_out(out_recovered, "out_recovered", (n, h, w), marked.dtype) if out_recovered is not None
+               else np.empty((n, h, w), marked.dtype))
     info = np.zeros((n, INFO), np.int64)
     ws = workspace(device)
     # a zero-width payload array still needs a valid pointer

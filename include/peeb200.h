@@ -56,10 +56,8 @@ int peeb_ws_create(int device, peeb_ws** ws);
 int peeb_ws_destroy(peeb_ws* ws);
 int peeb_ws_sync(peeb_ws* ws);                 /* synchronise the workspace streams  */
 void* peeb_ws_stream(peeb_ws* ws);             /* the workspace's own cudaStream_t   */
-/* tuning / debugging switches: PEEB_OPT_BULK (TMA bulk copies for band staging, default 1),
- * PEEB_OPT_CLUSTER (cluster-resident path for small images, default 1) */
+/* tuning / debugging switch: PEEB_OPT_BULK (TMA bulk copies for band staging, default 1) */
 #define PEEB_OPT_BULK 0
-#define PEEB_OPT_CLUSTER 1
 int peeb_ws_set_option(peeb_ws* ws, int option, int value);
 /* pinned host memory for callers that want full-speed PCIe copies */
 int peeb_host_alloc(size_t bytes, void** ptr);
@@ -210,7 +208,9 @@ int peeb_pee_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n
                          const uint8_t* payload, int64_t payload_stride, void* marked,
                          int64_t marked_stride, uint8_t* lm, int64_t lm_stride, int64_t* info,
                          void* stream);
-/* payload_out: per unit peeb_payload_bytes(n_bits[u]) writable bytes, 4-byte aligned */
+/* payload_out: n_units rows of payload_stride writable bytes each (>= peeb_payload_bytes(n_bits[u])), 4-byte
+ * aligned; every row comes back zero padded up to the stride.  One unit: payload_stride may be smaller than
+ * peeb_payload_bytes(n_bits[0]) (e.g. 0), the buffer then is peeb_payload_bytes(n_bits[0]) bytes long. */
 int peeb_pee_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h,
                            int w, int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
                            const uint8_t* lm, int64_t lm_stride, uint8_t* payload_out,
