@@ -4,13 +4,19 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
 
 One "step" = one max-capacity embed followed by one extract + recovery over one
-batch of synthetic DICOM-shaped images.  Workloads (BASELINE.json configs):
-  ct512   512 slices of 512x512, 16-bit  (configs[2]; the default; PER GPU -> weak scaling)
-  dx3000  64 radiographs of 3000x3000, 12-bit in uint16  (configs[3])
-  slice   one 512x512 16-bit slice  (configs[1]; latency case, L2 resident)
+batch of DICOM-shaped images.  Workloads (BASELINE.json configs):
+  ct512     512 slices of 512x512, 16-bit  (configs[2]; the headline; PER GPU -> weak scaling)
+  dx3000    64 radiographs of 3000x3000, 12-bit in uint16  (configs[3])
+  slice     one 512x512 16-bit slice  (configs[1]; latency case, L2 flushed between steps)
+  pe        the reference's own MR image images/pe.dcm (configs[0]; pixels from tests/golden/fixtures.npz,
+            512 copies as one batch) + the reference's LSB flow of main() on it through embed_pipeline
+  ct512sat  ct512 with large clipped regions and hard edges (the generic-code stress case)
+  sweep2048 threshold sweep T = 1..64 over 64 images of 2048x2048, 16-bit (configs[4]; the (image, T)
+            grid is sharded over the ranks; embed only: capacity / SSE table)
 Printed: ONE JSON line (rank 0).  `value` is device-resident throughput (inputs
 in HBM when the clock starts), `e2e` the same metric through the numpy API with
-pinned host buffers and both PCIe copies inside the timed region.
+pinned host buffers and both PCIe copies inside the timed region; the other
+workloads follow the headline timing as `other_workloads` (device resident).
 """
 from __future__ import annotations
 
@@ -33,7 +39,11 @@ WORKLOADS = {
     "ct512": (512, 512, 512, 65535, 16, 96),
     "dx3000": (64, 3000, 3000, 4095, 12, 12),
     "slice": (1, 512, 512, 65535, 16, 96),
+    "pe": (512, 512, 512, 4095, 12, 16),
+    "ct512sat": (512, 512, 512, 65535, 16, 96),
 }
+OTHER_WORKLOADS = ("slice", "dx3000", "pe", "ct512sat", "sweep2048")
+SWEEP = {"n_images": 64, "h": 2048, "w": 2048, "bit_depth": 16, "T": tuple(range(1, 65)), "distinct": 16}
 METRIC = "pee_embed_extract_roundtrip_throughput"
 UNIT = "Mpixel/s"
 
@@ -109,10 +119,12 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, world):
+def workload_config(name, world, distinct=None):
     n, h, w, maxval, bd, T = WORKLOADS[name]
+    kind = {"pe": "copies of the reference's images/pe.dcm", "ct512sat": "synthetic images with clipped regions and hard edges"}.get(name, "synthetic images")
+    rep = f" ({distinct} distinct)" if distinct and distinct != n else ""
     return {
-        "workload": f"{name}: {n} images/GPU of {h}x{w}, {bd}-bit in uint{16 if maxval > 255 else 8}, "
+        "workload": f"{name}: {n} {kind}/GPU of {h}x{w}{rep}, {bd}-bit in uint{16 if maxval > 255 else 8}, "
                     f"PEE T={T}, payload = capacity (max-capacity embed + extract + recovery)",
         "images_per_gpu": n, "height": h, "width": w, "bit_depth": bd, "T": T,
         "parallelism": f"image-sharded x{world}, no data-path collective",
@@ -216,20 +228,278 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ the GPU arm
+def workload_images(name, n, h, w, maxval, seed):
+    """Host images of a workload: synthetic (SURVEY.md 8d generators) or the reference's own fixture.
+    Large synthetic batches repeat a few distinct images (their generation on the host would take longer
+    than the whole measurement); the distinct count is part of the workload description."""
+    from codec_tcc_b200.synth import synth_batch, synth_saturated
+
+    dtype = np.uint16 if maxval > 255 else np.uint8
+    if name == "pe":
+        z = np.load(os.path.join(ROOT, "tests", "golden", "fixtures.npz"))
+        return np.broadcast_to(z["pe"].astype(dtype), (n, h, w)), 1
+    distinct = n if h * w <= 1 << 20 else min(n, 8)
+    if name == "ct512sat":
+        base = np.stack([synth_saturated(h, w, maxval, seed + k) for k in range(distinct)]).astype(dtype)
+    else:
+        base = synth_batch(distinct, h, w, maxval, seed)
+    if distinct == n:
+        return base, distinct
+    return base[np.arange(n) % distinct], distinct
+
+
+class RoundTrip:
+    """Device-resident embed + extract of one workload on the current device (the timed unit of bench.py)."""
+
+    def __init__(self, name, rank, dev, dims=None):
+        import torch
+
+        from codec_tcc_b200 import _cabi, device as D
+
+        self.name, self.dev, self.D, self.torch = name, dev, D, torch
+        n, h, w, maxval, bd, T = dims or WORKLOADS[name]
+        self.n, self.h, self.w, self.maxval, self.bd, self.T = n, h, w, maxval, bd, T
+        self.npx = n * h * w
+        t0 = time.perf_counter()
+        imgs, self.distinct = workload_images(name, n, h, w, maxval, 2 + rank * n)
+        self.imgs_h = _cabi.pinned_empty((n, h, w), imgs.dtype)
+        self.imgs_h[...] = imgs
+        self.stride = D.payload_stride(h * w)
+        self.pays_h = _cabi.pinned_empty((n, self.stride), np.uint8)
+        self.pays_h[...] = np.random.default_rng(7 + rank).integers(0, 256, (n, self.stride), dtype=np.uint8)
+        ih = self.imgs_h
+        self.d_imgs = torch.from_numpy(ih.view(np.int16) if ih.dtype == np.uint16 else ih).to(dev)
+        self.d_pays = torch.from_numpy(self.pays_h).to(dev)
+        self.gen_s = time.perf_counter() - t0
+        # capacity of every image with this payload stream (one untimed embed, nothing written)
+        big = np.full(n, h * w, np.int64)
+        _, _, d_info = D.pee_embed_device(self.d_imgs, self.d_pays, big, T, bd, marked=False, lm=False)
+        self.cap = d_info[:, 2].cpu().numpy().astype(np.int64)
+        assert (self.cap > 0).all()
+        self.d_marked = torch.empty_like(self.d_imgs)
+        self.d_lm = torch.empty((n, h, (w + 7) // 8), dtype=torch.uint8, device=dev)
+        self.d_rec = torch.empty_like(self.d_imgs)
+        self.d_out = torch.empty((n, self.stride), dtype=torch.uint8, device=dev)
+        self.d_info_e = torch.empty((n, 8), dtype=torch.int64, device=dev)
+        self.d_info_x = torch.empty((n, 8), dtype=torch.int64, device=dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if self.npx * ih.dtype.itemsize <= 130e6 else None
+
+    def step(self):
+        D = self.D
+        D.pee_embed_device(self.d_imgs, self.d_pays, self.cap, self.T, self.bd, marked=self.d_marked, lm=self.d_lm,
+                           info=self.d_info_e)
+        D.pee_extract_device(self.d_marked, self.d_lm, self.T, self.cap, self.bd, payload_out=self.d_out,
+                             recovered=self.d_rec, info=self.d_info_x)
+
+    def timed_steps(self, k, while_busy=None):
+        """K steps, CUDA events on the launching stream; with a small workload the L2 is flushed between steps
+        and only the steps are timed.  -> total ms."""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        for a, b in ev:
+            if self.flush is not None:
+                self.flush.fill_(1)
+            a.record()
+            self.step()
+            b.record()
+        if while_busy is not None:  # the host is ahead of the GPU here: the queued steps are still running
+            while_busy()
+        torch.cuda.synchronize(self.dev)
+        return sum(a.elapsed_time(b) for a, b in ev)
+
+    def check(self, oracle_units):
+        """What was just timed: identity round trip on every image, payload on a strided sample, and marked image /
+        location map / statistics of `oracle_units` strided images against the CPU oracle (oracle/pee_ref.c)."""
+        torch = self.torch
+        n = self.n
+        assert torch.equal(self.d_rec, self.d_imgs), "recovered images differ from the originals"
+        xi, ei = self.d_info_x.cpu().numpy(), self.d_info_e.cpu().numpy()
+        assert (xi[:, 7] == 0).all() and (ei[:, 7] == 0).all()
+        assert np.array_equal(xi[:, 2], self.cap) and np.array_equal(ei[:, 2], self.cap)
+        out_h = self.d_out.cpu().numpy()
+        for u in range(0, n, max(1, n // 64)):
+            nb_, rem = int(self.cap[u]) // 8, int(self.cap[u]) % 8
+            assert np.array_equal(out_h[u, :nb_], self.pays_h[u, :nb_]), "extracted payload differs"
+            if rem:
+                assert int(out_h[u, nb_]) == int(self.pays_h[u, nb_]) & ((0xFF00 >> rem) & 0xFF)
+        checked = 0
+        if oracle_units:
+            from oracle import pee_c
+            units = sorted(set(range(0, n, max(1, n // oracle_units))))[:oracle_units]
+            sel = torch.as_tensor(units, device=self.dev)
+            marked_h = self.d_marked[sel].cpu().numpy().view(self.imgs_h.dtype)
+            lm_h = self.d_lm[sel].cpu().numpy()
+            for k, u in enumerate(units):
+                m0, lm0, i0 = pee_c.embed(self.imgs_h[u], self.pays_h[u], int(self.cap[u]), self.T, self.bd)
+                assert np.array_equal(marked_h[k], m0) and np.array_equal(lm_h[k], lm0), f"unit {u}: GPU embed differs from the CPU oracle"
+                assert i0["sse"] == int(ei[u, 6]) and i0["n_flagged"] == int(ei[u, 5]) and i0["cap0"] == int(ei[u, 3])
+                checked += 1
+        return checked
+
+    def kernel_times(self, steps):
+        """Per-kernel device time (events around every launch; separate pass, not the timed one) and the share of
+        warp-steps of the embed kernel that took the generic code."""
+        from codec_tcc_b200 import _cabi
+
+        ws = _cabi.workspace(self.dev.index)
+        ws.prof_enable(True)
+        ws.step_counters(True)
+        for _ in range(steps):
+            if self.flush is not None:
+                self.flush.fill_(1)
+            self.step()
+        self.torch.cuda.synchronize(self.dev)
+        prof = ws.prof_report()
+        ws.prof_enable(False)
+        sc = ws.step_counters(False)
+        item = self.imgs_h.dtype.itemsize
+        alg = {"pee_embed": 2 * item + 0.25, "pee_extract": 2 * item + 0.25, "pee_count": float(item),
+               "pee_gather": 0.25, "pee_finalize": 0.0}
+        kernels = {}
+        for kname, (ms, calls) in prof.items():
+            avg = ms / calls
+            kernels[kname] = {"avg_ms": avg, "launches_per_step": calls / steps,
+                              "algorithmic_gb_per_s": (alg.get(kname, 0.0) * self.npx / 1e9) / (avg * 1e-3) if avg > 0 else None}
+        tot = max(sc["steps"], 1)
+        generic = {"embed_warp_steps": sc["steps"], "at_image_border": sc["edge"] / tot, "redone_out_of_range": sc["redone"] / tot}
+        return kernels, alg, generic
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def other_roundtrip(name, rank, dev, steps=5):
+    """One of the non-headline round-trip workloads, device resident: throughput, fraction of the HBM roofline of the
+    whole step, kernel times, generic-code share, oracle check on a strided sample."""
+    import torch
+
+    rt = RoundTrip(name, rank, dev)
+    # warm up for at least ~40 ms of GPU work: the host-side set-up of a workload lets the clocks fall back
+    t0 = time.perf_counter()
+    while True:
+        for _ in range(3):
+            rt.step()
+        torch.cuda.synchronize(dev)
+        if time.perf_counter() - t0 > 0.04:
+            break
+    ms = rt.timed_steps(steps) / steps
+    checked = rt.check(4 if rt.h * rt.w > 1 << 20 else 16)
+    kernels, _, generic = rt.kernel_times(3)
+    item = rt.imgs_h.dtype.itemsize
+    peak, _ = hbm_peak()
+    gbs = (4 * item + 0.5) * rt.npx / 1e9 / (ms * 1e-3)
+    out = {"config": workload_config(name, 1, rt.distinct), "value": rt.npx / (ms * 1e-3) / 1e6, "unit": UNIT,
+           "ms_per_step": ms, "steps": steps, "step_algorithmic_gb_per_s": gbs, "frac": gbs / peak,
+           "capacity_bpp": float(rt.cap.mean() / (rt.h * rt.w)),
+           "kernel_ms": {k: round(v["avg_ms"], 5) for k, v in kernels.items()}, "generic_code": generic,
+           "oracle_units_checked": checked}
+    if name == "slice":
+        out["latency_us_per_round_trip"] = ms * 1e3
+    return out
+
+
+def pe_lsb_flow(dev):
+    """configs[0], the part the reference really implements: steps 3-5 of its main() (src/codec.py:868-880:
+    decomposition at beta = 0.4, hybrid LSB embed with 16x16 search tiles, merge) on images/pe.dcm with main()'s
+    message, through codec_tcc_b200.codec.embed_pipeline (numpy in / numpy out), beside the numpy restatement of the
+    same three calls (oracle/codec_numpy.py, pinned byte for byte to the reference's outputs on this image by
+    tests/golden) on one host core."""
+    from codec_tcc_b200 import codec
+    from oracle import codec_numpy as OC
+
+    img = np.load(os.path.join(ROOT, "tests", "golden", "fixtures.npz"))["pe"]
+    bits = codec.message_to_bits("Mensagem de teste para esteganografia!")
+
+    def gpu():
+        return codec.embed_pipeline(img, bits, beta=0.4, search_block_size=16, device=dev.index)
+
+    def cpu():
+        g, loc = OC.adaptive_modalities_decomposition(img, 0.4)
+        st, bm, used, lens, idx = OC.lsb_embed_block_then_multiplane(loc, bits, search_block_size=16)
+        return OC.merge_modalities(g, st), bm
+
+    stego, bitmaps, meta = gpu()
+    ref_stego, ref_bm = cpu()
+    assert np.array_equal(stego, ref_stego) and np.array_equal(bitmaps, np.stack(ref_bm)), "LSB flow differs from the restatement"
+
+    def wall(fn, reps):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps
+
+    gpu_s, cpu_s = wall(gpu, 10), wall(cpu, 3)
+    return {"what": "reference main() steps 3-5 on images/pe.dcm (512x512, 12 bit), 304-bit message, numpy in / numpy out",
+            "gpu_ms_per_image": gpu_s * 1e3, "cpu_ms_per_image": cpu_s * 1e3, "cpu_kind": "port",
+            "cpu_note": "numpy restatement pinned to the reference's outputs on this image (tests/golden), 1 core",
+            "bit_exact": True, "s": int(meta["s"])}
+
+
+def sweep2048(rank, world, dev, barrier, all_max):
+    """configs[4]: every threshold T = 1..64 on every image of a series of 2048x2048 16-bit images; the unit of work is
+    the (image, T) pair, contiguous blocks of the flat grid per rank (shard.partition_grid), no exchange; one real
+    embed per pair (pass 1 depends on pass 0's output), statistics only (capacity, SSE -> PSNR)."""
+    import torch
+
+    from codec_tcc_b200 import device as D, shard
+    from codec_tcc_b200.synth import synth_batch
+
+    n_img, h, w, bd = SWEEP["n_images"], SWEEP["h"], SWEEP["w"], SWEEP["bit_depth"]
+    Ts = np.asarray(SWEEP["T"], np.int32)
+    img_idx, t_idx = shard.partition_grid(n_img, Ts.size, world, rank)
+    distinct = SWEEP["distinct"]
+    mine = sorted(set(int(i) for i in img_idx))
+    base = synth_batch(distinct, h, w, (1 << bd) - 1, 5)
+    stride = D.payload_stride(h * w)
+    pay = torch.from_numpy(np.random.default_rng(11).integers(0, 256, (1, stride), dtype=np.uint8)).to(dev).repeat(Ts.size, 1)
+    d_imgs = {i: torch.from_numpy(base[i % distinct].view(np.int16)).to(dev) for i in mine}
+    groups = [(i, Ts[t_idx[img_idx == i]]) for i in mine]
+    infos = [torch.empty((len(t), 8), dtype=torch.int64, device=dev) for _, t in groups]
+
+    def run():
+        for (i, t), info in zip(groups, infos):
+            D.pee_embed_device(d_imgs[i], pay[:len(t)], np.full(len(t), h * w, np.int64), t, bd, marked=False, lm=False,
+                               info=info, shared_cover=True)
+
+    run()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run()
+    b.record()
+    torch.cuda.synchronize(dev)
+    barrier()
+    ms = all_max(a.elapsed_time(b))
+    pairs = n_img * Ts.size
+    # sanity of the table: capacity grows with T, SSE too
+    first = infos[0].cpu().numpy()
+    assert (np.diff(first[:, 2]) >= 0).all() and (first[:, 7] <= 0).all()
+    peak, _ = hbm_peak()
+    gbs = 2.0 * pairs * h * w / 1e9 / (ms * 1e-3)  # statistics only: the image is read once per pair, nothing written
+    return {"config": {"workload": f"sweep2048: T = 1..{Ts.size} on {n_img} images of {h}x{w}, {bd}-bit ({distinct} distinct), "
+                                   f"{pairs} (image, T) embeds, statistics only", "parallelism": f"(image, T) grid sharded x{world}"},
+            "value": pairs * h * w / (ms * 1e-3) / 1e6, "unit": "Mpixel/s embedded", "ms": ms, "pairs": pairs,
+            "algorithmic_gb_per_s": gbs, "frac": gbs / peak / world,
+            "table_head": [{"T": int(r[0]), "capacity": int(r[2]), "sse": int(r[6])} for r in first[:4]]}
+
+
 def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     name = args.workload
     n, h, w, maxval, bd, T = WORKLOADS[name]
-    npx = n * h * w
 
     # CPU baseline first (fork pool before CUDA is initialised in this process)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         big = h * w > 1 << 20
         n_sample = 12 if big else 192
-        px, times, procs = cpu_port_throughput(name, n_sample)
+        px, times, procs = cpu_port_throughput(name if name in ("ct512", "dx3000", "slice") else "ct512", n_sample)
         cpu_baseline = {"value": px / times[0] / 1e6, "unit": UNIT, "cores": procs, "kind": "port",
                         "sample": f"{n_sample} images of {h}x{w} from the same generator, numpy oracle "
                                   f"(oracle/pee_numpy.py) embed+extract, fork pool of {procs}, {times[0]:.1f} s wall"}
@@ -237,8 +507,7 @@ def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
 
-    from codec_tcc_b200 import _cabi, device as D, pee, shard
-    from codec_tcc_b200.synth import synth_batch
+    from codec_tcc_b200 import _cabi, pee, shard
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -253,53 +522,16 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- synthetic inputs (host, pinned) and device copies
-    t0 = time.perf_counter()
-    imgs_h = _cabi.pinned_empty((n, h, w), np.uint16 if maxval > 255 else np.uint8)
-    imgs_h[...] = synth_batch(n, h, w, maxval, 2 + rank * n)
-    stride = D.payload_stride(h * w)
-    pays_h = _cabi.pinned_empty((n, stride), np.uint8)
-    pays_h[...] = np.random.default_rng(7 + rank).integers(0, 256, (n, stride), dtype=np.uint8)
-    tdt = torch.int16 if imgs_h.dtype == np.uint16 else torch.uint8
-    d_imgs = torch.from_numpy(imgs_h.view(np.int16) if imgs_h.dtype == np.uint16 else imgs_h).to(dev)
-    d_pays = torch.from_numpy(pays_h).to(dev)
-    gen_s = time.perf_counter() - t0
+    def all_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- capacity of every image with this payload stream (one untimed embed, nothing written)
-    big = np.full(n, h * w, np.int64)
-    _, _, d_info = D.pee_embed_device(d_imgs, d_pays, big, T, bd, marked=False, lm=False)
-    cap = d_info[:, 2].cpu().numpy().astype(np.int64)
-    assert (cap > 0).all()
-
-    d_marked = torch.empty_like(d_imgs)
-    d_lm = torch.empty((n, h, (w + 7) // 8), dtype=torch.uint8, device=dev)
-    d_rec = torch.empty_like(d_imgs)
-    d_out = torch.empty((n, stride), dtype=torch.uint8, device=dev)
-    d_info_e = torch.empty((n, 8), dtype=torch.int64, device=dev)
-    d_info_x = torch.empty((n, 8), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if npx * 2 <= 130e6 else None
-
-    def step():
-        D.pee_embed_device(d_imgs, d_pays, cap, T, bd, marked=d_marked, lm=d_lm, info=d_info_e)
-        D.pee_extract_device(d_marked, d_lm, T, cap, bd, payload_out=d_out, recovered=d_rec, info=d_info_x)
-
-    def timed_steps(k, while_busy=None):
-        """K steps, CUDA events on the launching stream; with a small workload the
-        L2 is flushed between steps and only the steps are timed."""
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
-        for a, b in ev:
-            if flush is not None:
-                flush.fill_(1)
-            a.record()
-            step()
-            b.record()
-        if while_busy is not None:  # the host is ahead of the GPU here: the queued steps are still running
-            while_busy()
-        torch.cuda.synchronize(dev)
-        return sum(a.elapsed_time(b) for a, b in ev)
-
+    rt = RoundTrip(name, rank, dev)
+    npx = rt.npx
     for _ in range(args.warmup):
-        step()
+        rt.step()
     barrier()
     try:
         gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(dev).uuid)
@@ -309,7 +541,7 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     barrier()
-    ms_total = timed_steps(args.steps, sampler.sample_now if rank == 0 else None)
+    ms_total = rt.timed_steps(args.steps, sampler.sample_now if rank == 0 else None)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -322,49 +554,13 @@ def run_gpu_arm(args):
     ms_step = float(t.item()) / args.steps
     value = npx * world / (ms_step * 1e-3) / 1e6
 
-    # ---- correctness of what was just timed: identity round trip + oracle on a bounded sample
-    assert torch.equal(d_rec, d_imgs), "recovered images differ from the originals"
-    xi = d_info_x.cpu().numpy()
-    ei = d_info_e.cpu().numpy()
-    assert (xi[:, 7] == 0).all() and (ei[:, 7] == 0).all() and np.array_equal(xi[:, 2], cap) and np.array_equal(ei[:, 2], cap)
-    out_h = d_out.cpu().numpy()
-    for u in range(0, n, max(1, n // 16)):
-        nb_, rem = int(cap[u]) // 8, int(cap[u]) % 8
-        assert np.array_equal(out_h[u, :nb_], pays_h[u, :nb_]), "extracted payload differs"
-        if rem:
-            assert int(out_h[u, nb_]) == int(pays_h[u, nb_]) & ((0xFF00 >> rem) & 0xFF)
-    if rank == 0:
-        from oracle import pee_c
-        marked_h = d_marked[:2].cpu().numpy().view(imgs_h.dtype)
-        lm_h = d_lm[:2].cpu().numpy()
-        for u in range(min(2, n)):
-            m0, lm0, i0 = pee_c.embed(imgs_h[u], pays_h[u], int(cap[u]), T, bd)
-            assert np.array_equal(marked_h[u], m0) and np.array_equal(lm_h[u], lm0) and i0["sse"] == int(ei[u, 6]), \
-                "GPU embed differs from the CPU oracle"
+    # ---- correctness of what was just timed: identity round trip on all images, payloads, and a strided sample of
+    # 32 images (marked image, location map, statistics) against the CPU oracle -- outside the timed region
+    oracle_checked = rt.check(32 if rank == 0 else 0)
 
-    # ---- per-kernel device time (events around every launch; separate pass, not the timed one)
-    ws = _cabi.workspace(local)
-    ws.prof_enable(True)
-    for _ in range(args.steps):
-        if flush is not None:
-            flush.fill_(1)
-        step()
-    torch.cuda.synchronize(dev)
-    prof = ws.prof_report()
-    ws.prof_enable(False)
-    item = imgs_h.dtype.itemsize
-    alg = {"pee_embed": 2 * item + 0.25, "pee_extract": 2 * item + 0.25, "pee_count": float(item),
-           "pee_gather": 0.25, "pee_finalize": 0.0}
-    kernels = {}
-    for kname, (ms, calls) in prof.items():
-        avg = ms / calls
-        kernels[kname] = {"avg_ms": avg, "launches_per_step": calls / args.steps,
-                          "algorithmic_gb_per_s": (alg.get(kname, 0.0) * npx / 1e9) / (avg * 1e-3) if avg > 0 else None}
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    kernels, alg, generic = rt.kernel_times(args.steps)
+    item = rt.imgs_h.dtype.itemsize
+    peak, peak_src = hbm_peak()
     dom = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
@@ -378,6 +574,7 @@ def run_gpu_arm(args):
                 "step_frac": (4 * item + 0.5) * npx / 1e9 / (ms_step * 1e-3) / peak}
 
     # ---- end to end through the numpy API: pinned host buffers, both copies inside the clock
+    imgs_h, pays_h, cap = rt.imgs_h, rt.pays_h, rt.cap
     marked_p = _cabi.pinned_empty((n, h, w), imgs_h.dtype)
     lm_p = _cabi.pinned_empty((n, h, (w + 7) // 8), np.uint8)
     rec_p = _cabi.pinned_empty((n, h, w), imgs_h.dtype)
@@ -399,19 +596,42 @@ def run_gpu_arm(args):
         ie, ix = e2e_step()
     sec = time.perf_counter() - t0
     barrier()
-    t = torch.tensor([sec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps * 1e3
+    e2e_ms = all_max(sec) / e2e_steps * 1e3
     assert np.array_equal(rec_p, imgs_h) and (ie[:, 7] == 0).all() and (ix[:, 7] == 0).all()
-    lmb = lm_p.nbytes
-    h2d = imgs_h.nbytes + pay_p.nbytes + marked_p.nbytes + lmb
-    d2h = marked_p.nbytes + lmb + rec_p.nbytes + out_p.nbytes + 2 * n * 64
-    e2e = {"value": npx * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+    pcie = e2e_bytes(n, h, w, item, cap, ie)
+    e2e = {"value": npx * world / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(pcie["h2d"]),
+           "d2h_bytes_per_step": int(pcie["d2h"]), "ms_per_step": e2e_ms, "steps": e2e_steps,
            "api": "codec_tcc_b200.pee.pee_embed_batch + pee_extract_batch (numpy in / numpy out, pinned host buffers)"}
+    floor = pcie_floor(world)
+    if floor:
+        # both directions run at once: the floor of a step is the larger direction at the per-direction rate
+        e2e["pcie_floor_ms"] = max(pcie["h2d"], pcie["d2h"]) / (floor["per_rank_gbs_both_directions"] * 1e9) * 1e3
+        e2e["frac_of_pcie_floor"] = e2e["pcie_floor_ms"] / e2e_ms
+        e2e["pcie_floor_source"] = floor["source"]
 
-    stats = shard.gather_stats(d_info_e[:, :7]) if world > 1 else d_info_e
+    stats = shard.gather_stats(rt.d_info_e[:, :7]) if world > 1 else rt.d_info_e
+    images_total = int(stats.shape[0])
+    gen_s, capacity_bpp = rt.gen_s, float(cap.mean() / (h * w))
+    del rt, marked_p, lm_p, rec_p, out_p, pay_p
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs and data distributions, after the headline timing
+    others = {}
+    if not args.no_other_workloads:
+        for wl in OTHER_WORKLOADS:
+            if wl == name:
+                continue
+            try:
+                if wl == "sweep2048":
+                    others[wl] = sweep2048(rank, world, dev, barrier, all_max)
+                elif world == 1:
+                    others[wl] = other_roundtrip(wl, rank, dev)
+                    if wl == "pe":
+                        others[wl]["lsb_flow"] = pe_lsb_flow(dev)
+            except Exception as exc:  # noqa: BLE001 -- reported, never hides the headline
+                others[wl] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         launches_per_step = sum(v["launches_per_step"] for v in kernels.values())
         line = {
@@ -420,16 +640,43 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "u16" if item == 2 else "u8", "data": "synthetic",
             "config": workload_config(name, world), "roofline": roofline, "kernels": kernels, "e2e": e2e,
             "gpu_launches": int(round(launches_per_step * args.steps)), "clocks": clocks,
-            "capacity_bpp": float(cap.mean() / (h * w)), "images_total": int(stats.shape[0]),
-            "bit_exact": "round trip identity on all images; first 2 images == CPU oracle (oracle/pee_ref.c)",
+            "capacity_bpp": capacity_bpp, "images_total": images_total,
+            "bit_exact": f"round trip identity on all images; marked image, location map and statistics of {oracle_checked} "
+                         "strided images == CPU oracle (oracle/pee_ref.c); PEE parity is unpinned (no reference PEE exists)",
+            "generic_code": generic,
             "numa_cores_rank0": len(numa_cores), "ms_per_step_by_rank": [round(x, 4) for x in rank_ms],
-            "setup_s": gen_s,
+            "setup_s": gen_s, "other_workloads": others,
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def e2e_bytes(n, h, w, item, cap, info_embed):
+    """Bytes one e2e step moves over PCIe in each direction (what the host wrappers copy: payload rows are moved up
+    to the longest payload of the batch, rounded up to 16 bytes, not up to their stride)."""
+    img = n * h * w * item
+    lmb = n * h * ((w + 7) // 8)
+    pay = n * ((int(((cap + 7) // 8).max()) + 15) // 16 * 16)
+    h2d = img + pay + img + lmb                     # embed: images + payload bytes; extract: marked images + maps
+    d2h = img + lmb + img + pay + 2 * n * 64        # embed: marked + maps; extract: recovered + payloads; info rows
+    return {"h2d": h2d, "d2h": d2h}
+
+
+def pcie_floor(world):
+    """The measured host<->device copy floor of this pool's boxes with `world` ranks copying at once
+    (profiles/pcie_floor_r02.json, written by scripts/pcie_probe.py under the same torchrun launch)."""
+    path = os.path.join(ROOT, "profiles", "pcie_floor_r02.json")
+    if not os.path.exists(path):
+        return None
+    rows = json.load(open(path)).get("by_world", {})
+    row = rows.get(str(world))
+    if not row:
+        return None
+    return {"per_rank_gbs_both_directions": row["per_rank_gbs_both_directions_per_direction"],
+            "source": "profiles/pcie_floor_r02.json (scripts/pcie_probe.py, all ranks copying both ways at once)"}
 
 
 def main():
@@ -440,6 +687,7 @@ def main():
     ap.add_argument("--workload", default="ct512", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

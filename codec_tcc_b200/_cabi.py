@@ -44,6 +44,7 @@ SIGNATURES = {
     "peeb_prof_enable": (_i32, [_vp, _i32]),
     "peeb_prof_get": (_i32, [_vp, _i32, _vp, _vp]),
     "peeb_prof_name": (C.c_char_p, [_i32]),
+    "peeb_pee_step_counters": (_i32, [_vp, _i32, _vp]),
     "peeb_moments_batch": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp]),
     "peeb_moments_h": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "peeb_sse_batch": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i64, _i64, _vp, _vp]),
@@ -161,6 +162,12 @@ class Workspace:
     # profiling counters (bench.py's roofline leg)
     def prof_enable(self, on: bool):
         check(lib().peeb_prof_enable(self.handle, 1 if on else 0))
+
+    def step_counters(self, on: bool):
+        """{steps, edge, redone}: warp-steps of the PEE embed kernel counted since the last call with on=True."""
+        out = (C.c_uint64 * 3)()
+        check(lib().peeb_pee_step_counters(self.handle, 1 if on else 0, out), "peeb_pee_step_counters")
+        return {"steps": int(out[0]), "edge": int(out[1]), "redone": int(out[2])}
 
     def prof_report(self):
         out = {}

@@ -109,6 +109,7 @@ int peeb_ws_destroy(peeb_ws* ws) {
         scratch_free(ws->ptables[i]);
         scratch_free(ws->ptables_h[i], true);
         scratch_free(ws->pbits[i]);
+        if (i == 0) scratch_free(ws->step_counters);
         if (ws->pev[i]) cudaEventDestroy(ws->pev[i]);
     }
     for (int i = 0; i < 4; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
@@ -193,6 +194,20 @@ int peeb_prof_get(peeb_ws* ws, int slot, double* total_ms, long long* launches) 
     PEEB_REQUIRE(ws && slot >= 0 && slot < PEEB_PROF_SLOTS, "peeb_prof_get: bad arguments");
     if (total_ms) *total_ms = ws->prof_ms[slot];
     if (launches) *launches = ws->prof_calls[slot];
+    return PEEB_OK;
+}
+
+// Counters of the PEE embed kernel's warp-steps: {all, generic code at a border column, redone by the generic code
+// after the fast code saw a value leave the range}.  on = 1 starts counting from zero, on = 0 stops; out3 may be null.
+int peeb_pee_step_counters(peeb_ws* ws, int on, uint64_t* out3) {
+    PEEB_REQUIRE(ws != nullptr, "peeb_pee_step_counters: null workspace");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    int rc = scratch_reserve(ws->step_counters, 64);
+    if (rc) return rc;
+    PEEB_CUDA(cudaDeviceSynchronize());
+    if (out3) PEEB_CUDA(cudaMemcpy(out3, ws->step_counters.ptr, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (on) PEEB_CUDA(cudaMemset(ws->step_counters.ptr, 0, 64));
+    ws->step_counters_on = on ? 1 : 0;
     return PEEB_OK;
 }
 

@@ -60,6 +60,8 @@ struct peeb_ws {
     peeb::Scratch info_h;            // pinned landing zone for per-unit info rows (keeps every copy of a
                                      // host batch asynchronous even when the caller's info array is pageable)
     int use_bulk = 1;                // TMA bulk copies (PEEB_NO_BULK=1 disables)
+    peeb::Scratch step_counters;     // device: 3 x uint64 counters of the PEE embed kernel's step kinds
+    int step_counters_on = 0;
     // profiling: accumulate per-kernel device time with events when enabled
     int prof_on = 0;
     float prof_ms[PEEB_PROF_SLOTS] = {0};

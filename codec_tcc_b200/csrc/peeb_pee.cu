@@ -241,6 +241,13 @@ static int64_t max_payload_bytes(int n_units, const int64_t* n_bits) {
     return m;
 }
 
+// longest payload of a batch in bytes (the part of a payload row that has to cross the PCIe link)
+static int64_t max_bits_bytes(int n_units, const int64_t* n_bits) {
+    int64_t m = 0;
+    for (int u = 0; u < n_units; ++u) m = std::max<int64_t>(m, (n_bits[u] + 7) / 8);
+    return m;
+}
+
 // Units per chunk of a host batch: small enough that several chunks overlap their PCIe copies
 // with each other's kernels, large enough to fill the GPU.
 static int chunk_units(int n_units, size_t unit_bytes) {
@@ -310,6 +317,7 @@ static int peeb_pee_embed_h_impl(peeb_ws* ws, const void* src_host, int shared_f
     // two streams, each doing its own copy-in, kernels and copy-out.
     const bool roles = ws->pipe_roles != 0;
     const std::vector<int> plan = chunk_plan(n_units, img);
+    const size_t pay_width = std::min<size_t>((size_t)payload_stride, align_up((size_t)max_bits_bytes(n_units, n_bits), 16));
     for (int u0 = 0, c = 0; c < (int)plan.size(); u0 += plan[c], ++c) {
         const int n = plan[c], slot = c & 1;
         cudaStream_t st_in = roles ? ws->stream : streams[slot], st = roles ? ws->stream2 : streams[slot];
@@ -317,9 +325,9 @@ static int peeb_pee_embed_h_impl(peeb_ws* ws, const void* src_host, int shared_f
         if (!shared_src)
             PEEB_CUDA(cudaMemcpy2DAsync(d1 + (size_t)u0 * img_al, img_al, (const char*)src_host + (size_t)u0 * img, img, img, n,
                                         cudaMemcpyHostToDevice, st_in));
-        if (!shared_pay && payload_stride > 0 && payload_host)
+        if (!shared_pay && pay_width > 0 && payload_host)  // only the bytes that hold payload bits travel
             PEEB_CUDA(cudaMemcpy2DAsync(d2 + (size_t)u0 * pstride, pstride, payload_host + (size_t)u0 * payload_stride,
-                                        (size_t)payload_stride, (size_t)payload_stride, n, cudaMemcpyHostToDevice, st_in));
+                                        (size_t)payload_stride, pay_width, n, cudaMemcpyHostToDevice, st_in));
         if (roles) {
             cudaEvent_t e = ws->pipe_ev[(2 * c) % peeb_ws::kPipeEvents];
             PEEB_CUDA(cudaEventRecord(e, st_in));
@@ -386,6 +394,7 @@ static int peeb_pee_extract_h_impl(peeb_ws* ws, const void* marked_host, int n_u
     cudaStream_t streams[2] = {ws->stream, ws->stream2};
     const bool roles = ws->pipe_roles != 0;  // see peeb_pee_embed_h
     const std::vector<int> plan = chunk_plan(n_units, img, 65535);
+    const size_t pay_width = std::min<size_t>((size_t)payload_stride, align_up((size_t)max_bits_bytes(n_units, n_bits), 16));
     for (int u0 = 0, c = 0; c < (int)plan.size(); u0 += plan[c], ++c) {
         const int n = plan[c], slot = c & 1;
         cudaStream_t st_in = roles ? ws->stream : streams[slot], st = roles ? ws->stream2 : streams[slot];
@@ -413,12 +422,16 @@ static int peeb_pee_extract_h_impl(peeb_ws* ws, const void* marked_host, int n_u
         if (recovered_host)
             PEEB_CUDA(cudaMemcpy2DAsync((char*)recovered_host + (size_t)u0 * img, img, d1 + o_rec + (size_t)u0 * img_al, img_al,
                                         img, n, cudaMemcpyDeviceToHost, st_out));
-        if (payload_stride > 0)
+        if (pay_width > 0)  // the bytes that can hold payload bits; the rest of every row is zero filled on the host below
             PEEB_CUDA(cudaMemcpy2DAsync(payload_out_host + (size_t)u0 * payload_stride, (size_t)payload_stride,
-                                        d2 + (size_t)u0 * pstride, pstride, (size_t)payload_stride, n, cudaMemcpyDeviceToHost, st_out));
+                                        d2 + (size_t)u0 * pstride, pstride, pay_width, n, cudaMemcpyDeviceToHost, st_out));
         PEEB_CUDA(cudaMemcpyAsync(info_pin + (size_t)u0 * PEEB_INFO, (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO,
                                   (size_t)n * PEEB_INFO * 8, cudaMemcpyDeviceToHost, st_out));
     }
+    // zero padding of the rows past the copied bytes (while the copies are still in flight: other bytes)
+    if ((size_t)payload_stride > pay_width)
+        for (int u = 0; u < n_units; ++u)
+            memset(payload_out_host + (size_t)u * payload_stride + pay_width, 0, (size_t)payload_stride - pay_width);
     PEEB_CUDA(cudaStreamSynchronize(ws->stream));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream2));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream3));

@@ -17,6 +17,7 @@ struct PeeBatch {
     const int* T;                                      // device, per unit
     const unsigned* n_bits;                            // device, per unit
     long long* info;                                   // device, per unit x 8
+    unsigned long long* steps;                         // embed, optional: {warp-steps, at a border, redone} counters
     int n_units;
 };
 

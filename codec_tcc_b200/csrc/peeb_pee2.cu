@@ -42,12 +42,6 @@ __device__ unsigned long long g_phase[32];
 #define PHASE_INIT do {} while (0)
 #endif
 
-#ifdef PEEB_COUNT_REDO
-// development aid: warp-steps of the embed kernel that took the generic code [0] at a border column, [1] after the
-// fast code saw a value leave the range; [2] all warp-steps (peeb_debug_redo)
-__device__ unsigned long long g_redo[4];
-#endif
-
 struct Geom2 {
     int h, w, itemsize, maxval;
     int R, nb;              // band height, bands per unit
@@ -432,6 +426,9 @@ __device__ __forceinline__ KX make_kx(int T) { return KX{3 + 8 * T, 16 * T, 2 * 
 struct Stats2 {
     long long sse = 0;
     unsigned flagged = 0;
+    // warp-steps of the apply sweeps (the same in every lane of a warp): all of them, those that took the generic
+    // code because they touch a border column, and those redone after the fast code saw a value leave the range
+    unsigned steps = 0, steps_edge = 0, steps_redone = 0;
 };
 
 // ---- predicated tails (explicit PTX: the compiler turns these into select chains otherwise) ----
@@ -729,13 +726,8 @@ struct Apply2 {
             const uint4 A0 = A, B0 = B;
             generic<QA>(A0, A, prev, next, U, B0, ka, c, Wa, ssea, owna, lma);
             generic<1 - QA>(B0, B, prev, next, A0, D, kb, c, Wb, sseb, ownb, lma ? lma + lmwords : nullptr);
-#ifdef PEEB_COUNT_REDO
-            if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo[special ? 0 : 1], 1ull);
-#endif
+            if (special) ++st->steps_edge; else ++st->steps_redone;
         }
-#ifdef PEEB_COUNT_REDO
-        if ((threadIdx.x & 31) == 0) atomicAdd(&g_redo[2], 1ull);
-#endif
         // (steps past the end of the row run the generic code with T = 0 everywhere: they store back what they read,
         // into the padding of the shared rows)
         if (sta) sts128(pa, A);
@@ -744,6 +736,7 @@ struct Apply2 {
     __device__ __forceinline__ void end() {
         if (owna) st->sse += ssea;
         if (ownb) st->sse += sseb;
+        st->steps += g.cws;
     }
 };
 
@@ -937,6 +930,11 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         if ((threadIdx.x & 31) == 0) {
             if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(info + 6), (unsigned long long)sse);
             if (fl) atomicAdd(reinterpret_cast<unsigned long long*>(info + 5), (unsigned long long)fl);
+            if (bt.steps) {  // optional counters of the generic-code share (peeb_pee_step_counters)
+                atomicAdd(bt.steps, (unsigned long long)st.steps);
+                if (st.steps_edge) atomicAdd(bt.steps + 1, (unsigned long long)st.steps_edge);
+                if (st.steps_redone) atomicAdd(bt.steps + 2, (unsigned long long)st.steps_redone);
+            }
         }
     }
     PHASE_MARK(8);  // stats
@@ -1285,7 +1283,8 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
     const int forceT = getenv("PEEB_CTA_THREADS") ? atoi(getenv("PEEB_CTA_THREADS")) : 0;
     const int forceCW = getenv("PEEB_CELL_W") ? atoi(getenv("PEEB_CELL_W")) : 0;
     const int forceB = getenv("PEEB_CTA_MINB") ? atoi(getenv("PEEB_CTA_MINB")) : 0;
-    for (int R : {62, 58, 54, 30, 26, 14, 6, 2}) {
+    const bool old_model = getenv("PEEB_MODEL_R01") != nullptr;  // A/B runs against the first round's fit
+    for (int R : {62, 58, 54, 30, 26, 14, 12, 10, 6, 2}) {
         if (forceR && R != forceR) continue;
         Geom2 t = g;
         t.R = R;
@@ -1322,11 +1321,16 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
                 // the per-band latencies (24 warps per SM ~ saturation), with a penalty when the
                 // register budget per thread falls under what the row-pair step needs without spilling.
                 const double work = (double)rounds * nwarps * 32 * (cws + 2.5) * 2;  // + per-item set-up, ~2.5 steps
-                const double fixed = 4096.0;  // per-band latencies (tables, look-back, store) in lane-steps per pass
+                // per-band latencies (tables, look-back, store) in lane-steps per pass; the extract kernel has no
+                // look-back and no payload fetches, its bands can be smaller
+                const double fixed = (kind == 2 && !old_model) ? 2048.0 : 4096.0;
                 const double useful = (double)R * nsteps;
                 const double warps_sm = (double)cps * threads / 32.0;
-                // fewer, larger CTAs hide each other's barriers and latencies less well than three small ones
-                const double occ = std::pow(std::min(1.0, warps_sm / 24.0), 0.7) * (cps >= 3 ? 1.0 : 0.85);
+                // fewer, larger CTAs hide each other's barriers and latencies less well than three small ones; a single
+                // CTA per SM overlaps nothing of its load and store phases (3000-wide radiographs, extract: 6-row bands
+                // with three 256-thread CTAs per SM measured 1.12 ms against 1.33 ms for one 1024-thread CTA with 26 rows)
+                const double occ = std::pow(std::min(1.0, warps_sm / 24.0), 0.7) *
+                                   (cps >= 3 ? 1.0 : (cps == 1 && kind == 2 && !old_model) ? 0.6 : 0.85);
                 // the embed step spills under ~72 registers per thread; count and extract fit 64
                 const double regpen = (kind == 1 && 65536 / (cps * threads) < 72) ? 1.45 : 1.0;
                 const double score = (work + fixed) / useful / occ * regpen;
@@ -1424,6 +1428,7 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     bt.lm = lm; bt.lm_stride = lm_stride;
     bt.payload = payload; bt.payload_stride = payload_stride;
     bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    bt.steps = ws->step_counters_on ? (unsigned long long*)ws->step_counters.ptr : nullptr;
     rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
     if (rc) return rc;
     PEEB_CUDA(cudaGetLastError());

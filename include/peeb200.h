@@ -80,6 +80,10 @@ enum {
 int peeb_prof_enable(peeb_ws* ws, int on);  /* also resets the counters */
 int peeb_prof_get(peeb_ws* ws, int slot, double* total_ms, long long* launches);
 const char* peeb_prof_name(int slot);
+/* warp-steps of the PEE embed kernel {all, generic code at a border column, redone by the generic code after the
+ * fast code saw a value leave [0, maxval)}: on = 1 starts counting from zero, on = 0 stops; out3 (3 x uint64) gets
+ * the counts so far (may be NULL).  Synchronises the device. */
+int peeb_pee_step_counters(peeb_ws* ws, int on, uint64_t* out3);
 
 /* ---- a1-a4: distortion moments ---------------------------------------- *
  * One pass over two images gives every integer the metrics need
