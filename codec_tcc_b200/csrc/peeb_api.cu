@@ -109,7 +109,7 @@ int peeb_ws_destroy(peeb_ws* ws) {
         scratch_free(ws->ptables[i]);
         scratch_free(ws->ptables_h[i], true);
         scratch_free(ws->pbits[i]);
-        if (i == 0) scratch_free(ws->step_counters);
+        if (i == 0) { scratch_free(ws->step_counters); scratch_free(ws->hist); }
         if (ws->pev[i]) cudaEventDestroy(ws->pev[i]);
     }
     for (int i = 0; i < 4; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);

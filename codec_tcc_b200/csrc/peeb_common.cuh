@@ -61,6 +61,7 @@ struct peeb_ws {
                                      // host batch asynchronous even when the caller's info array is pageable)
     int use_bulk = 1;                // TMA bulk copies (PEEB_NO_BULK=1 disables)
     peeb::Scratch step_counters;     // device: 3 x uint64 counters of the PEE embed kernel's step kinds
+    peeb::Scratch hist;              // device: prediction-error histograms of a batch (threshold selection)
     int step_counters_on = 0;
     // profiling: accumulate per-kernel device time with events when enabled
     int prof_on = 0;

@@ -23,59 +23,6 @@ __global__ void pee_finalize_kernel(PeeBatch bt) {
     info[7] = ((long long)bt.n_bits[u] > info[2]) ? PEEB_E_CAPACITY : 0;
 }
 
-// ------------------------------------------------------------------ prediction-error histogram
-// Appendix A threshold selection: hist[u][c][e + tmax] over interior pixels not flagged
-// for expansion.  One pixel per thread; |e| < 512 goes through warp-aggregated
-// shared-memory atomics, the rare rest straight to global memory.
-constexpr int HWIN = 512;
-template <typename PixT>
-__global__ void __launch_bounds__(256) pee_hist_kernel(const unsigned char* __restrict__ src, long long src_stride,
-                                                       int h, int w, int maxval, int tmax,
-                                                       unsigned* __restrict__ hist) {
-    __shared__ unsigned sh[2][2 * HWIN];
-    for (int k = threadIdx.x; k < 4 * HWIN; k += blockDim.x) (&sh[0][0])[k] = 0;
-    __syncthreads();
-    const int unit = blockIdx.y;
-    const PixT* img = reinterpret_cast<const PixT*>(src + (long long)unit * src_stride);
-    unsigned* uh = hist + (long long)unit * 4 * tmax;
-    const long long npx = (long long)(h - 2) * (w - 2);
-    const int lane = threadIdx.x & 31;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long base = warp0 * 32; base < npx; base += nwarps * 32) {  // warp-uniform trip count
-        const long long t = base + lane;
-        bool ok = t < npx;
-        int e = 0, c = 0;
-        if (ok) {
-            const int i = 1 + (int)(t / (w - 2)), j = 1 + (int)(t % (w - 2));
-            const long long at = (long long)i * w + j;
-            const int x = img[at];
-            const int p = ((int)img[at - w] + (int)img[at + w] + (int)img[at - 1] + (int)img[at + 1]) >> 2;
-            e = x - p;
-            const int v = x + e;
-            c = (i + j) & 1;
-            ok = !((unsigned)v >= (unsigned)maxval) && e >= -tmax && e < tmax;
-        }
-        const bool in_win = ok && e >= -HWIN && e < HWIN;
-        const unsigned active = __ballot_sync(0xffffffffu, in_win);
-        if (in_win) {
-            const int key = c * 2 * HWIN + e + HWIN;
-            const unsigned peers = __match_any_sync(active, key);
-            if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&sh[0][0] + key, __popc(peers));
-        } else if (ok) {
-            atomicAdd(uh + (long long)c * 2 * tmax + e + tmax, 1u);
-        }
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < 4 * HWIN; k += blockDim.x) {
-        const unsigned v = (&sh[0][0])[k];
-        if (v) {
-            const int c = k / (2 * HWIN), e = k % (2 * HWIN) - HWIN;
-            if (e >= -tmax && e < tmax) atomicAdd(uh + (long long)c * 2 * tmax + e + tmax, v);
-        }
-    }
-}
-
 // ------------------------------------------------------------------ host side
 // upload T / n_bits (host arrays) into table set `slot` of the workspace; returns device pointers
 int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, const int64_t* n_bits,
@@ -86,7 +33,7 @@ int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, con
     if (rc) return rc;
     // the pinned mirror is reused by the next call: wait until the previous upload has been consumed
     PEEB_CUDA(cudaEventSynchronize(ws->pev[slot]));
-    rc = scratch_reserve(ws->ptables_h[slot], head, true);
+    rc = scratch_reserve(ws->ptables_h[slot], head + 256, true);  // (+ a pinned word behind the tables for callers)
     if (rc) return rc;
     int* hT = (int*)ws->ptables_h[slot].ptr;
     unsigned* hN = (unsigned*)(hT + n_units);
@@ -111,7 +58,7 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
                             int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
                             int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm,
                             int64_t lm_stride, int64_t* info, cudaStream_t st, int slot = 0) {
-    PEEB_REQUIRE(ws && src && T && n_bits && payload && info, "peeb_pee_embed_batch: null pointer");
+    PEEB_REQUIRE(ws && src && n_bits && payload && info, "peeb_pee_embed_batch: null pointer");  // T may be null: chosen on the device
     PEEB_REQUIRE(n_units >= 1, "peeb_pee_embed_batch: n_units must be >= 1");
     PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_embed_batch: payload must be 4-byte aligned");
     PEEB_REQUIRE(itemsize == 1 || itemsize == 2, "pee: itemsize must be 1 or 2");
@@ -122,6 +69,8 @@ static int embed_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, in
         return embed_batch_impl2(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, T, n_bits, payload, payload_stride,
                                  marked, marked_stride, lm, lm_stride, info, st, slot);
     int* dT; unsigned* dN; char* extra;
+    std::vector<int32_t> ones;
+    if (!T) { ones.assign((size_t)n_units, 1); T = ones.data(); }  // nothing can be embedded: T = 1 is as good as any
     int rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, 256, st, &dT, &dN, &extra);
     if (rc) return rc;
     PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
@@ -184,19 +133,7 @@ static int hist_batch_impl(peeb_ws* ws, const void* src, int64_t src_stride, int
     const int tmax = 1 << (bit_depth - 1);
     PEEB_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * 4 * (size_t)tmax * n_units, st));
     if (h < 3 || w < 3) return PEEB_OK;
-    const long long npx = (long long)(h - 2) * (w - 2);
-    long long blocks = (npx + 256 * 8 - 1) / (256 * 8);
-    long long cap = (long long)ws->sm_count * 8 / n_units;
-    if (cap < 1) cap = 1;
-    if (blocks > cap) blocks = cap;
-    dim3 grid((unsigned)blocks, (unsigned)n_units);
-    ProfScope p(ws, PEEB_K_PEE_HIST, st);
-    if (itemsize == 2)
-        pee_hist_kernel<unsigned short><<<grid, 256, 0, st>>>((const unsigned char*)src, src_stride, h, w, (1 << bit_depth) - 1, tmax, hist);
-    else
-        pee_hist_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)src, src_stride, h, w, (1 << bit_depth) - 1, tmax, hist);
-    PEEB_CUDA(cudaGetLastError());
-    return PEEB_OK;
+    return hist_batch_impl2(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, hist, st);
 }
 
 }  // namespace peeb
@@ -284,7 +221,7 @@ static std::vector<int> chunk_plan(int n_units, size_t unit_bytes, int cmax_limi
 static int peeb_pee_embed_h_impl(peeb_ws* ws, const void* src_host, int shared_flags, int n_units, int h, int w, int itemsize,
                      int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host,
                      int64_t payload_stride, void* marked_host, uint8_t* lm_host, int64_t* info_host) {
-    PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_embed_h: null pointer");
+    PEEB_REQUIRE(ws && src_host && n_bits && info_host, "peeb_pee_embed_h: null pointer");  // T may be null
     PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2), "peeb_pee_embed_h: bad sizes");
     PEEB_REQUIRE(payload_stride >= 0, "peeb_pee_embed_h: negative payload stride");
     PEEB_CUDA(cudaSetDevice(ws->device));
@@ -334,7 +271,7 @@ static int peeb_pee_embed_h_impl(peeb_ws* ws, const void* src_host, int shared_f
             PEEB_CUDA(cudaStreamWaitEvent(st, e, 0));
         }
         rc = embed_batch_impl(ws, shared_src ? d1 : d1 + (size_t)u0 * img_al, shared_src ? 0 : (int64_t)img_al, n, h, w,
-                              itemsize, bit_depth, T + u0, n_bits + u0, (const uint8_t*)(shared_pay ? d2 : d2 + (size_t)u0 * pstride),
+                              itemsize, bit_depth, T ? T + u0 : nullptr, n_bits + u0, (const uint8_t*)(shared_pay ? d2 : d2 + (size_t)u0 * pstride),
                               shared_pay ? 0 : (int64_t)pstride, marked_host ? d1 + o_marked + (size_t)u0 * img_al : nullptr, (int64_t)img_al,
                               lm_host ? (uint8_t*)(d2 + o_lm + (size_t)u0 * lm_al) : nullptr, (int64_t)lm_al,
                               (int64_t*)(d2 + o_info) + (size_t)u0 * PEEB_INFO, st, slot);

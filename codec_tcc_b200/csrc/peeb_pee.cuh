@@ -18,6 +18,7 @@ struct PeeBatch {
     const unsigned* n_bits;                            // device, per unit
     long long* info;                                   // device, per unit x 8
     unsigned long long* steps;                         // embed, optional: {warp-steps, at a border, redone} counters
+    const int* active;                                 // embed, optional: units with 0 are skipped (threshold search)
     int n_units;
 };
 
@@ -31,6 +32,9 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
                       int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
                       int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
                       int64_t* info, cudaStream_t st, int slot);
+// T = NULL: thresholds are chosen on the device (Appendix A: histogram estimate, then verify and increment)
+int hist_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                     int bit_depth, uint32_t* hist, cudaStream_t st);
 int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
                         int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm,
                         int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,

@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
+#include <vector>
 
 #include "peeb_common.cuh"
 #include "peeb_pee.cuh"
@@ -63,7 +64,8 @@ struct Geom2 {
 struct Smem2 {
     size_t img, lm, tab, misc, bar, tn0, tn1, tw0, tw1, stream, total;
 };
-__host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 embed, 2 extract*/) {
+constexpr int HWIN = 512;  // errors -HWIN <= e < HWIN of the threshold-selection histogram are counted in shared memory
+__host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 embed, 2 extract, 3 histogram*/) {
     Smem2 L{};
     size_t o = 0;
     L.img = o; o += align_up((size_t)16 + (size_t)(g.R + 5) * g.pitch + 192, 16);
@@ -71,6 +73,7 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 e
     if (kind == 2 || (kind == 1 && !g.lm_direct)) o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
     L.tab = o;
     if (kind == 1) o += (size_t)(g.R + 2) * g.tpitch;   // pass-1 carriers per (row, cell), one byte each
+    if (kind == 3) o += (size_t)4 * HWIN * sizeof(unsigned);  // [colour][e + HWIN]
     L.misc = o; o += 64 * sizeof(int);
     L.bar = o; o += 16;
     L.tn0 = L.tn1 = L.tw0 = L.tw1 = L.stream = o;
@@ -750,6 +753,136 @@ __device__ __forceinline__ int table_total(const Geom2& g, const unsigned char* 
     return sum;
 }
 
+// ------------------------------------------------------------------ threshold selection (Appendix A)
+// Prediction-error histogram of the ORIGINAL image, per colour, over interior pixels that are not flagged for
+// expansion (0 <= x + e < maxval) with -tmax <= e < tmax: hist[unit][colour][e + tmax].  Same band staging and
+// row-pair sweep as the count kernel (the errors of a lane's pixels come from the same IDP accumulations);
+// |e| < HWIN is counted in a shared window of the CTA, the rare rest straight in global memory.
+template <typename PixT>
+struct Hist2 {
+    using P = PixOps<PixT>;
+    const Geom2& g;
+    unsigned* sh;   // shared window of this colour: [e + HWIN]
+    unsigned* gh;   // the unit's global histogram of this colour: [e + tmax]
+    int tmax;
+    bool acta, actb, primed;
+    __device__ __forceinline__ void begin(int, int, bool a, bool b, bool, bool, int) { acta = a; actb = b; }
+    __device__ __forceinline__ bool item_special() const { return false; }
+    template <int Q, bool EDGE>
+    __device__ __forceinline__ void row(const uint4& M, unsigned prev, unsigned next, const uint4& U, const uint4& D,
+                                        int c, bool act) {
+        static_for<0, P::NS>([&](auto Sc) {
+            constexpr int S = decltype(Sc)::value;
+            bool ok = act;
+            if (EDGE) {
+                const int col = c + 2 * S + Q;
+                ok = ok && col >= 1 && col <= g.w - 2;
+            }
+            const int q = P::template qsum<Q, S>(M, prev, next, U, D, 3);  // 4e + r, 0 <= r <= 3
+            const int e = q >> 2;
+            ok = ok && (unsigned)P::template add4x<Q, S>(M, q) < 4u * (unsigned)g.maxval;  // 0 <= x + e < maxval
+            ok = ok && e >= -tmax && e < tmax;
+            if (ok) {
+                if (e >= -HWIN && e < HWIN) atomicAdd(sh + e + HWIN, 1u);
+                else atomicAdd(gh + e + tmax, 1u);
+            }
+        });
+    }
+    template <int QA>
+    __device__ __forceinline__ void step(int c, int, bool special, const uint4& U, uint4& A, uint4& B, const uint4& D,
+                                         unsigned prev, unsigned next, unsigned char*, unsigned char*) {
+        if (special) {
+            row<QA, true>(A, prev, next, U, B, c, acta);
+            row<1 - QA, true>(B, prev, next, A, D, c, actb);
+        } else {
+            row<QA, false>(A, prev, next, U, B, c, acta);
+            row<1 - QA, false>(B, prev, next, A, D, c, actb);
+        }
+    }
+    __device__ __forceinline__ void end() {}
+};
+
+template <typename PixT, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) pee2_hist_kernel(Geom2 g, const unsigned char* __restrict__ src,
+                                                             long long src_stride, int tmax, unsigned* __restrict__ hist) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem2 L = layout2(g, 3);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned* sh = reinterpret_cast<unsigned*>(smem_raw + L.tab);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    const int unit = blockIdx.x / g.nb, band = blockIdx.x % g.nb;
+    if (threadIdx.x == 0 && g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
+    for (int k = threadIdx.x; k < 4 * HWIN; k += blockDim.x) sh[k] = 0u;
+    __syncthreads();
+    const int r0 = band * g.R, r_first = r0 - 2;
+    const unsigned char* usrc = src + (long long)unit * src_stride;
+    load_rows2<PixT>(g, usrc, simg, r_first, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    unsigned* uh = hist + (long long)unit * 4 * tmax;
+    for (int colour = 0; colour < 2; ++colour) {
+        Hist2<PixT> body{g, sh + colour * 2 * HWIN, uh + (long long)colour * 2 * tmax, tmax};
+        sweep2_colour<PixT>(g, simg, r_first, colour, own_lo, own_hi, 0, body);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4 * HWIN; k += blockDim.x) {
+        const unsigned v = sh[k];
+        const int colour = k / (2 * HWIN), e = k % (2 * HWIN) - HWIN;
+        if (v && e >= -tmax && e < tmax) atomicAdd(uh + (long long)colour * 2 * tmax + e + tmax, v);
+    }
+}
+
+// One CTA per unit: T0 = min{T >= 1 : sum_c sum_{-T <= e < T} hist_c[e] >= n_bits}, tmax + 1 if there is none.
+__global__ void __launch_bounds__(256) pee2_pick_T_kernel(const unsigned* __restrict__ hist, int tmax,
+                                                          const unsigned* __restrict__ n_bits, int* __restrict__ T,
+                                                          int* __restrict__ active) {
+    const int unit = blockIdx.x;
+    const unsigned* h0 = hist + (long long)unit * 4 * tmax;
+    const unsigned* h1 = h0 + 2 * tmax;
+    const unsigned long long want = n_bits[unit];
+    __shared__ unsigned long long s_warp[8];
+    __shared__ int s_found;
+    if (threadIdx.x == 0) s_found = tmax + 1;
+    __syncthreads();
+    unsigned long long before = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 1; t0 <= tmax; t0 += 256) {
+        const int t = t0 + (int)threadIdx.x;  // this thread adds the bins that T = t brings in: e = -t and e = t - 1
+        unsigned long long v = 0;
+        if (t <= tmax) v = (unsigned long long)h0[tmax - t] + h0[tmax + t - 1] + h1[tmax - t] + h1[tmax + t - 1];
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned long long wbefore = 0, total = 0;
+        for (int k = 0; k < 8; ++k) { if (k < warp) wbefore += s_warp[k]; total += s_warp[k]; }
+        const unsigned long long est = before + wbefore + incl;
+        if (t <= tmax && est >= want) atomicMin(&s_found, t);
+        __syncthreads();
+        if (s_found <= tmax) break;
+        before += total;
+    }
+    // no T whose estimate holds the payload (Appendix A: an error, even if the real capacity at tmax turned out larger
+    // than its estimate): the unit is embedded once at tmax, zero padded, and keeps the capacity status (active = 2)
+    if (threadIdx.x == 0) { T[unit] = min(s_found, tmax); active[unit] = s_found <= tmax ? 1 : 2; }
+}
+
+// After an embed with device-side thresholds: units whose payload did not fit (status PEEB_E_CAPACITY) and whose
+// T can still grow get T + 1 and stay active for the next round; everything else is done.  remaining: units to redo.
+__global__ void pee2_retry_kernel(int n_units, int tmax, long long* __restrict__ info, int* __restrict__ T,
+                                  int* __restrict__ active, int* __restrict__ remaining) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    int again = 0;
+    if (active[u] == 2) info[(long long)u * PEEB_INFO + 7] = PEEB_E_CAPACITY;
+    else if (active[u] && info[(long long)u * PEEB_INFO + 7] == PEEB_E_CAPACITY && T[u] < tmax) { T[u] += 1; again = 1; }
+    active[u] = again;
+    if (again) atomicAdd(remaining, 1);
+}
+
 // ------------------------------------------------------------------ K_A: pass-0 counts
 // rowcnt: one byte per (row, cell) of every unit, rows `tpitch` bytes apart.
 template <typename PixT, int NT, int MINB>
@@ -774,8 +907,10 @@ __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch 
         status[blockIdx.x] = 0ull;
         if (blockIdx.x == 0) *ticket = 0u;
     }
-    if (band == 0 && threadIdx.x < PEEB_INFO) bt.info[(long long)unit * PEEB_INFO + threadIdx.x] = 0;
+    const bool skip = bt.active && !bt.active[unit];  // threshold search: this unit is done
+    if (!skip && band == 0 && threadIdx.x < PEEB_INFO) bt.info[(long long)unit * PEEB_INFO + threadIdx.x] = 0;
     wait_rows2(g, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
+    if (skip) return;
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     {   // bytes past ncol of this band's table rows are summed with the rest by the embed kernel: they are 0
         const int padn = g.tpitch - g.ncol;
@@ -826,6 +961,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     // look-back finds an inclusive prefix at once instead of waiting on bands that run beside it.
     const int tk = misc[40];
     const int band = tk / bt.n_units, unit = tk - band * bt.n_units;
+    if (bt.active && !bt.active[unit]) return;  // threshold search: this unit is done
     const int r0 = band * g.R, r_first = r0 - 2;
     const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
     const int T = bt.T[unit];
@@ -1349,7 +1485,7 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
     g.R = (h + g.nb - 1) / g.nb;  // same number of bands, rows spread evenly
     g.bandwords = (g.R * ((w + 1) / 2) + 31) / 32 + 2;
     if (getenv("PEEB_DEBUG_GEOM")) {
-        static int printed[3] = {0, 0, 0};
+        static int printed[4] = {0, 0, 0, 0};
         if (printed[kind]++ < 1)
             fprintf(stderr, "[peeb] %dx%dx%d kind %d: R=%d rpw=%d CW=%d ncol=%d threads=%d minb=%d smem=%zu score=%.3f\n", h, w, itemsize,
                     kind, g.R, g.rpw, g.CW, g.ncol, g.threads, g.minb, layout2(g, kind).total, best);
@@ -1401,6 +1537,34 @@ static int launch_extract2(peeb_ws* ws, const Geom2& g, const PeeBatch& bt, long
     (g.itemsize == 2 ? PEEB_DISPATCH2_T(FN, unsigned short, __VA_ARGS__) : PEEB_DISPATCH2_T(FN, unsigned char, __VA_ARGS__))
 #endif
 
+template <typename PixT, int NT, int MINB>
+static int launch_hist2(peeb_ws* ws, const Geom2& g, long long nbands, const unsigned char* src, long long src_stride,
+                        int tmax, unsigned* hist, cudaStream_t st) {
+    const size_t smem = layout2(g, 3).total;
+    int rc = set_smem2(pee2_hist_kernel<PixT, NT, MINB>, smem); if (rc) return rc;
+    ProfScope p(ws, PEEB_K_PEE_HIST, st);
+    pee2_hist_kernel<PixT, NT, MINB><<<(unsigned)nbands, NT, smem, st>>>(g, src, src_stride, tmax, hist);
+    return PEEB_OK;
+}
+
+int hist_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
+                     int bit_depth, uint32_t* hist, cudaStream_t st) {
+    Geom2 g;
+    int rc = make_geom2(ws, h, w, itemsize, bit_depth, 3, false, g);
+    if (rc) return rc;
+    if (g.bulk && ((((uintptr_t)src) | (uint64_t)src_stride) & 15)) g.bulk = 0;
+    const long long nbands = (long long)n_units * g.nb;
+    PEEB_REQUIRE(nbands < (1ll << 30), "peeb_pee_hist_batch: too many bands");
+    rc = PEEB_DISPATCH2(launch_hist2, ws, g, nbands, (const unsigned char*)src, (long long)src_stride, 1 << (bit_depth - 1), hist, st);
+    if (rc) return rc;
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+// T == nullptr: the thresholds are chosen on the device (SURVEY Appendix A "threshold selection"): error histogram of
+// every unit -> smallest T whose estimate holds the payload -> embed -> units whose real capacity falls short get
+// T + 1 and are embedded again (only they), until every unit fits or has reached tmax.  The host only reads one
+// counter per round.  The chosen T comes back in info[u][0].
 int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
                       int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
                       int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
@@ -1412,16 +1576,23 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
         g.bulk = 0;  // unaligned user buffers: plain copies
     const long long nbands = (long long)n_units * g.nb;
     PEEB_REQUIRE(nbands < (1ll << 30), "peeb_pee_embed_batch: too many bands");
+    const bool auto_T = T == nullptr;
+    PEEB_REQUIRE(!auto_T || src_stride != 0, "peeb_pee_embed_batch: threshold selection needs one cover per unit");
     int* dT; unsigned* dN; char* extra;
     const size_t cnt_bytes = align_up((size_t)nbands * sizeof(int), 256);
     const size_t st_bytes = align_up((size_t)nbands * sizeof(unsigned long long), 256);
     const size_t rc_bytes = align_up((size_t)n_units * h * g.tpitch, 256);
-    rc = upload_unit_tables(ws, slot, n_units, T, n_bits, bit_depth, cnt_bytes + st_bytes + 256 + rc_bytes, st, &dT, &dN, &extra);
+    const size_t act_bytes = auto_T ? align_up((size_t)(n_units + 1) * sizeof(int), 256) : 0;
+    std::vector<int32_t> ones;
+    if (auto_T) ones.assign((size_t)n_units, 1);
+    rc = upload_unit_tables(ws, slot, n_units, auto_T ? ones.data() : T, n_bits, bit_depth,
+                            cnt_bytes + st_bytes + 256 + rc_bytes + act_bytes, st, &dT, &dN, &extra);
     if (rc) return rc;
     int* band_cnt = (int*)extra;
     unsigned long long* status = (unsigned long long*)(extra + cnt_bytes);
     unsigned* ticket = (unsigned*)(extra + cnt_bytes + st_bytes);
     unsigned char* rowcnt = (unsigned char*)(extra + cnt_bytes + st_bytes + 256);
+    int* active = auto_T ? (int*)(extra + cnt_bytes + st_bytes + 256 + rc_bytes) : nullptr;
     PeeBatch bt{};
     bt.src = (const unsigned char*)src; bt.src_stride = src_stride;
     bt.dst = (unsigned char*)marked; bt.dst_stride = marked_stride;
@@ -1429,8 +1600,32 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     bt.payload = payload; bt.payload_stride = payload_stride;
     bt.payload_out = nullptr; bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
     bt.steps = ws->step_counters_on ? (unsigned long long*)ws->step_counters.ptr : nullptr;
-    rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
+    bt.active = active;
+    if (!auto_T) {
+        rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
+        if (rc) return rc;
+        PEEB_CUDA(cudaGetLastError());
+        return PEEB_OK;
+    }
+    const int tmax = 1 << (bit_depth - 1);
+    rc = scratch_reserve(ws->hist, (size_t)n_units * 4 * tmax * sizeof(unsigned));
     if (rc) return rc;
+    unsigned* hist = (unsigned*)ws->hist.ptr;
+    PEEB_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_units * 4 * tmax * sizeof(unsigned), st));
+    rc = hist_batch_impl2(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, hist, st);
+    if (rc) return rc;
+    pee2_pick_T_kernel<<<n_units, 256, 0, st>>>(hist, tmax, dN, dT, active);  // every unit takes part in round one
+    int* remaining_h = (int*)((char*)ws->ptables_h[slot].ptr + align_up((size_t)n_units * 8, 256));  // pinned, behind the tables
+    int* remaining = active + n_units;
+    for (int round = 0; round <= tmax; ++round) {
+        rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
+        if (rc) return rc;
+        PEEB_CUDA(cudaMemsetAsync(remaining, 0, sizeof(int), st));
+        pee2_retry_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(n_units, tmax, (long long*)info, dT, active, remaining);
+        PEEB_CUDA(cudaMemcpyAsync(remaining_h, remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PEEB_CUDA(cudaStreamSynchronize(st));
+        if (*remaining_h == 0) break;
+    }
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }

@@ -36,7 +36,8 @@ def payload_stride(max_bits: int) -> int:
 def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None, info=None, shared_cover=False,
                      predictor="rhombus"):
     """imgs (n,h,w) [or (h,w) with shared_cover]; payloads (n, stride) uint8 with
-    stride >= payload_stride(max n_bits); n_bits / T host int arrays.
+    stride >= payload_stride(max n_bits); n_bits / T host int arrays; T=None: the smallest threshold that holds
+    each unit's payload is chosen on the device (see info[:, 0]; the call then synchronises the stream).
     -> (marked, lm, info) tensors; enqueued, not synchronised."""
     dev = imgs.device
     item = _pixels(imgs, "imgs")
@@ -50,7 +51,9 @@ def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None,
             raise ValueError("n_bits must have one entry per image")
         _, h, w = imgs.shape
         src_stride = h * w * item
-    Ts = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.int32), (n,)))
+    if T is None and (shared_cover or predictor != "rhombus"):
+        raise ValueError("T=None needs one cover per unit and the rhombus predictor")
+    Ts = None if T is None else np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.int32), (n,)))
     if payloads.dtype != torch.uint8 or payloads.dim() != 2 or payloads.shape[0] != n:
         raise ValueError("payloads must be (n, stride) uint8")
     if payloads.shape[1] % 4 or payloads.shape[1] < _cabi.payload_bytes(int(nb.max()) if n else 0):
@@ -67,7 +70,8 @@ def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None,
         raise ValueError("shared_cover is not supported with predictor='med'")
     fn = lib().peeb_pee_med_embed_batch if predictor == "med" else lib().peeb_pee_embed_batch
     check(fn(
-        ws.handle, _raw(imgs, "imgs"), src_stride, n, h, w, item, int(bit_depth), Ts.ctypes.data, nb.ctypes.data,
+        ws.handle, _raw(imgs, "imgs"), src_stride, n, h, w, item, int(bit_depth),
+        Ts.ctypes.data if Ts is not None else None, nb.ctypes.data,
         _raw(payloads, "payloads"), payloads.shape[1], _raw(marked, "marked") if marked is not False else None,
         h * w * item, _raw(lm, "lm") if lm is not False else None, h * lmw, _raw(info, "info"), _stream(dev)),
         "peeb_pee_embed_batch")

@@ -97,7 +97,8 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
               every unit then embeds into the same cover (threshold sweep)
     payloads  (n, stride) uint8, packed MSB first; row u holds unit u's bits
               (one row of (1, stride) or (stride,) with ``shared_payload=True``)
-    n_bits    (n,) ints; T scalar or (n,) ints
+    n_bits    (n,) ints; T scalar or (n,) ints, or None: every unit gets the smallest threshold that holds its
+              payload (histogram estimate, then verify-and-increment, all on the device); see info[:, 0]
     -> (marked (n,h,w) or None, lm_packed (n,h,ceil(w/8)) or None, info (n, 8) int64)
     ``info[:, 7]`` is 0 or PEEB_E_CAPACITY (-2): nothing is raised here, the
     embed of an oversize payload is the zero-padded embed of what fits.
@@ -119,9 +120,13 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
     nb = np.ascontiguousarray(n_bits, dtype=np.int64).reshape(-1)
     if nb.size != n:
         raise ValueError("n_bits must have one entry per image")
-    Ts = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.int32), (n,)))
-    for t in np.unique(Ts):
-        _check_T(t, bd)
+    Ts = None  # T=None: chosen per unit on the device (Appendix A threshold selection), reported in info[:, 0]
+    if T is not None:
+        Ts = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.int32), (n,)))
+        for t in np.unique(Ts):
+            _check_T(t, bd)
+    elif shared_cover or predictor != "rhombus":
+        raise ValueError("T=None needs one cover per unit and the rhombus predictor")
     payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
     if shared_payload:
         payloads = payloads.reshape(1, -1)
@@ -150,7 +155,7 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
                                          ptr(info)), "peeb_pee_med_embed_h")
         return marked, lm, info
     check(lib().peeb_pee_embed_h(ws.handle, ptr(imgs), flags, n, h, w, imgs.dtype.itemsize, bd,
-                                 ptr(Ts), ptr(nb), ptr(payloads) if payloads.size else None, payloads.shape[1],
+                                 ptr(Ts) if Ts is not None else None, ptr(nb), ptr(payloads) if payloads.size else None, payloads.shape[1],
                                  ptr(marked), ptr(lm), ptr(info)), "peeb_pee_embed_h")
     return marked, lm, info
 
@@ -244,11 +249,14 @@ def pee_embed(img, payload, T=None, bit_depth=None, n_bits=None, device=None, pr
         marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], t, bd, device=device, predictor=predictor)
         return marked[0], lm[0], info[0]
 
-    if T is None:
-        # the histogram estimate belongs to the rhombus predictor; the causal one starts its search at T = 1
-        T = estimate_threshold(pee_histogram(img, bd, device), n_bits) if predictor == "rhombus" else 1
-        if T is None:
+    if T is None and predictor == "rhombus":
+        # threshold selection runs on the device (histogram estimate, verify and increment)
+        marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], None, bd, device=device)
+        marked, lm, info = marked[0], lm[0], info[0]
+        if info[7] == PEEB_E_CAPACITY:
             raise ValueError("payload exceeds capacity at every threshold")
+    elif T is None:
+        T = 1  # the causal predictor has no histogram estimate: the search starts at T = 1
         while True:
             marked, lm, info = run(T)
             if info[7] == 0:

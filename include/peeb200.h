@@ -197,7 +197,10 @@ int peeb_lsb_extract_h(peeb_ws* ws, const void* stego_host, int64_t n, int items
  * Not in the reference; specified in SURVEY.md Appendix A.
  * Units (images) are independent; a batch is n_units images of h x w with byte
  * strides between them.  src_stride may be 0 (every unit embeds into the same
- * cover -- the threshold sweep).  T[u], n_bits[u] are HOST arrays.
+ * cover -- the threshold sweep).  T[u], n_bits[u] are HOST arrays.  T may be NULL in the embed calls: every unit
+ * then gets the smallest threshold that holds its payload, chosen on the device (error histogram of the unit ->
+ * estimate -> embed -> T + 1 for the units that fall short, only those are embedded again); it comes back in
+ * info[u][0], a unit that fits at no threshold up to 2^(bit_depth-1) keeps status PEEB_E_CAPACITY.
  * info: n_units x 8 int64 = {T, n_bits, capacity, cap0, cap1, n_flagged, sse, status}
  * with status 0 or PEEB_E_CAPACITY (the embed is still the zero-padded embed of
  * the first `capacity` bits, which is what a sweep wants).  The function's own

@@ -165,6 +165,47 @@ def test_batch_matches_oracle_per_unit():
     assert np.array_equal(xinfo[:, 2], info[:, 2])
 
 
+def test_batch_auto_threshold_matches_oracle_per_unit():
+    """T=None for a batch: every unit's threshold is chosen on the device (histogram estimate, then only the units that
+    fall short are embedded again at T + 1) -- same T, marked image, location map and statistics as the oracle's
+    per-image search; a unit no threshold can hold keeps the capacity status without disturbing the others."""
+    for maxval, bd, gen in ((4095, 12, synth_batch), (255, 8, synth_batch), (65535, 16, None)):
+        n, h, w = 9, 150, 272
+        if gen is None:
+            imgs = np.stack([synth_saturated(h, w, maxval, 60 + u) for u in range(n)])
+        else:
+            imgs = gen(n, h, w, maxval, 50)
+        caps = [PC.embed(imgs[u], np.zeros(h * w // 8 + 8, np.uint8), 0, 1 << (bd - 1), bd)[2]["capacity"] for u in range(n)]
+        fr = [0.0, 0.02, 0.2, 0.45, 0.6, 0.75, 0.9, 0.97, 2.0]
+        nb = np.array([int(caps[u] * fr[u]) for u in range(n)], np.int64)
+        stride = int(((nb + 7) // 8).max()) + 4
+        stride += -stride % 4
+        pays = np.zeros((n, stride), np.uint8)
+        for u in range(n):
+            p = random_payload(int(nb[u]), 300 + u)
+            pays[u, :p.size] = p
+        marked, lm, info = pee.pee_embed_batch(imgs, pays, nb, None, bd)
+        fits = 0
+        for u in range(n):
+            try:
+                m0, lm0, i0 = PN.pee_embed(imgs[u], pays[u], None, bd, n_bits=int(nb[u]))
+            except ValueError:
+                assert int(info[u, 7]) == pee.PEEB_E_CAPACITY, u
+                continue
+            fits += 1
+            assert int(info[u, 7]) == 0, (u, info[u])
+            assert [int(v) for v in info[u, :7]] == [i0[k] for k in ("T", "n_bits", "capacity", "cap0", "cap1", "n_flagged", "sse")], u
+            assert np.array_equal(marked[u], m0) and np.array_equal(lm[u], lm0), u
+        assert fits >= 7
+        ok = info[:, 7] == 0
+        out, rec, xinfo = pee.pee_extract_batch(marked[ok], lm[ok], info[ok, 0].astype(np.int32), nb[ok], bd)
+        assert np.array_equal(rec, imgs[ok]) and (xinfo[:, 7] == 0).all()
+        for k, u in enumerate(np.flatnonzero(ok)):
+            assert np.array_equal(np.unpackbits(out[k])[:nb[u]], np.unpackbits(pays[u])[:nb[u]]), u
+    with pytest.raises(ValueError):
+        pee.pee_embed_batch(imgs[0], pays, nb, None, bd, shared_cover=True)
+
+
 def test_large_batch_of_small_images_matches_oracle_per_unit():
     """Many units with several bands each: the payload assembly takes several pieces per block, the units'
     summaries come from their last bands, the output rows are cleared by the kernel (dirty buffers passed in)."""
