@@ -23,7 +23,7 @@ MOMENTS = 12
 INFO = 8
 INFO_KEYS = ("T", "n_bits", "capacity", "cap0", "cap1", "n_flagged", "sse", "status")
 
-_vp, _i32, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+_vp, _i32, _i64, _sz, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); every symbol include/peeb200.h declares
 SIGNATURES = {
@@ -80,6 +80,13 @@ SIGNATURES = {
                                           _vp, _i64, _vp, _vp]),
     "peeb_pee_med_embed_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "peeb_pee_med_extract_h": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "peeb_moments_f64": (_i32, [_vp, _vp, _vp, _i64, _i32, _f64, _f64, _f64, _f64, _f64, _f64, _vp, _vp]),
+    "peeb_moments_f64_h": (_i32, [_vp, _vp, _vp, _i64, _vp]),
+    "peeb_bitmap_blob_bound": (_sz, [_i64]),
+    "peeb_bitmap_encode": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _vp, _vp]),
+    "peeb_bitmap_decode": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp]),
+    "peeb_bitmap_encode_h": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "peeb_bitmap_decode_h": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32]),
 }
 
 _lib = None
@@ -171,7 +178,7 @@ class Workspace:
 
     def prof_report(self):
         out = {}
-        for slot in range(16):
+        for slot in range(20):
             ms, calls = C.c_double(0), C.c_longlong(0)
             check(lib().peeb_prof_get(self.handle, slot, C.byref(ms), C.byref(calls)))
             if calls.value:

@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 LIBDIR = os.path.join(PKG, "lib")
 LIBPATH = os.path.join(LIBDIR, "libpeeb200.so")
-SOURCES = ["peeb_api.cu", "peeb_moments.cu", "peeb_lsb.cu", "peeb_pee.cu", "peeb_pee2.cu", "peeb_pee_med.cu"]
+SOURCES = ["peeb_api.cu", "peeb_moments.cu", "peeb_lsb.cu", "peeb_pee.cu", "peeb_pee2.cu", "peeb_pee_med.cu", "peeb_bitcode.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

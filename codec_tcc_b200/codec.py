@@ -143,29 +143,55 @@ def _plane_information(hist, ones, total, bit, nbins):
 
 
 def calculate_mutual_information(bit_plane, image_array):
-    """src/codec.py:504-559 for a plane that is one of the image's own bit
-    planes (how the reference calls it, :571,:588).  Which bit it is gets
-    identified on the device: the plane's population count narrows the
-    candidates, an exact SSE of zero against the unpacked candidate confirms."""
+    """src/codec.py:504-559: I(X;Y) = H(X) + H(Y) - H(X,Y) of a plane X and the image Y.
+
+    A plane that is one of the image's own bit planes (how the reference calls it, :571,:588) needs no joint
+    histogram: the image histogram and the plane's population count give all three entropies.  Which bit it is
+    gets identified on the device: the population count narrows the candidates, an exact SSE of zero against
+    the unpacked candidate confirms.  Any other plane (the reference accepts whatever ``np.bincount`` does) takes
+    one more device histogram per distinct plane value: the image with the pixels outside that value zeroed,
+    bin 0 corrected by their number -- the joint counts in ``np.bincount``'s order (index = x * (max + 1) + y,
+    src/codec.py:546-548)."""
     img = _cabi.as_image(image_array, "image_array")
     plane = np.ascontiguousarray(np.asarray(bit_plane))
     if plane.shape != img.shape:
         raise ValueError("bit_plane and image_array must have the same shape")
-    if plane.dtype != img.dtype:
-        plane = plane.astype(img.dtype)
+    if plane.dtype not in (np.uint8, np.uint16):
+        if not np.issubdtype(plane.dtype, np.integer) and plane.dtype != np.bool_:
+            raise TypeError(f"Cannot cast array data from {plane.dtype} to dtype('int64') according to the rule 'safe'")
+        if plane.size and (plane.min() < 0 or plane.max() > 65535):
+            raise ValueError("bit_plane values must be in 0..65535")
+        plane = plane.astype(np.uint16)
+    if img.size == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")
     hist, ones = _image_histogram(img)
     nbins = hist.size
+    total = img.size
     from .mse import image_moments
     pm = image_moments(plane, plane)
-    if pm["max_a"] > 1:
-        raise NotImplementedError("bit_plane must hold 0/1 values")
-    for bit in range(8 * img.dtype.itemsize):
-        if int(ones[bit]) != pm["sum_a"]:
-            continue
-        cand = extract_bit_plane(img, bit)
-        if image_moments(cand, plane)["sse"] == 0:
-            return _plane_information(hist, int(ones[bit]), img.size, bit, nbins)
-    raise NotImplementedError("bit_plane is not a bit-plane of image_array; only that case is on the device path")
+    if pm["max_a"] <= 1:
+        cmp_plane = plane if plane.dtype == img.dtype else plane.astype(img.dtype)
+        for bit in range(8 * img.dtype.itemsize):
+            if int(ones[bit]) != pm["sum_a"]:
+                continue
+            cand = extract_bit_plane(img, bit)
+            if image_moments(cand, cmp_plane)["sse"] == 0:
+                return _plane_information(hist, int(ones[bit]), total, bit, nbins)
+    # general plane: counts of its values, then one masked image histogram per value
+    xhist, _ = _image_histogram(plane)
+    xvals = np.flatnonzero(xhist)
+    if xvals.size <= 1 or np.count_nonzero(hist) <= 1:
+        return 0.0  # src/codec.py:520-523
+    h_x = _entropy_from_counts(xhist, total)
+    h_y = _entropy_from_counts(hist, total)
+    joint = []
+    for v in xvals:
+        sel = plane == v
+        masked, _ = _image_histogram(np.where(sel, img, img.dtype.type(0)))
+        masked[0] -= total - int(xhist[v])
+        joint.append(masked)
+    h_xy = _entropy_from_counts(np.concatenate(joint), total)
+    return max(0.0, h_x + h_y - h_xy)
 
 
 def extract_bit_plane(image, bit, device=None):

@@ -5,8 +5,13 @@ with the same arguments, return values and error behaviour -- including the 16-b
 make ``struct.pack`` raise for segments longer than 65 535 bits or sides over 65 535 pixels
 (SURVEY.md F3.4).  Plus the two blob steps ``main()`` / ``decode_bin`` do around them:
 ``zlib.compress(np.stack(bitmaps).tobytes())`` (:888-889) and ``np.split(np.frombuffer(
-zlib.decompress(...)), s)`` (:820-821).  Host-only code; the stego image codecs (cjxl / gdcmconv,
-src/codec.py:108-209) stay out of scope: the compressed image is passed in as bytes.
+zlib.decompress(...)), s)`` (:820-821).  The container itself is host code; the stego image codecs
+(cjxl / gdcmconv, src/codec.py:108-209) stay out of scope: the compressed image is passed in as bytes.
+
+The blob steps also come in a device form, ``coding="pbr"``: the bitmaps are bit packed and their zero
+runs removed by CUDA kernels (format "PBR1", ``csrc/peeb_bitcode.cu``), instead of one byte per pixel
+going through zlib on the host.  ``unpack_bitmaps`` recognises either blob; the reference's own
+``decode_bin`` only reads the zlib form, which stays the default.
 """
 from __future__ import annotations
 
@@ -14,7 +19,11 @@ import os
 import struct
 import zlib
 
+import ctypes as _C
+
 import numpy as np
+
+from ._cabi import check, lib, ptr, workspace
 
 CODEC_IDS = {"png": 1, "j2k": 2, "jls": 3, "jxl": 4}          # src/codec.py:616
 CODEC_NAMES = {v: k for k, v in CODEC_IDS.items()}           # src/codec.py:693
@@ -71,11 +80,55 @@ def parse_bin_file(filepath):
     return metadata, bitmaps_data, stego_image_data
 
 
-def pack_bitmaps(bitmaps):
-    """``zlib.compress(np.stack(bitmaps).tobytes())`` (src/codec.py:888-889)."""
-    return zlib.compress(np.stack([np.asarray(b) for b in bitmaps]).tobytes())
+PBR_MAGIC = b"PBR1"
 
 
-def unpack_bitmaps(bitmaps_data, s):
-    """``np.split(np.frombuffer(zlib.decompress(blob), np.uint8), s)`` (src/codec.py:820-821): flat uint8 arrays."""
+def encode_bitmap(elements, packed=False, n=None, device=None) -> bytes:
+    """Side bitmap -> "PBR1" blob on the GPU.  ``elements``: uint8 array (non-zero = 1, flattened in C
+    order), or with ``packed`` np.packbits bytes holding ``n`` elements (a PEE location map)."""
+    a = np.ascontiguousarray(elements)
+    if a.dtype != np.uint8:
+        raise ValueError("bitmaps must be uint8 arrays")
+    a = a.reshape(-1)
+    if packed:
+        n = a.size * 8 if n is None else int(n)
+        if n < 0 or (n + 7) // 8 != a.size:
+            raise ValueError("n does not match the packed array's length")
+    else:
+        n = a.size
+    cap = int(lib().peeb_bitmap_blob_bound(n))
+    blob = np.empty(cap, np.uint8)
+    got = _C.c_int64(0)
+    check(lib().peeb_bitmap_encode_h(workspace(device).handle, ptr(a) if a.size else None, n, 1 if packed else 0,
+                                     ptr(blob), cap, _C.byref(got)), "peeb_bitmap_encode_h")
+    return blob[:got.value].tobytes()
+
+
+def decode_bitmap(blob, n, packed=False, device=None) -> np.ndarray:
+    """"PBR1" blob -> ``n`` uint8 values 0/1 (or the ceil(n/8) np.packbits bytes with ``packed``)."""
+    b = np.frombuffer(bytes(blob), np.uint8)
+    n = int(n)
+    out = np.empty((n + 7) // 8 if packed else n, np.uint8)
+    check(lib().peeb_bitmap_decode_h(workspace(device).handle, ptr(b) if b.size else None, b.size,
+                                     ptr(out) if out.size else None, n, 1 if packed else 0), "peeb_bitmap_decode_h")
+    return out
+
+
+def pack_bitmaps(bitmaps, coding="zlib", device=None):
+    """``zlib.compress(np.stack(bitmaps).tobytes())`` (src/codec.py:888-889); ``coding="pbr"``: the same
+    stack of bitmaps bit packed with its zero runs removed, on the GPU."""
+    stack = np.stack([np.asarray(b) for b in bitmaps])
+    if coding == "zlib":
+        return zlib.compress(stack.tobytes())
+    if coding != "pbr":
+        raise ValueError("coding must be 'zlib' or 'pbr'")
+    return encode_bitmap(stack.astype(np.uint8, copy=False), device=device)
+
+
+def unpack_bitmaps(bitmaps_data, s, device=None):
+    """``np.split(np.frombuffer(zlib.decompress(blob), np.uint8), s)`` (src/codec.py:820-821): flat uint8
+    arrays; a "PBR1" blob is expanded on the GPU to the same arrays."""
+    if bytes(bitmaps_data[:4]) == PBR_MAGIC:
+        n = int.from_bytes(bytes(bitmaps_data[8:16]), "little")
+        return np.split(decode_bitmap(bitmaps_data, n, device=device), s)
     return np.split(np.frombuffer(zlib.decompress(bitmaps_data), dtype=np.uint8), s)

@@ -214,7 +214,8 @@ int peeb_pee_step_counters(peeb_ws* ws, int on, uint64_t* out3) {
 const char* peeb_prof_name(int slot) {
     static const char* names[PEEB_PROF_SLOTS] = {
         "moments", "hist_planes", "tile_moments", "lsb_embed", "planes_pack", "planes_unpack", "compact_bits",
-        "pee_count", "pee_embed", "pee_extract", "pee_gather", "pee_hist", "pee_finalize", "lsb_recover", "lsb_extract", ""};
+        "pee_count", "pee_embed", "pee_extract", "pee_gather", "pee_hist", "pee_finalize", "lsb_recover", "lsb_extract",
+        "bitmap_encode", "bitmap_decode", "", "", ""};
     return (slot >= 0 && slot < PEEB_PROF_SLOTS) ? names[slot] : "";
 }
 

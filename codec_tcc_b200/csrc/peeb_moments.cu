@@ -1,6 +1,9 @@
 // K5: fused integer moment reduction for MSE / PSNR / global SSIM / difference
 // statistics (rows a1-a4).  One streaming pass over both images, 128-bit loads,
 // exact 64-bit integer sums; HBM bound (2*itemsize algorithmic bytes per pixel).
+#include <algorithm>
+#include <cmath>
+
 #include "peeb_common.cuh"
 
 namespace peeb {
@@ -214,6 +217,133 @@ static int moments_host(peeb_ws* ws, const void* a_host, const void* b_host, int
     if (rc) return rc;
     PEEB_CUDA(cudaMemcpyAsync(out_host, dout, sizeof(int64_t) * PEEB_MOMENTS, cudaMemcpyDeviceToHost, ws->stream));
     PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    return PEEB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ a1 / a3 / a4 on float64 pixel data
+// The reference converts whatever it is given with np.array(img, dtype=np.float64) (src/mse.py:85,91) and
+// works element-wise in float64 from there; integer-valued pixel data takes the exact integer kernel above,
+// everything else (fractional, negative or > 16-bit values) comes here.  One kernel, run twice by the Python
+// side: first plain (maxima, sums, difference statistics), then with the reference's range normalisation
+// u = (a / div_a) * mul_a (src/mse.py:104-105, same operation order) and the means of pass one, which gives
+// the squared difference and the centred second moments (np.var / covariance of src/mse.py:166-168) without
+// cancellation.  Per-CTA partial sums, added up in a fixed order by one CTA: results do not depend on timing.
+namespace peeb {
+
+constexpr int F64_OUT = 12;  // sum u, sum v, sum (u-mu)^2, sum (v-mv)^2, sum (u-mu)(v-mv), sum (u-v)^2,
+                             // sum |a-b|, max |a-b|, max a, max b, #(a != b), n
+
+struct F64Acc {
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};
+    double maxd = 0.0, maxa = -INFINITY, maxb = -INFINITY;
+    double ne = 0.0;
+};
+
+__global__ void __launch_bounds__(256) moments_f64_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                          long long n, double div_a, double mul_a, double div_b,
+                                                          double mul_b, double mu, double mv, int scaled,
+                                                          double* __restrict__ partial) {
+    F64Acc acc;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = a[i], y = b[i];
+        const double u = scaled ? (x / div_a) * mul_a : x, v = scaled ? (y / div_b) * mul_b : y;
+        const double du = u - mu, dv = v - mv, d = u - v, r = fabs(x - y);
+        acc.s[0] += u; acc.s[1] += v;
+        acc.s[2] += du * du; acc.s[3] += dv * dv; acc.s[4] += du * dv;
+        acc.s[5] += d * d; acc.s[6] += r;
+        acc.maxd = fmax(acc.maxd, r); acc.maxa = fmax(acc.maxa, x); acc.maxb = fmax(acc.maxb, y);
+        acc.ne += (x != y) ? 1.0 : 0.0;
+    }
+    __shared__ double sh[8][F64_OUT];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double vals[F64_OUT] = {acc.s[0], acc.s[1], acc.s[2], acc.s[3], acc.s[4], acc.s[5], acc.s[6],
+                            acc.maxd, acc.maxa, acc.maxb, acc.ne, 0.0};
+#pragma unroll
+    for (int k = 0; k < F64_OUT; ++k) {
+        double v = vals[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, v, o);
+            v = (k >= 7 && k <= 9) ? fmax(v, t) : v + t;
+        }
+        if (lane == 0) sh[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < F64_OUT) {
+        const int k = threadIdx.x;
+        double v = sh[0][k];
+        for (int w = 1; w < 8; ++w) v = (k >= 7 && k <= 9) ? fmax(v, sh[w][k]) : v + sh[w][k];
+        partial[(long long)blockIdx.x * F64_OUT + k] = v;
+    }
+}
+
+__global__ void moments_f64_final_kernel(const double* __restrict__ partial, int nblocks, long long n,
+                                         double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= F64_OUT) return;
+    double v = partial[k];
+    for (int b = 1; b < nblocks; ++b) {
+        const double t = partial[(long long)b * F64_OUT + k];
+        v = (k >= 7 && k <= 9) ? fmax(v, t) : v + t;
+    }
+    out[k] = k == 11 ? (double)n : v;
+}
+
+}  // namespace peeb
+
+extern "C" {
+
+int peeb_moments_f64(peeb_ws* ws, const double* a, const double* b, int64_t n, int scaled, double div_a, double mul_a,
+                     double div_b, double mul_b, double mean_a, double mean_b, double* out, void* stream) {
+    PEEB_REQUIRE(ws && a && b && out, "peeb_moments_f64: null pointer");
+    PEEB_REQUIRE(n >= 1, "peeb_moments_f64: n must be >= 1");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    long long want = (n + 256 * 8 - 1) / (256 * 8);
+    const int nblocks = (int)std::min<long long>(std::max<long long>(want, 1), (long long)ws->sm_count * 8);
+    int rc = scratch_reserve(ws->tables, (size_t)nblocks * F64_OUT * sizeof(double) + 256);
+    if (rc) return rc;
+    double* partial = (double*)ws->tables.ptr;
+    ProfScope prof(ws, PEEB_K_MOMENTS, st);
+    moments_f64_kernel<<<nblocks, 256, 0, st>>>(a, b, n, div_a, mul_a, div_b, mul_b, mean_a, mean_b, scaled, partial);
+    moments_f64_final_kernel<<<1, 32, 0, st>>>(partial, nblocks, n, out);
+    PEEB_CUDA(cudaGetLastError());
+    return PEEB_OK;
+}
+
+int peeb_moments_f64_h(peeb_ws* ws, const double* a_host, const double* b_host, int64_t n, double* out_host) {
+    PEEB_REQUIRE(ws && a_host && b_host && out_host, "peeb_moments_f64_h: null pointer");
+    PEEB_REQUIRE(n >= 1, "peeb_moments_f64_h: n must be >= 1");
+    PEEB_CUDA(cudaSetDevice(ws->device));
+    const size_t bytes = (size_t)n * sizeof(double), o_b = align_up(bytes, 256), o_out = 2 * o_b;
+    int rc = scratch_reserve(ws->stage, o_out + 256);
+    if (rc) return rc;
+    char* d = (char*)ws->stage.ptr;
+    const double* da = (const double*)d;
+    const double* db = (const double*)(d + o_b);
+    double* dout = (double*)(d + o_out);
+    PEEB_CUDA(cudaMemcpyAsync(d, a_host, bytes, cudaMemcpyHostToDevice, ws->stream));
+    PEEB_CUDA(cudaMemcpyAsync(d + o_b, b_host, bytes, cudaMemcpyHostToDevice, ws->stream));
+    // pass one: plain values (maxima, sums, difference statistics)
+    rc = peeb_moments_f64(ws, da, db, n, 0, 1.0, 1.0, 1.0, 1.0, 0.0, 0.0, dout, ws->stream);
+    if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+    PEEB_CUDA(cudaMemcpyAsync(out_host, dout, F64_OUT * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    // pass two: the reference's range normalisation (only when the maxima differ, src/mse.py:101) and moments
+    // centred on (an estimate of) the means -- the caller corrects with the exact means of this pass
+    const double maxa = out_host[8], maxb = out_host[9], top = maxa > maxb ? maxa : maxb;
+    const int scaled = maxa != maxb;
+    const double mu = scaled ? ((out_host[0] / (double)n) / maxa) * top : out_host[0] / (double)n;
+    const double mv = scaled ? ((out_host[1] / (double)n) / maxb) * top : out_host[1] / (double)n;
+    rc = peeb_moments_f64(ws, da, db, n, scaled, maxa, top, maxb, top, mu, mv, dout, ws->stream);
+    if (rc) { cudaStreamSynchronize(ws->stream); return rc; }
+    PEEB_CUDA(cudaMemcpyAsync(out_host + F64_OUT, dout, F64_OUT * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    PEEB_CUDA(cudaStreamSynchronize(ws->stream));
+    out_host[2 * F64_OUT] = mu;
+    out_host[2 * F64_OUT + 1] = mv;
     return PEEB_OK;
 }
 

@@ -119,3 +119,45 @@ def moments_device(a, b, out=None, full=True):
     check(fn(ws.handle, _raw(a, "a"), _raw(b, "b"), per, item, n, per, per, _raw(out, "out"), _stream(dev)),
           "peeb_moments_batch")
     return out
+
+
+def bitmap_encode_device(elements, n=None, packed=False, blob=None):
+    """Side bitmap (uint8 CUDA tensor, non-zero = 1; or np.packbits bytes holding ``n`` elements with
+    ``packed``) -> ("PBR1" blob as a uint8 CUDA tensor view of the right length).  Synchronises the
+    stream once to learn the blob's size."""
+    import ctypes as C
+
+    dev = elements.device
+    if elements.dtype != torch.uint8:
+        raise ValueError("elements must be a uint8 tensor")
+    if packed:
+        n = elements.numel() * 8 if n is None else int(n)
+        if (n + 7) // 8 != elements.numel():
+            raise ValueError("n does not match the packed tensor's length")
+    else:
+        n = elements.numel()
+    cap = int(lib().peeb_bitmap_blob_bound(n))
+    if blob is None:
+        blob = torch.empty(cap, dtype=torch.uint8, device=dev)
+    elif blob.numel() < cap:
+        raise ValueError("blob is smaller than peeb_bitmap_blob_bound(n)")
+    ws = workspace(dev.index if dev.index is not None else torch.cuda.current_device())
+    got = C.c_int64(0)
+    check(lib().peeb_bitmap_encode(ws.handle, _raw(elements, "elements") if n else None, n, 1 if packed else 0,
+                                   _raw(blob, "blob"), blob.numel(), C.byref(got), _stream(dev)), "peeb_bitmap_encode")
+    return blob[:got.value]
+
+
+def bitmap_decode_device(blob, n, packed=False, out=None):
+    """"PBR1" blob (uint8 CUDA tensor) -> n bytes of 0/1, or the packed bits.  Synchronises the stream."""
+    dev = blob.device
+    n = int(n)
+    size = (n + 7) // 8 if packed else n
+    if out is None:
+        out = torch.empty(size, dtype=torch.uint8, device=dev)
+    elif out.numel() != size or out.dtype != torch.uint8:
+        raise ValueError("out must be a uint8 tensor of the decoded size")
+    ws = workspace(dev.index if dev.index is not None else torch.cuda.current_device())
+    check(lib().peeb_bitmap_decode(ws.handle, _raw(blob, "blob"), blob.numel(), _raw(out, "out") if size else None, n,
+                                   1 if packed else 0, _stream(dev)), "peeb_bitmap_decode")
+    return out

@@ -46,14 +46,37 @@ def _as_pixels(img, name):
         return np.ascontiguousarray(a.astype(np.uint8))
     if np.issubdtype(a.dtype, np.integer):
         if a.size and (a.min() < 0 or a.max() > 65535):
-            raise TypeError(f"{name}: only unsigned 8/16-bit pixel data is supported on the device path")
+            return None  # wider than 16 bits or negative: the float64 kernels
         return np.ascontiguousarray(a.astype(np.uint16))
     if np.issubdtype(a.dtype, np.floating):
         r = np.rint(a)
         if a.size and (not np.array_equal(r, a) or a.min() < 0 or a.max() > 65535):
-            raise TypeError(f"{name}: only integer-valued pixel data in [0, 65535] is supported on the device path")
+            return None  # fractional / negative / wide values: the float64 kernels
         return np.ascontiguousarray(r.astype(np.uint16))
     raise TypeError(f"{name}: unsupported dtype {a.dtype}")
+
+
+def _float_moments(img1, img2, device=None) -> dict:
+    """The float64 route of the reference (``np.array(img, dtype=np.float64)``, src/mse.py:85,91) for pixel data
+    that is not integer-valued 8/16-bit: plain sums and difference statistics, plus the normalised, centred second
+    moments (src/mse.py:100-110, :152-168), all reduced on the device."""
+    a = np.ascontiguousarray(np.array(img1, dtype=np.float64))
+    b = np.ascontiguousarray(np.array(img2, dtype=np.float64))
+    if a.shape != b.shape:
+        raise ValueError(f"Dimensões diferentes: {a.shape} vs {b.shape}")  # src/mse.py:97-98
+    if a.size == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")
+    out = np.zeros(26, np.float64)
+    check(lib().peeb_moments_f64_h(workspace(device).handle, ptr(a), ptr(b), a.size, ptr(out)), "peeb_moments_f64_h")
+    n = a.size
+    p1, p2, mu0, mv0 = out[:12], out[12:24], out[24], out[25]
+    mu, mv = p2[0] / n, p2[1] / n                       # exact means of the (normalised) images
+    return {
+        "float": True, "n": n, "max_a": p1[8], "max_b": p1[9], "sad": p1[6], "max_abs": p1[7], "changed": int(p1[10]),
+        "mu1": mu, "mu2": mv,
+        "var1": p2[2] / n - (mu - mu0) ** 2, "var2": p2[3] / n - (mv - mv0) ** 2,
+        "cov": p2[4] / n - (mu - mu0) * (mv - mv0), "mse": p2[5] / n,
+    }
 
 
 def image_moments(img1, img2, device=None, full=True) -> dict:
@@ -70,6 +93,10 @@ def image_moments(img1, img2, device=None, full=True) -> dict:
         rb = (1 << info["BitsStored"]) - 1
     a = _as_pixels(img1, "img1")
     b = _as_pixels(img2, "img2")
+    if a is None or b is None:
+        if ra is not None or rb is not None:
+            raise TypeError("a .dcm path can only be compared with integer pixel data")
+        return _float_moments(img1, img2, device)
     if a.shape != b.shape:
         raise ValueError(f"Dimensões diferentes: {a.shape} vs {b.shape}")  # src/mse.py:97-98
     if a.size == 0:
@@ -121,12 +148,14 @@ class AnalisadorMSE:
     def calcular_mse(self, imagem1, imagem2):
         """src/mse.py:74-116 -> ``(np.float64 mse, np.float64 max_range)``."""
         m = image_moments(imagem1, imagem2, self._device, full=False)
-        if m["max_a"] != m["max_b"]:  # the normalisation branch needs the second moments too
+        if not m.get("float") and m["max_a"] != m["max_b"]:  # the normalisation branch needs the second moments too
             m = image_moments(imagem1, imagem2, self._device)
         return self._mse_from(m)
 
     @staticmethod
     def _mse_from(m):
+        if m.get("float"):
+            return np.float64(m["mse"]), np.float64(max(m["max_a"], m["max_b"]))
         al, be, top = _scales(m)
         n = m["n"]
         if al == 1 and be == 1:
@@ -154,6 +183,12 @@ class AnalisadorMSE:
 
     @staticmethod
     def _ssim_from(m):
+        if m.get("float"):  # src/mse.py:152-178 on the device-reduced float64 moments
+            top_f = float(max(m["max_a"], m["max_b"]))
+            c1, c2 = (0.01 * top_f) ** 2, (0.03 * top_f) ** 2
+            num = (2 * m["mu1"] * m["mu2"] + c1) * (2 * m["cov"] + c2)
+            den = (m["mu1"] ** 2 + m["mu2"] ** 2 + c1) * (m["var1"] + m["var2"] + c2)
+            return np.float64(num / den)
         al, be, top = _scales(m)
         n = m["n"]
         mu1 = al * Fraction(m["sum_a"], n)

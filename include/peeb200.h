@@ -70,12 +70,13 @@ int peeb_memcpy_d2h(peeb_ws* ws, void* dst_host, const void* src_dev, size_t byt
 
 /* per-kernel device time accounting (CUDA events around each launch; adds a
  * sync per launch -- for bench.py's roofline leg, never for a timed `value`) */
-#define PEEB_PROF_SLOTS 16
+#define PEEB_PROF_SLOTS 20
 enum {
     PEEB_K_MOMENTS = 0, PEEB_K_HIST_PLANES = 1, PEEB_K_TILE_MOMENTS = 2, PEEB_K_LSB_EMBED = 3,
     PEEB_K_PLANES_PACK = 4, PEEB_K_PLANES_UNPACK = 5, PEEB_K_COMPACT = 6,
     PEEB_K_PEE_COUNT = 7, PEEB_K_PEE_EMBED = 8, PEEB_K_PEE_EXTRACT = 9, PEEB_K_PEE_GATHER = 10,
-    PEEB_K_PEE_HIST = 11, PEEB_K_PEE_FINAL = 12, PEEB_K_LSB_RECOVER = 13, PEEB_K_LSB_EXTRACT = 14
+    PEEB_K_PEE_HIST = 11, PEEB_K_PEE_FINAL = 12, PEEB_K_LSB_RECOVER = 13, PEEB_K_LSB_EXTRACT = 14,
+    PEEB_K_BITMAP_ENCODE = 15, PEEB_K_BITMAP_DECODE = 16
 };
 int peeb_prof_enable(peeb_ws* ws, int on);  /* also resets the counters */
 int peeb_prof_get(peeb_ws* ws, int slot, double* total_ms, long long* launches);
@@ -106,6 +107,20 @@ int peeb_sse_batch(peeb_ws* ws, const void* a, const void* b, int64_t n_per_imag
                    int n_images, int64_t stride_a, int64_t stride_b, int64_t* out, void* stream);
 int peeb_sse_h(peeb_ws* ws, const void* a_host, const void* b_host, int64_t n, int itemsize,
                int64_t* out_host);
+
+/* a1 / a3 / a4 on float64 pixel data: the reference converts any input with
+ * np.array(img, dtype=np.float64) (src/mse.py:85,91); integer-valued 8/16-bit data takes
+ * the exact integer kernels above, everything else (fractional, negative, wider values)
+ * these.  out (DEVICE, 12 doubles) = {sum u, sum v, sum (u-mean_a)^2, sum (v-mean_b)^2,
+ * sum (u-mean_a)(v-mean_b), sum (u-v)^2, sum |a-b|, max |a-b|, max a, max b, #(a != b), n}
+ * with u = scaled ? (a / div_a) * mul_a : a (the operation order of src/mse.py:104-105),
+ * v likewise.  The _h form uploads once and runs both passes the metrics need: out_host
+ * (26 doubles) = plain pass | normalised + centred pass (scaled only when the maxima
+ * differ, src/mse.py:101) | the two centring values used.  Tolerance vs numpy: 1e-9 rel. */
+int peeb_moments_f64(peeb_ws* ws, const double* a, const double* b, int64_t n, int scaled, double div_a,
+                     double mul_a, double div_b, double mul_b, double mean_a, double mean_b, double* out,
+                     void* stream);
+int peeb_moments_f64_h(peeb_ws* ws, const double* a_host, const double* b_host, int64_t n, double* out_host);
 
 /* ---- a5: histogram + bit-plane population counts ---------------------- *
  * Everything adaptive_modalities_decomposition / calculate_entropy /
@@ -266,6 +281,28 @@ int peeb_pee_med_embed_h(peeb_ws* ws, const void* src_host, int n_units, int h, 
 int peeb_pee_med_extract_h(peeb_ws* ws, const void* marked_host, int n_units, int h, int w, int itemsize,
                            int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm_host,
                            uint8_t* payload_out_host, int64_t payload_stride, void* recovered_host, int64_t* info_host);
+
+/* ---- N2: coding of the side bitmaps --------------------------- *
+ * Replaces, as an opt-in format, the reference's blob steps around its container:
+ * zlib.compress(np.stack(bitmaps).tobytes()) (src/codec.py:888-889) and
+ * np.frombuffer(zlib.decompress(blob), uint8) (src/codec.py:820-821), which push one
+ * BYTE per pixel and plane through a serial host coder.  Format "PBR1" (bit packing +
+ * three levels of 32-way zero-run elimination; layout in csrc/peeb_bitcode.cu and
+ * oracle/bitcode_numpy.py).  src: n map elements, one uint8 each (non-zero = 1), or
+ * with packed_input != 0 the np.packbits form (ceil(n/8) bytes, e.g. a PEE location
+ * map).  The blob needs peeb_bitmap_blob_bound(n) bytes of capacity; the encoded size
+ * comes back in *blob_bytes (HOST pointer; the call synchronises the stream).
+ * decode writes n bytes of 0/1 (or ceil(n/8) packed bytes) and fails with
+ * PEEB_E_INVALID on a blob whose header, size or level tables are inconsistent.     */
+size_t peeb_bitmap_blob_bound(int64_t n);
+int peeb_bitmap_encode(peeb_ws* ws, const uint8_t* src, int64_t n, int packed_input, uint8_t* blob,
+                       int64_t blob_capacity, int64_t* blob_bytes, void* stream);
+int peeb_bitmap_decode(peeb_ws* ws, const uint8_t* blob, int64_t blob_bytes, uint8_t* dst, int64_t n,
+                       int packed_output, void* stream);
+int peeb_bitmap_encode_h(peeb_ws* ws, const uint8_t* src_host, int64_t n, int packed_input, uint8_t* blob_host,
+                         int64_t blob_capacity, int64_t* blob_bytes);
+int peeb_bitmap_decode_h(peeb_ws* ws, const uint8_t* blob_host, int64_t blob_bytes, uint8_t* dst_host, int64_t n,
+                         int packed_output);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

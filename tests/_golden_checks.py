@@ -103,3 +103,37 @@ def check_entropy_and_split(impl, img, rec):
     for i, mi in enumerate(rec["mi"]):
         got = impl.calculate_mutual_information((img >> i) & 1, img)
         assert float(got) == mi, (i, float(got), mi)
+
+
+# ---- inputs of the golden entries added in round 2 (shared with tests/golden/make_golden.py) ----
+def general_mi_cases():
+    """(name, plane, image): planes that are NOT bit planes of the image -- the general branch of
+    calculate_mutual_information (src/codec.py:504-559 accepts any non-negative integer plane)."""
+    from codec_tcc_b200.synth import synth_image
+
+    a, b = synth_image(129, 70, 255, 13), synth_image(129, 70, 255, 31)
+    c, d = synth_image(120, 96, 4095, 12), synth_image(120, 96, 4095, 33)
+    rng = np.random.default_rng(77)
+    return [
+        ("u8_other_image_bit3", (b >> 3) & 1, a),
+        ("u8_random_bits", rng.integers(0, 2, a.shape).astype(np.uint8), a),
+        ("u8_three_values", ((b >> 6) % 3).astype(np.uint8), a),
+        ("u16_other_image_bit5", ((d >> 5) & 1).astype(np.uint16), c),
+        ("u16_threshold_of_image", (c > 2000).astype(np.uint16), c),
+        ("u16_image_u8_plane", (d >> 11).astype(np.uint8), c),
+    ]
+
+
+def float_metric_cases():
+    """(name, img1, img2): inputs the reference handles through np.array(img, dtype=np.float64) (src/mse.py:85)
+    that are not integer-valued 8/16-bit pixel data."""
+    from codec_tcc_b200.synth import synth_image
+
+    a = synth_image(120, 90, 4095, 21).astype(np.float64)
+    b = a + np.random.default_rng(9).normal(0.0, 2.5, a.shape)
+    return [
+        ("fractional", a, b),
+        ("negative", a - 1000.25, b - 1000.0),
+        ("different_ranges", a * 0.5, b),
+        ("wide_integers", (a * 40).astype(np.int64), (b * 40).astype(np.int64)),
+    ]

@@ -17,9 +17,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from codec_tcc_b200.synth import synth_image, synth_saturated  # noqa: E402
 from oracle import ref_import  # noqa: E402
+import _golden_checks as GC  # noqa: E402  (input builders shared with the tests)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 MAIN_MESSAGE = "Mensagem de teste para esteganografia!"  # src/codec.py:863
@@ -134,6 +136,18 @@ def main():
     with ref_import.quiet():
         sc["header_hex"] = codec.create_header("jxl", 5, [1966, 1256, 706, 314, 78], [3, 1, 2, 4, 0],
                                                1234, 64, 64, 0, False).hex()
+
+    # round 2: the general branch of calculate_mutual_information and the float64 route of the metrics
+    sc["mi_general"] = {name: float(codec.calculate_mutual_information(plane, img)) for name, plane, img in GC.general_mi_cases()}
+    sc["float_metrics"] = {}
+    for name, x, y in GC.float_metric_cases():
+        with ref_import.quiet():
+            m, r = an.calcular_mse(x, y)
+            ss = an.calcular_ssim_simples(x, y)
+        fx, fy = np.array(x, dtype=np.float64), np.array(y, dtype=np.float64)
+        sc["float_metrics"][name] = {"mse": float(m), "max_range": float(r), "ssim": float(ss),
+                                     "mean_abs": float(np.mean(np.abs(fx - fy))), "max_abs": float(np.max(np.abs(fx - fy))),
+                                     "changed": int(np.sum(fx != fy))}
 
     def enc(o):
         if isinstance(o, float) and o == float("inf"):

@@ -171,8 +171,44 @@ def test_normalisation_branch_and_mixed_inputs():
     assert abs(float(m1) - float(m0)) <= 1e-9 * float(m0) and float(r1) == float(r0)
     res = an.analisar_par_arrays(a, b, "par")
     assert set(res) >= {"mse", "psnr", "ssim", "diferenca_media", "diferenca_max", "percentual_mudanca"}
-    with pytest.raises(TypeError):
-        an.calcular_mse(a.astype(np.float64) + 0.5, b)
+
+
+def test_float_route_of_the_metrics(golden):
+    """Inputs that are not integer-valued 8/16-bit data take the float64 kernels (the reference's own
+    np.array(img, dtype=np.float64) route, src/mse.py:85): golden values of the unmodified reference, 1e-9."""
+    an = mse.AnalisadorMSE()
+    for name, x, y in GC.float_metric_cases():
+        want = golden["scalars"]["float_metrics"][name]
+        m, r = an.calcular_mse(x, y)
+        assert abs(float(m) - want["mse"]) <= 1e-9 * want["mse"], (name, float(m), want["mse"])
+        assert abs(float(r) - want["max_range"]) <= 1e-12 * abs(want["max_range"]), name
+        assert abs(float(an.calcular_ssim_simples(x, y)) - want["ssim"]) <= 1e-9, name
+        st = an.difference_stats(x, y)
+        assert abs(float(st[0]) - want["mean_abs"]) <= 1e-9 * want["mean_abs"] and int(st[2]) == want["changed"], name
+        assert abs(float(st[1]) - want["max_abs"]) <= 1e-12 * want["max_abs"], name
+        m0, r0 = OM.calcular_mse(x, y)
+        assert abs(float(m) - float(m0)) <= 1e-9 * float(m0)
+    # lists of floats, one float and one integer image
+    a = synth_image(64, 80, 4095, 2)
+    m1, r1 = an.calcular_mse((a + 0.25).tolist(), a)   # (the maxima differ: the range normalisation applies)
+    m0, r0 = OM.calcular_mse((a + 0.25).tolist(), a)
+    assert abs(float(m1) - float(m0)) <= 1e-9 * float(m0) and abs(float(r1) - float(r0)) <= 1e-12 * float(r0)
+    with pytest.raises(ValueError):
+        an.calcular_mse(np.zeros((2, 3)) + 0.5, np.zeros((3, 2)))
+
+
+def test_mutual_information_of_arbitrary_planes(golden):
+    """calculate_mutual_information for planes that are not bit planes of the image (src/codec.py:504-559 accepts
+    any): bit for bit the reference's value (golden) and the restatement's."""
+    for name, plane, img in GC.general_mi_cases():
+        got = float(codec.calculate_mutual_information(plane, img))
+        assert got == golden["scalars"]["mi_general"][name], (name, got)
+        assert got == float(OC.calculate_mutual_information(plane, img))
+    img = synth_image(64, 64, 255, 3)
+    assert codec.calculate_mutual_information(np.zeros_like(img), img) == 0.0          # constant plane
+    assert codec.calculate_mutual_information(img & 1, np.full_like(img, 7)) == 0.0    # constant image
+    with pytest.raises(ValueError):
+        codec.calculate_mutual_information(np.zeros((3, 3), np.uint8), img)
 
 
 @pytest.mark.parametrize("name", IMAGES)

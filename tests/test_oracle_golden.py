@@ -58,3 +58,16 @@ def test_scalars(golden):
     assert OC.message_to_bits("Olá, DICOM ✓") == sc["message_bits_hex"]
     with pytest.raises(ValueError):
         OM.calcular_mse(np.zeros((2, 3)), np.zeros((3, 2)))
+
+
+def test_general_mutual_information_and_float_metrics(golden):
+    """Round-2 golden entries (produced by the unmodified reference): planes that are not bit planes of the
+    image, and metric inputs that are not integer-valued 8/16-bit data."""
+    from oracle import mse_numpy as OM
+    for name, plane, img in GC.general_mi_cases():
+        assert float(OC.calculate_mutual_information(plane, img)) == golden["scalars"]["mi_general"][name], name
+    for name, x, y in GC.float_metric_cases():
+        want = golden["scalars"]["float_metrics"][name]
+        m, r = OM.calcular_mse(x, y)
+        assert float(m) == want["mse"] and float(r) == want["max_range"], name
+        assert float(OM.calcular_ssim_simples(x, y)) == want["ssim"], name

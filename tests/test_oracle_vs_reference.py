@@ -70,6 +70,17 @@ def test_entropy_mi_random():
             assert float(R.calculate_mutual_information(pl, img)) == float(OC.calculate_mutual_information(pl, img))
 
 
+def test_general_mutual_information_random():
+    """planes that are not bit planes of the image: the restatement's joint-bincount branch, live"""
+    R = ref_import.codec()
+    rng = np.random.default_rng(3)
+    for seed in range(4):
+        img = synth_image(40 + seed, 50, [255, 4095, 65535, 1023][seed], seed)
+        other = synth_image(40 + seed, 50, [255, 4095, 65535, 1023][seed], seed + 100)
+        for plane in ((other >> 2) & 1, rng.integers(0, 2, img.shape).astype(img.dtype), (other % 5).astype(np.uint8)):
+            assert float(R.calculate_mutual_information(plane, img)) == float(OC.calculate_mutual_information(plane, img))
+
+
 def test_metrics_match_reference():
     an = ref_import.mse().AnalisadorMSE()
     rng = np.random.default_rng(0)
