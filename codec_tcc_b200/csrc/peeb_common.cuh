@@ -136,11 +136,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
-        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");  // (suspend-time hint: sleep, do not spin)
 }
 // global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, both 16-B aligned)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {

@@ -116,11 +116,18 @@ __device__ __forceinline__ void issue_rows2(const Geom2& g, const unsigned char*
         }
     }
 }
+#ifdef PEEB_AB_POLLALL
+#define POLL_THREAD true
+#else
+#define POLL_THREAD (threadIdx.x < 32)
+#endif
+// (one warp polls the mbarrier -- its acquire, followed by the CTA barrier, orders the copied rows before every
+// thread's reads; seven more polling warps would only take issue slots from the CTAs that are computing)
 __device__ __forceinline__ void wait_rows2(const Geom2& g, int lo, int hi, uint64_t* bar) {
-    if (g.bulk && hi > lo) mbar_wait(bar, 0);
+    if (g.bulk && hi > lo && POLL_THREAD) mbar_wait(bar, 0);
     __syncthreads();
 }
-#define WAIT_ROWS2_MARKED(g, lo, hi, bar, slot) do { if ((g).bulk && (hi) > (lo)) mbar_wait(bar, 0); PHASE_MARK(slot); __syncthreads(); } while (0)
+#define WAIT_ROWS2_MARKED(g, lo, hi, bar, slot) do { if ((g).bulk && (hi) > (lo) && POLL_THREAD) mbar_wait(bar, 0); PHASE_MARK(slot); __syncthreads(); } while (0)
 template <typename PixT>
 __device__ __forceinline__ void load_rows2(const Geom2& g, const unsigned char* usrc, unsigned char* simg, int r_first,
                                            int lo, int hi, uint64_t* bar) {
@@ -909,14 +916,15 @@ __global__ void __launch_bounds__(NT, MINB) pee2_count_kernel(Geom2 g, PeeBatch 
     }
     const bool skip = bt.active && !bt.active[unit];  // threshold search: this unit is done
     if (!skip && band == 0 && threadIdx.x < PEEB_INFO) bt.info[(long long)unit * PEEB_INFO + threadIdx.x] = 0;
+    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
+    if (!skip) {
+        // bytes past ncol of this band's table rows are summed with the rest by the embed kernel: the rows start from
+        // zero (16-byte stores; the barrier below orders them before the sweep's byte stores)
+        uint4* rt = reinterpret_cast<uint4*>(rowcnt + ((long long)unit * g.h + own_lo) * g.tpitch);
+        for (int k = threadIdx.x; k < ((own_hi - own_lo) * g.tpitch) >> 4; k += blockDim.x) rt[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
     wait_rows2(g, max(r0 - 1, 0), min(r0 + g.R + 1, g.h), bar);
     if (skip) return;
-    const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
-    {   // bytes past ncol of this band's table rows are summed with the rest by the embed kernel: they are 0
-        const int padn = g.tpitch - g.ncol;
-        unsigned char* rt = rowcnt + ((long long)unit * g.h + own_lo) * g.tpitch + g.ncol;
-        for (int k = threadIdx.x; k < (own_hi - own_lo) * padn; k += blockDim.x) rt[(k / padn) * g.tpitch + (k % padn)] = 0;
-    }
     Count2<PixT, true> body{g, 0, rowcnt + (long long)unit * g.h * g.tpitch, 0};
     sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, bt.T[unit], body);
     int tot = body.total;
@@ -954,7 +962,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
     }
     // bytes of the pass-1 table past ncol are summed with the rest: keep them 0
-    for (int k = threadIdx.x; k < ((g.R + 2) * g.tpitch) >> 2; k += blockDim.x) reinterpret_cast<unsigned*>(tab)[k] = 0u;
+    for (int k = threadIdx.x; k < ((g.R + 2) * g.tpitch) >> 4; k += blockDim.x) reinterpret_cast<uint4*>(tab)[k] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     // Tickets run band-major over the batch (band 0 of every unit, then band 1, ...): with more units
     // than resident CTAs the earlier bands of a unit have finished when a band looks back, so the
@@ -986,7 +994,12 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         // flagged pixels are rare: their bits are OR-ed straight into the (zeroed) global rows of this band
         const int b_lo = r0, b_hi = min(r0 + g.R, g.h);
         unsigned* glm = reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride + (size_t)b_lo * g.lmw);
-        for (int k = threadIdx.x; k < (b_hi - b_lo) * (g.lmw >> 2); k += blockDim.x) glm[k] = 0u;
+        if ((g.lmw & 15) == 0 && ((uintptr_t)glm & 15) == 0) {
+            uint4* gq = reinterpret_cast<uint4*>(glm);
+            for (int k = threadIdx.x; k < (b_hi - b_lo) * (g.lmw >> 4); k += blockDim.x) gq[k] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            for (int k = threadIdx.x; k < (b_hi - b_lo) * (g.lmw >> 2); k += blockDim.x) glm[k] = 0u;
+        }
     }
     PHASE_MARK(0);  // set-up
     Stats2 st;
@@ -1096,6 +1109,19 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
 // ------------------------------------------------------------------ K_X: extract
 // Carrier bits of a (row, cell) are collected MSB-first in a lane register (first carrier ends up
 // in the highest of the n used bits); tn/tw tables hold count and bits per cell of the own rows.
+// the location-map bytes (nbytes <= 8) of a lane's cell in its two rows, fetched once per cell ahead of use: the
+// common all-zero cell then costs one test per step.  (A plain function returning values: called from the rare
+// path only, and the body's state stays in registers.)
+__device__ __noinline__ ulonglong2 fetch_lm_bytes(const unsigned char* p, int pitch, int nbytes) {
+    ulonglong2 v = make_ulonglong2(0ull, 0ull);
+#pragma unroll 1
+    for (int k = 0; k < nbytes; ++k) {
+        v.x |= (unsigned long long)p[k] << (8 * k);
+        v.y |= (unsigned long long)p[pitch + k] << (8 * k);
+    }
+    return v;
+}
+
 template <typename PixT>
 struct Extract2 {
     using P = PixOps<PixT>;
@@ -1105,11 +1131,13 @@ struct Extract2 {
     int lm_row0;
     unsigned char* tn;         // carriers per (own row, cell), one byte each, rows tpitch apart
     unsigned* tw;              // their bits, rows ncol words apart
+    bool has_lm;               // some pixel of the band's (or its halo rows') location-map rows is flagged
     KX ka, kb;
     unsigned Wa, Wb;
     int na, nb, ia, in;
     bool sta, stb, reca, recb, primed;
     unsigned long long la, lb;  // location-map bytes of this lane's cell in rows a and b (byte k = columns 8k..8k+7 of the cell)
+               // some pixel of the band's (or its halo rows') location-map rows is flagged
     __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool, bool, int T) {
         sta = a; stb = b;
         ka = kb = make_kx(T);
@@ -1118,23 +1146,11 @@ struct Extract2 {
         in = (rowa - own_lo) * g.tpitch + cell;
         reca = a && rowa >= own_lo && rowa < own_hi;
         recb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
-        // fetched once per cell, ahead of use: the common all-zero case then costs one test per step
-        const unsigned char* lmpa = slm + (size_t)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3);
         la = lb = 0ull;
-        const int nbytes = g.cws * (P::PXS >> 3);  // <= 8
-        if ((g.CW & 31) == 0) {
-            // cells start on a 4-byte boundary of the (4-byte aligned) map rows: two word loads per row; bytes
-            // past the cell belong to the next cell or to the row padding and are masked off
-            const unsigned* wa = reinterpret_cast<const unsigned*>(lmpa);
-            const unsigned* wb = reinterpret_cast<const unsigned*>(lmpa + g.lmpitch);
-            la = wa[0]; lb = wb[0];
-            if (nbytes > 4) { la |= (unsigned long long)wa[1] << 32; lb |= (unsigned long long)wb[1] << 32; }
-            if (nbytes < 8) { const unsigned long long m = (1ull << (8 * nbytes)) - 1ull; la &= m; lb &= m; }
-        } else {
-            for (int k = 0; k < nbytes; ++k) {
-                la |= (unsigned long long)lmpa[k] << (8 * k);
-                lb |= (unsigned long long)lmpa[g.lmpitch + k] << (8 * k);
-            }
+        if (has_lm) {  // flagged pixels are rare: most bands have none at all
+            const ulonglong2 v = fetch_lm_bytes(slm + (size_t)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3), g.lmpitch,
+                                                g.cws * (P::PXS >> 3));
+            la = v.x; lb = v.y;
         }
     }
     __device__ __forceinline__ unsigned lmbits(unsigned long long v, int s) const {
@@ -1182,32 +1198,65 @@ struct Extract2 {
     }
 };
 
-// The carrier bits of the band, in payload order: every lane places the bits of its cells (count in tn, bits in
-// tw) at the offset cell_prefix gives it, with shared-memory atomics; same lane -> (row pair, cell) mapping
-// as a sweep over the own rows.  Returns the carriers of the band (every lane).
-__device__ __forceinline__ int assemble_stream(const Geom2& g, int nrows, const unsigned char* tn, const unsigned* tw,
-                                               unsigned* out) {
-    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int total = 0;
-    for (int item = warp; item < g.nic; item += nwarps) {
-        const Lane2 l = lane_of(g, 0, nrows, item);
-        const unsigned char* ta = tn + l.rowa * g.tpitch;
-        const CellPrefix cp = cell_prefix_inl<false>(g, ta, l.rowa_in, l.rowb_in, l.cell);
-        total = cp.total;
+// The carrier bits of the band in payload order, both passes at once.  A thread takes one 32-bit word of a count
+// table (four cells of a row; tn1 follows tn0, rows tpitch bytes apart, bytes of cells >= ncol are 0): block scan
+// of the word sums in raster order -- one warp scan, one barrier, the warps of a pass never mix with the other's
+// (pass 1 starts at a multiple of 32) -- then the bits of its cells (tw) go to their offsets with shared-memory
+// atomics.  scan: >= 64 ints of shared memory.  Every thread gets the carriers of the band per pass.
+__device__ __forceinline__ void assemble_streams(const Geom2& g, int nrows, const unsigned char* tn0, const unsigned* tw0,
+                                                 const unsigned* tw1, unsigned* stream, int* scan, int& total0, int& total1) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int wu = (g.ncol + 3) >> 2;             // table words per row that hold cells
+    const int per = nrows * wu;                   // words per pass
+    const int p1 = (per + 31) & ~31;              // first index of pass 1
+    int carry0 = 0, carry1 = 0;
+    int flip = 0;
+    for (int base = 0; base < p1 + per; base += blockDim.x, flip ^= 32) {
+        const int k = base + threadIdx.x;
+        const int pass = k >= p1 ? 1 : 0;
+        const int kk = k - (pass ? p1 : 0);
+        const bool in = kk < per;
+        int row = 0, j = 0;
+        unsigned cw = 0u;
+        if (in) {
+            row = kk / wu; j = kk - row * wu;
+            cw = *reinterpret_cast<const unsigned*>(tn0 + (size_t)(pass * g.R + row) * g.tpitch + 4 * j);
+        }
+        const int tot = idp4_sum(cw, 0x01010101u, 0);
+        int incl = tot;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            if (!(r ? l.actb : l.acta)) continue;
-            const int cc = ta[r * g.tpitch + l.cell];
-            if (cc > 0) {
-                const int o = r ? cp.offb : cp.offa, sh = o & 31;
-                const unsigned long long v = (unsigned long long)tw[(l.rowa + r) * g.ncol + l.cell] << (64 - cc - sh);
-                atomicOr(out + (o >> 5), (unsigned)(v >> 32));
-                if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) scan[flip + warp] = incl;
+        __syncthreads();
+        int before = 0, all0 = 0, all1 = 0;
+        for (int q = 0; q < nwarps; ++q) {
+            const int a = scan[flip + q];
+            const bool q1 = (base + 32 * q) >= p1;
+            if (q1 == (pass != 0) && q < warp) before += a;
+            if (q1) all1 += a; else all0 += a;
+        }
+        if (cw != 0u) {
+            int o = (pass ? carry1 : carry0) + before + incl - tot;
+            unsigned* out = stream + (size_t)pass * g.bandwords;
+            const unsigned* tw = (pass ? tw1 : tw0) + (size_t)row * g.ncol + 4 * j;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cc = (int)((cw >> (8 * i)) & 0xffu);
+                if (cc > 0) {
+                    const int sh = o & 31;
+                    const unsigned long long v = (unsigned long long)tw[i] << (64 - cc - sh);
+                    atomicOr(out + (o >> 5), (unsigned)(v >> 32));
+                    if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
+                    o += cc;
+                }
             }
         }
+        carry0 += all0; carry1 += all1;
     }
-    if (warp >= g.nic) total = table_total(g, tn, nrows);  // warps without an item still report the total
-    return total;
+    total0 = carry0; total1 = carry1;
 }
 
 // grid = n_units * nb.  stage_bits: per (unit, pass, band) `bandwords` words, stream bit k at bit
@@ -1234,72 +1283,114 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     const int T = bt.T[unit];
     const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
     PHASE_INIT;
-    {   // location-map rows [r0-1, r0+R+1) -> slm; their loads are issued before the band's bulk copies
-        // (small reads would otherwise queue behind them)
+    int lm_any = 0;
+    {   // location-map rows [r0-1, r0+R+1) -> slm (shared row r = image row r0-1+r, lmpitch bytes, zero padded); the
+        // loads are issued before the band's bulk copies (small reads would otherwise queue behind them)
         const int l_lo = max(r0 - 1, 0), l_hi = min(r0 + g.R + 1, g.h);
         const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        if ((g.lmw & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
-            const int wpr = g.lmw >> 2, nwords = (l_hi - l_lo) * wpr;
-            const unsigned* gw = reinterpret_cast<const unsigned*>(glm + (size_t)l_lo * g.lmw);
-            unsigned* sw = reinterpret_cast<unsigned*>(slm);
-            // word k of the copy -> (row, word in row); rows are usually a power of two words long.  (The shared rows
-            // keep their 12-byte pad: lanes are rows, a pitch of a multiple of 128 bytes would put the map bytes of
-            // every lane in the same bank.)
-            const int wsh = (wpr & (wpr - 1)) == 0 ? 31 - __clz(wpr) : -1;
-            auto slot = [&](int k) {
-                const int r = wsh >= 0 ? k >> wsh : k / wpr;
-                return (size_t)(l_lo - (r0 - 1) + r) * (g.lmpitch >> 2) + (k - r * wpr);
-            };
-            unsigned v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = threadIdx.x + i * blockDim.x;
-                v[i] = k < nwords ? __ldg(gw + k) : 0u;
-            }
+        if (g.lmpitch == g.lmw && ((uintptr_t)glm & 15) == 0) {
+            // rows of whole 16-byte pieces, no padding between them: one flat copy of the rows inside the image, two
+            // pieces per thread in flight (a cell that sticks out of its row then sees the first bytes of the next
+            // row: columns past the image run with T = 0 whatever their flag says)
+            const int npieces = (l_hi - l_lo) * (g.lmw >> 4);
+            const uint4* gq = reinterpret_cast<const uint4*>(glm + (size_t)l_lo * g.lmw);
+            uint4* sq = reinterpret_cast<uint4*>(slm + (size_t)(l_lo - (r0 - 1)) * g.lmw);
+            const int k0 = threadIdx.x, k1 = threadIdx.x + blockDim.x;
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 v0 = k0 < npieces ? __ldg(gq + k0) : zero4, v1 = k1 < npieces ? __ldg(gq + k1) : zero4;
             issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int k = threadIdx.x + i * blockDim.x;
-                if (k < nwords) sw[slot(k)] = v[i];
+            if (k0 < npieces) sq[k0] = v0;
+            if (k1 < npieces) sq[k1] = v1;
+            lm_any = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0u;
+            for (int k = threadIdx.x + 2 * blockDim.x; k < npieces; k += blockDim.x) {
+                const uint4 v = __ldg(gq + k);
+                sq[k] = v;
+                lm_any |= (v.x | v.y | v.z | v.w) != 0u;
             }
-            for (int k = threadIdx.x + 4 * blockDim.x; k < nwords; k += blockDim.x)
-                sw[slot(k)] = __ldg(gw + k);
+            // rows of the copy outside the image (first / last band) are read by idle lanes only: zero
+            const int q = g.lmw >> 4;
+            if (l_lo > r0 - 1 && (int)threadIdx.x < q) reinterpret_cast<uint4*>(slm)[threadIdx.x] = zero4;
+            for (int k = (l_hi - (r0 - 1)) * q + threadIdx.x; k < (g.R + 2) * q; k += blockDim.x)
+                reinterpret_cast<uint4*>(slm)[k] = zero4;
+        } else if ((g.lmw & 15) == 0 && (g.lmpitch & 15) == 0 && ((uintptr_t)glm & 15) == 0) {
+            // padded rows of 16-byte pieces: piece k of the shared copy -> (row, piece of the row)
+            const int q = g.lmpitch >> 4, qv = g.lmw >> 4, npieces = (g.R + 2) * q;
+            auto fetch = [&](int k) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                const int r = k / q, j = k - r * q, row = r0 - 1 + r;
+                if (k < npieces && j < qv && row >= l_lo && row < l_hi)
+                    v = __ldg(reinterpret_cast<const uint4*>(glm + (size_t)row * g.lmw) + j);
+                return v;
+            };
+            const int k0 = threadIdx.x, k1 = threadIdx.x + blockDim.x;
+            const uint4 v0 = fetch(k0), v1 = fetch(k1);
+            issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+            uint4* sq = reinterpret_cast<uint4*>(slm);
+            if (k0 < npieces) sq[k0] = v0;
+            if (k1 < npieces) sq[k1] = v1;
+            lm_any = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0u;
+            for (int k = threadIdx.x + 2 * blockDim.x; k < npieces; k += blockDim.x) {
+                const uint4 v = fetch(k);
+                sq[k] = v;
+                lm_any |= (v.x | v.y | v.z | v.w) != 0u;
+            }
         } else {
             issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
-            for (int r = l_lo + warp; r < l_hi; r += nwarps)
-                for (int k = lane; k < g.lmw; k += 32) slm[(size_t)(r - (r0 - 1)) * g.lmpitch + k] = glm[(size_t)r * g.lmw + k];
+            for (int r = warp; r < g.R + 2; r += nwarps) {
+                const int row = r0 - 1 + r;
+                const bool valid = row >= l_lo && row < l_hi;
+                for (int k = lane; k < g.lmpitch; k += 32) {
+                    const unsigned char v = (valid && k < g.lmw) ? glm[(size_t)row * g.lmw + k] : (unsigned char)0;
+                    slm[(size_t)r * g.lmpitch + k] = v;
+                    lm_any |= v != 0;
+                }
+            }
         }
         PHASE_MARK(24);  // location map + copies issued
-        // bytes between lmw and the pitch are read by steps past the row end: keep them defined
-        const int padb = g.lmpitch - g.lmw;
-        if (padb > 0)
-            for (int r = warp; r < g.R + 2; r += nwarps)
-                if (lane < padb) slm[(size_t)r * g.lmpitch + g.lmw + lane] = 0;
-        for (int k = threadIdx.x; k < 2 * g.bandwords; k += blockDim.x) stream[k] = 0;
-        // count tables: the bytes past ncol are summed with the rest (tn0 and tn1 are adjacent)
-        for (int k = threadIdx.x; k < (2 * g.R * g.tpitch) >> 2; k += blockDim.x) reinterpret_cast<unsigned*>(tn0)[k] = 0u;
+        // the band streams (assembled with atomics) and the count tables (tn0 and tn1 are adjacent; the bytes
+        // past ncol are summed with the rest) start from zero: 16-byte stores
+        {
+            uint4* z = reinterpret_cast<uint4*>(stream);
+            const int nz = (int)(align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16) >> 4);
+            for (int k = threadIdx.x; k < nz; k += blockDim.x) z[k] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* t = reinterpret_cast<uint4*>(tn0);
+            for (int k = threadIdx.x; k < (2 * g.R * g.tpitch) >> 4; k += blockDim.x) t[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
         // the unit's output words start from zero (the gather kernel ORs the boundary words in and skips
         // zero words): every band clears its share, instead of a memset on the stream
         unsigned* pout = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
-        const long long z_lo = zero_words * band / g.nb, z_hi = zero_words * (band + 1) / g.nb;
-        for (long long k = z_lo + threadIdx.x; k < z_hi; k += blockDim.x) pout[k] = 0u;
+#ifdef PEEB_AB_ZWORD
+        if (false) {
+#else
+        if ((zero_words & 3) == 0 && ((uintptr_t)pout & 15) == 0) {
+#endif
+            const int nq = (int)(zero_words >> 2);
+            const int q_lo = (int)((long long)nq * band / g.nb), q_hi = (int)((long long)nq * (band + 1) / g.nb);
+            uint4* pq = reinterpret_cast<uint4*>(pout);
+            for (int k = q_lo + (int)threadIdx.x; k < q_hi; k += blockDim.x) pq[k] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            const long long z_lo = zero_words * band / g.nb, z_hi = zero_words * (band + 1) / g.nb;
+            for (long long k = z_lo + threadIdx.x; k < z_hi; k += blockDim.x) pout[k] = 0u;
+        }
     }
     PHASE_MARK(25);  // tables cleared
-    WAIT_ROWS2_MARKED(g, s_lo, s_hi, bar, 26);
+    if (g.bulk && s_hi > s_lo && POLL_THREAD) mbar_wait(bar, 0);  // (see wait_rows2)
+    PHASE_MARK(26);
+    const bool has_lm = __syncthreads_or(lm_any) != 0;  // (also the barrier that makes the staged rows visible)
     PHASE_MARK(0);  // load
     const int own_lo = max(r0, 1), own_hi = min(r0 + g.R, g.h - 1);
     const int p1_lo = max(r0 - 1, 1), p1_hi = min(r0 + g.R + 1, g.h - 1);
     const int nrows = max(own_hi - own_lo, 0);
     {   // colour 1 first (band rows + one halo row each side), then colour 0 (band rows)
-        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn1, tw1};
+        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn1, tw1, has_lm};
         sweep2_colour<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
         PHASE_MARK(1);  // sweep colour 1
     }
     __syncthreads();
     PHASE_MARK(2);
     {
-        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn0, tw0};
+        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn0, tw0, has_lm};
         sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
         PHASE_MARK(3);  // sweep colour 0
     }
@@ -1310,8 +1401,8 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     if (bt.dst)
         store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, min(r0 + g.R, g.h));
     PHASE_MARK(27);  // stores issued
-    const int total0 = assemble_stream(g, nrows, tn0, tw0, stream);
-    const int total1 = assemble_stream(g, nrows, tn1, tw1, stream + g.bandwords);
+    int total0, total1;
+    assemble_streams(g, nrows, tn0, tw0, tw1, stream, reinterpret_cast<int*>(smem_raw + L.misc), total0, total1);
     PHASE_MARK(28);  // assembled
     __syncthreads();
     PHASE_MARK(29);  // barrier
@@ -1405,7 +1496,12 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
     g.bulk = ws->use_bulk && (g.rowbytes % 16 == 0);
     g.pitch = (int)align_up((size_t)g.rowbytes, 128) + 16;
     g.lmw = (w + 7) / 8;
-    g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 12;
+    // extract copies rows of whole 16-byte pieces flat, without padding (they are read once per cell: bank conflicts do
+    // not matter); otherwise 12 bytes of pad spread the rows of the lanes of a warp over the banks
+    // (one 16-byte piece of padding per row measured 6 % faster on the 512-slice batch than rows back to back:
+    // scripts/ab_variants.sh, gpurun_out/r02_ab11.log; PEEB_LM_PAD overrides it for such runs)
+    g.lmpitch = (kind == 2 && (g.lmw & 15) == 0) ? g.lmw + (getenv("PEEB_LM_PAD") ? atoi(getenv("PEEB_LM_PAD")) : 16)
+                                                  : (int)align_up((size_t)g.lmw, 4) + 12;
     g.lm_direct = (kind == 1 && lm_direct_ok && (g.lmw & 3) == 0 && !getenv("PEEB_LM_SHARED")) ? 1 : 0;
     const int pxs = 16 / itemsize;
     const int nsteps = (g.rowbytes + 15) / 16;
