@@ -62,12 +62,14 @@ struct Geom2 {
 };
 
 struct Smem2 {
-    size_t img, lm, tab, misc, bar, tn0, tn1, tw0, tw1, stream, total;
+    size_t img, lm, tab, misc, bar, tn0, tn1, tw0, tw1, stream, tab0, xch, total;
 };
+constexpr int CLUSTER_MAX = 16;  // CTAs of one image's cluster (small-image path)
 constexpr int HWIN = 512;  // errors -HWIN <= e < HWIN of the threshold-selection histogram are counted in shared memory
-__host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 embed, 2 extract, 3 histogram*/) {
+__host__ __device__ inline Smem2 layout2(const Geom2& g, int kind_ /*0 count, 1 embed, 2 extract, 3 histogram, 4 / 5 embed / extract of the cluster path*/) {
     Smem2 L{};
     size_t o = 0;
+    const int kind = kind_ == 4 ? 1 : kind_ == 5 ? 2 : kind_;
     L.img = o; o += align_up((size_t)16 + (size_t)(g.R + 5) * g.pitch + 192, 16);
     L.lm = o;
     if (kind == 2 || (kind == 1 && !g.lm_direct)) o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
@@ -85,6 +87,9 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind /*0 count, 1 e
         L.tw1 = o; o += align_up(cells * sizeof(unsigned), 16);
         L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
     }
+    L.tab0 = L.xch = o;
+    if (kind_ == 4) { L.tab0 = o; o += (size_t)(g.R + 2) * g.tpitch; }   // pass-0 carriers per (row, cell)
+    if (kind_ >= 4) { L.xch = o; o += (size_t)8 * CLUSTER_MAX * sizeof(unsigned); }  // what the CTAs of a cluster tell each other
     L.total = o;
     return L;
 }
@@ -1289,6 +1294,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         const int l_lo = max(r0 - 1, 0), l_hi = min(r0 + g.R + 1, g.h);
         const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        (void)lane; (void)warp; (void)nwarps;
         if (g.lmpitch == g.lmw && ((uintptr_t)glm & 15) == 0) {
             // rows of whole 16-byte pieces, no padding between them: one flat copy of the rows inside the image, two
             // pieces per thread in flight (a cell that sticks out of its row then sees the first bytes of the next
@@ -1483,6 +1489,286 @@ __global__ void __launch_bounds__(256) pee2_gather_kernel(int nb, int bandwords,
     }
 }
 
+// ------------------------------------------------------------------ small-image path: one thread-block cluster per image
+// A single slice (or a handful) cannot fill the GPU with the band kernels above, and their order of events -- count
+// kernel, embed kernel with a look-back chain through global memory, extract kernel, gather kernel -- is four
+// launches of mostly latency.  Here one CLUSTER of up to 16 CTAs owns an image: CTA k stages band k in its shared
+// memory as before, and what the bands must tell each other (carriers per pass, statistics) goes through
+// distributed shared memory: every CTA writes its word into the exchange array of every other CTA
+// (st.shared::cluster) and one cluster barrier later everybody knows all of them -- no status words, no tickets, no
+// pre-zeroed counters, no second kernel.  Embed = 1 launch (count, scan, apply for both passes, summary written by
+// CTA 0), extract = 1 launch (the bands write their bits straight to their place in the unit's payload).
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// word `idx` of the exchange array of CTA `cta` of this cluster (same offset as in this CTA's own shared memory)
+__device__ __forceinline__ void st_cluster(unsigned* own_addr, unsigned cta, unsigned v) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(own_addr)), "r"(cta));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" :: "r"(remote), "r"(v) : "memory");
+}
+// every CTA of the cluster publishes `v` in slot [row][its rank] of everybody's exchange array (a warp does it, one
+// destination per lane); the caller runs a cluster barrier before reading
+__device__ __forceinline__ void cluster_publish(unsigned* xch, int row, unsigned rank, int C, unsigned v) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32 && lane < C) st_cluster(xch + row * CLUSTER_MAX + rank, (unsigned)lane, v);
+}
+__device__ __forceinline__ void cluster_sums(const unsigned* xch, int row, int rank, int C, unsigned& before, unsigned& all) {
+    before = 0u; all = 0u;
+    for (int k = 0; k < C; ++k) {
+        const unsigned v = xch[row * CLUSTER_MAX + k];
+        if (k < rank) before += v;
+        all += v;
+    }
+}
+
+template <typename PixT, int NT>
+__global__ void __launch_bounds__(NT, 1) pee2_cluster_embed_kernel(Geom2 g, PeeBatch bt, int C) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem2 L = layout2(g, 4);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned char* tab1 = smem_raw + L.tab;
+    unsigned char* tab0 = smem_raw + L.tab0;
+    unsigned* xch = reinterpret_cast<unsigned*>(smem_raw + L.xch);
+    int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    const int lane = threadIdx.x & 31;
+    const int band = (int)cluster_rank(), unit = blockIdx.x / C;
+    PHASE_INIT;
+    cluster_arrive();  // (waited for before the first remote store: every CTA of the cluster is then running)
+    if (threadIdx.x == 0) {
+        misc[0] = misc[1] = misc[2] = misc[3] = 0;
+        if (g.bulk) { mbar_init(bar, 1); fence_mbar_init(); }
+    }
+    for (int k = threadIdx.x; k < ((g.R + 2) * g.tpitch) >> 4; k += blockDim.x) {
+        reinterpret_cast<uint4*>(tab0)[k] = make_uint4(0u, 0u, 0u, 0u);
+        reinterpret_cast<uint4*>(tab1)[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    // (CTAs past the last band of the image own no rows: they publish zeros and take part in the barriers)
+    const int r0 = min(band * g.R, g.h), r_first = r0 - 2;
+    const int r1 = min(r0 + g.R, g.h);
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    const int T = bt.T[unit];
+    const unsigned n_bits = bt.n_bits[unit];
+    const unsigned* payload = reinterpret_cast<const unsigned*>(bt.payload + (long long)unit * bt.payload_stride);
+    long long* info = bt.info + (long long)unit * PEEB_INFO;
+    const bool live = r1 > r0;
+    const int own_lo = max(r0, 1), own_hi = live ? min(r1, g.h - 1) : own_lo;
+    const int p0_lo = max(r0 - 1, 1), p0_hi = live ? min(r1 + 1, g.h - 1) : p0_lo;
+    const int s_lo = max(r0 - 2, 0), s_hi = live ? min(r1 + 2, g.h) : s_lo;
+    issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+    unsigned* lmbase = bt.lm ? reinterpret_cast<unsigned*>(bt.lm + (long long)unit * bt.lm_stride) : nullptr;
+    const int lmwords = g.lmw >> 2;
+    if (lmbase)   // flagged pixels are rare: their bits are OR-ed straight into the (zeroed) global rows of this band
+        for (int k = threadIdx.x; k < (r1 - r0) * lmwords; k += blockDim.x) lmbase[(size_t)r0 * lmwords + k] = 0u;
+    PHASE_MARK(0);  // set-up
+    wait_rows2(g, s_lo, s_hi, bar);
+    PHASE_MARK(1);  // band copy wait
+    Stats2 st;
+    // ---- pass 0: carriers per (row, cell) of the band and its halo rows, the cluster's scan, apply
+    {
+        Count2<PixT, false> body{g, p0_lo, tab0, 0};
+        sweep2_colour<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
+    }
+    __syncthreads();
+    PHASE_MARK(2);  // count 0
+    const unsigned total0 = (unsigned)table_total(g, tab0 + (size_t)(own_lo - p0_lo) * g.tpitch, max(own_hi - own_lo, 0));
+    cluster_wait();
+    cluster_publish(xch, 0, (unsigned)band, C, total0);
+    cluster_arrive(); cluster_wait();
+    unsigned before0, cap0;
+    cluster_sums(xch, 0, band, C, before0, cap0);
+    PHASE_MARK(3);  // exchange 0
+    {
+        Apply2<PixT, false> body{g, p0_lo, own_lo, own_hi, tab0, payload, n_bits, before0, p0_lo < own_lo, lmbase, 0, lmwords, &st};
+        sweep2_colour<PixT>(g, simg, r_first, 0, p0_lo, p0_hi, T, body);
+    }
+    __syncthreads();
+    PHASE_MARK(4);  // apply 0
+    // ---- pass 1 over the band rows
+    {
+        Count2<PixT, false> body{g, own_lo, tab1, 0};
+        sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
+    }
+    __syncthreads();
+    PHASE_MARK(5);  // count 1
+    const unsigned total1 = (unsigned)table_total(g, tab1, max(own_hi - own_lo, 0));
+    cluster_publish(xch, 1, (unsigned)band, C, total1);
+    cluster_arrive(); cluster_wait();
+    unsigned before1, cap1;
+    cluster_sums(xch, 1, band, C, before1, cap1);
+    PHASE_MARK(6);  // exchange 1
+    {
+        Apply2<PixT, false> body{g, own_lo, own_lo, own_hi, tab1, payload, n_bits, cap0 + before1, false, lmbase, 0, lmwords, &st};
+        sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
+    }
+    __syncthreads();
+    PHASE_MARK(7);  // apply 1
+    if (bt.dst) store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, r1);
+    {   // statistics: per CTA in shared memory, then to CTA 0 of the cluster, which writes the unit's summary
+        const long long sse = warp_sum_i64(st.sse);
+        const unsigned fl = (unsigned)warp_sum_i64((long long)st.flagged);
+        if (lane == 0) {
+            if (sse) atomicAdd(reinterpret_cast<unsigned long long*>(misc), (unsigned long long)sse);
+            if (fl) atomicAdd(reinterpret_cast<unsigned*>(misc) + 2, fl);
+            if (bt.steps) {
+                atomicAdd(bt.steps, (unsigned long long)st.steps);
+                if (st.steps_edge) atomicAdd(bt.steps + 1, (unsigned long long)st.steps_edge);
+                if (st.steps_redone) atomicAdd(bt.steps + 2, (unsigned long long)st.steps_redone);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st_cluster(xch + 2 * CLUSTER_MAX + band, 0u, (unsigned)misc[0]);
+            st_cluster(xch + 3 * CLUSTER_MAX + band, 0u, (unsigned)misc[1]);
+            st_cluster(xch + 4 * CLUSTER_MAX + band, 0u, (unsigned)misc[2]);
+        }
+        cluster_arrive(); cluster_wait();
+        if (band == 0 && threadIdx.x == 0) {
+            unsigned long long sse_all = 0, fl_all = 0;
+            for (int k = 0; k < C; ++k) {
+                sse_all += (unsigned long long)xch[2 * CLUSTER_MAX + k] | ((unsigned long long)xch[3 * CLUSTER_MAX + k] << 32);
+                fl_all += xch[4 * CLUSTER_MAX + k];
+            }
+            const long long cap = (long long)cap0 + cap1;
+            info[0] = T; info[1] = n_bits; info[2] = cap; info[3] = cap0; info[4] = cap1;
+            info[5] = (long long)fl_all; info[6] = (long long)sse_all;
+            info[7] = ((long long)n_bits > cap) ? PEEB_E_CAPACITY : 0;
+        }
+    }
+    PHASE_MARK(8);  // statistics + summary
+    store_rows2_wait(g);
+    PHASE_MARK(9);  // store drain
+}
+
+template <typename PixT, int NT>
+__global__ void __launch_bounds__(NT, 1) pee2_cluster_extract_kernel(Geom2 g, PeeBatch bt, int C, long long zero_words) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Smem2 L = layout2(g, 5);
+    unsigned char* simg = smem_raw + L.img;
+    unsigned char* slm = smem_raw + L.lm;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    unsigned char* tn0 = smem_raw + L.tn0;
+    unsigned char* tn1 = smem_raw + L.tn1;
+    unsigned* tw0 = reinterpret_cast<unsigned*>(smem_raw + L.tw0);
+    unsigned* tw1 = reinterpret_cast<unsigned*>(smem_raw + L.tw1);
+    unsigned* stream = reinterpret_cast<unsigned*>(smem_raw + L.stream);
+    unsigned* xch = reinterpret_cast<unsigned*>(smem_raw + L.xch);
+    const int band = (int)cluster_rank(), unit = blockIdx.x / C;
+    cluster_arrive();
+    if (g.bulk && threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const int r0 = min(band * g.R, g.h), r_first = r0 - 2, r1 = min(r0 + g.R, g.h);
+    const bool live = r1 > r0;
+    const unsigned char* usrc = bt.src + (long long)unit * bt.src_stride;
+    const int T = bt.T[unit];
+    const long long n_bits = bt.n_bits[unit];
+    const int s_lo = max(r0 - 2, 0), s_hi = live ? min(r1 + 2, g.h) : s_lo;
+    int lm_any = 0;
+    {
+        const int l_lo = max(r0 - 1, 0), l_hi = live ? min(r1 + 1, g.h) : l_lo;
+        const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+        if ((g.lmw & 3) == 0 && (g.lmpitch & 3) == 0 && ((uintptr_t)glm & 3) == 0) {
+            const int wpr = g.lmw >> 2, wpp = g.lmpitch >> 2;
+            for (int r = warp; r < g.R + 2; r += nwarps) {
+                const int row = r0 - 1 + r;
+                const bool valid = row >= l_lo && row < l_hi;
+                for (int k = lane; k < wpp; k += 32) {
+                    const unsigned v = (valid && k < wpr) ? __ldg(reinterpret_cast<const unsigned*>(glm + (size_t)row * g.lmw) + k) : 0u;
+                    reinterpret_cast<unsigned*>(slm + (size_t)r * g.lmpitch)[k] = v;
+                    lm_any |= v != 0u;
+                }
+            }
+        } else {
+            for (int r = warp; r < g.R + 2; r += nwarps) {
+                const int row = r0 - 1 + r;
+                const bool valid = row >= l_lo && row < l_hi;
+                for (int k = lane; k < g.lmpitch; k += 32) {
+                    const unsigned char v = (valid && k < g.lmw) ? glm[(size_t)row * g.lmw + k] : (unsigned char)0;
+                    slm[(size_t)r * g.lmpitch + k] = v;
+                    lm_any |= v != 0;
+                }
+            }
+        }
+        uint4* z = reinterpret_cast<uint4*>(stream);
+        const int nz = (int)(align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16) >> 4);
+        for (int k = threadIdx.x; k < nz; k += blockDim.x) z[k] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* t = reinterpret_cast<uint4*>(tn0);
+        for (int k = threadIdx.x; k < (2 * g.R * g.tpitch) >> 4; k += blockDim.x) t[k] = make_uint4(0u, 0u, 0u, 0u);
+        // the unit's output words start from zero: every CTA of the cluster clears its share (the cluster barrier
+        // before the bits are written orders these stores before the other CTAs' atomics on boundary words)
+        unsigned* pout = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
+        const long long z_lo = zero_words * band / C, z_hi = zero_words * (band + 1) / C;
+        for (long long k = z_lo + threadIdx.x; k < z_hi; k += blockDim.x) pout[k] = 0u;
+    }
+    if (g.bulk && s_hi > s_lo && POLL_THREAD) mbar_wait(bar, 0);
+    const bool has_lm = __syncthreads_or(lm_any) != 0;
+    const int own_lo = max(r0, 1), own_hi = live ? min(r1, g.h - 1) : own_lo;
+    const int p1_lo = max(r0 - 1, 1), p1_hi = live ? min(r1 + 1, g.h - 1) : p1_lo;
+    const int nrows = max(own_hi - own_lo, 0);
+    {
+        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn1, tw1, has_lm};
+        sweep2_colour<PixT>(g, simg, r_first, 1, p1_lo, p1_hi, T, body);
+    }
+    __syncthreads();
+    {
+        Extract2<PixT> body{g, own_lo, own_hi, slm, r0 - 1, tn0, tw0, has_lm};
+        sweep2_colour<PixT>(g, simg, r_first, 0, own_lo, own_hi, T, body);
+    }
+    __syncthreads();
+    if (bt.dst) store_rows2_issue<PixT>(g, bt.dst + (long long)unit * bt.dst_stride, simg, r_first, r0, r1);
+    int total0, total1;
+    assemble_streams(g, nrows, tn0, tw0, tw1, stream, reinterpret_cast<int*>(smem_raw + L.misc), total0, total1);
+    __syncthreads();
+    cluster_wait();
+    cluster_publish(xch, 0, (unsigned)band, C, (unsigned)total0);
+    cluster_publish(xch, 1, (unsigned)band, C, (unsigned)total1);
+    cluster_arrive(); cluster_wait();
+    unsigned b0, all0, b1, all1;
+    cluster_sums(xch, 0, band, C, b0, all0);
+    cluster_sums(xch, 1, band, C, b1, all1);
+    const long long all = (long long)all0 + all1;
+    if (band == 0 && threadIdx.x == 0) {
+        long long* info = bt.info + (long long)unit * PEEB_INFO;
+        info[0] = T; info[1] = n_bits; info[2] = all; info[3] = all0; info[4] = all1;
+        info[5] = 0; info[6] = 0; info[7] = n_bits > all ? PEEB_E_CAPACITY : 0;
+    }
+    // the band's two streams go straight to their place in the unit's payload (MSB-first bytes, cut at n_bits)
+    unsigned* out = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
+    for (int pass = 0; pass < 2; ++pass) {
+        const int cnt = pass ? total1 : total0;
+        const long long before = pass ? (long long)all0 + b1 : (long long)b0;
+        if (cnt == 0 || before >= n_bits) continue;
+        const unsigned* src = stream + (size_t)pass * g.bandwords;
+        const int nsrc = (cnt + 31) >> 5;
+        const long long first = before >> 5, last = (before + cnt - 1) >> 5;
+        const int sh = (int)(before & 31);
+        for (long long mw = first + threadIdx.x; mw <= last; mw += blockDim.x) {
+            const int i = (int)(mw - first);
+            const unsigned cur = i < nsrc ? src[i] : 0u;
+            const unsigned prev = (i >= 1 && i - 1 < nsrc) ? src[i - 1] : 0u;
+            unsigned val = __funnelshift_r(cur, prev, sh);
+            const long long bit0 = mw << 5;
+            if (bit0 + 32 > n_bits) {
+                const int keep = (int)(n_bits - bit0);
+                val = keep <= 0 ? 0u : (val & ~(0xffffffffu >> keep));
+            }
+            if (val == 0) continue;
+            const unsigned packed = __byte_perm(val, 0, 0x0123);
+            if (mw == first || mw == last) atomicOr(out + mw, packed);
+            else out[mw] = packed;
+        }
+    }
+    store_rows2_wait(g);
+}
+
 // ------------------------------------------------------------------ host side
 static int ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) ++l; return l; }
 
@@ -1657,6 +1943,113 @@ int hist_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_uni
     return PEEB_OK;
 }
 
+// ---- small-image path: geometry and launch of the cluster kernels
+// A batch takes it when it is one or two small images (the band kernels would run a dozen CTAs; measured: one
+// 512x512 slice 51 against 58 us per round trip, but eight slices 107 against 60 us -- clusters of 16 CTAs are
+// placed one per GPC at a time) and an image fits one cluster: C CTAs of R = ceil(h / C) rows each, R + 2 <= 64
+// (one sweep covers a band and its halo rows).  PEEB_CLUSTER=0 / 1 forces the choice (tests, A/B runs).
+static bool make_geom_cluster(peeb_ws* ws, int n_units, int h, int w, int itemsize, int bit_depth, int kind /*4, 5*/,
+                              int regular_bands, int max_c, Geom2& g, int& C) {
+    const char* force = getenv("PEEB_CLUSTER");
+    if (force && atoi(force) == 0) return false;
+    if (!(force && atoi(force) == 1) && (long long)n_units * regular_bands * 8 > ws->sm_count) return false;
+    if (h < 3 || w < 3) return false;
+    g = Geom2{};
+    g.h = h; g.w = w; g.itemsize = itemsize;
+    g.maxval = (1 << bit_depth) - 1;
+    g.rowbytes = w * itemsize;
+    g.bulk = ws->use_bulk && (g.rowbytes % 16 == 0);
+    g.lmw = (w + 7) / 8;
+    g.lmpitch = (int)align_up((size_t)g.lmw, 4) + 12;
+    g.lm_direct = 1;
+    // (512 threads per CTA: more, smaller warp items -- 28 against 31 us for the embed of one 512x512 slice)
+    g.threads = getenv("PEEB_CLUSTER_THREADS") ? atoi(getenv("PEEB_CLUSTER_THREADS")) : 512; g.minb = 1;
+    if (g.threads != 256 && g.threads != 512) g.threads = 512;
+    const int pxs = 16 / itemsize, nsteps = (g.rowbytes + 15) / 16;
+    for (int c : {CLUSTER_MAX, 8}) {
+        const int R = (h + c - 1) / c;
+        if (c > max_c || R + 2 > 64) continue;
+        g.R = std::max(R, 1);
+        g.nb = (h + g.R - 1) / g.R;
+        g.rpw_log2 = 0;
+        while ((1 << g.rpw_log2) < (g.R + 3) / 2) ++g.rpw_log2;
+        g.rpw = 1 << g.rpw_log2;
+        const int parts = 32 / g.rpw;
+        // about one warp item per warp and sweep
+        int cws = nsteps / (parts * (g.threads / 32));
+        cws = std::max(1, std::min(cws, 64 / pxs));
+        g.cws = cws; g.CW = cws * pxs;
+        g.ncol = (nsteps + cws - 1) / cws;
+        g.pitch = (int)align_up((size_t)std::max(g.rowbytes, g.ncol * g.CW * itemsize), 128) + 16;
+        g.tpitch = (int)align_up((size_t)g.ncol, 16);
+        g.nic = (g.ncol + parts - 1) / parts;
+        g.bandwords = (g.R * ((w + 1) / 2) + 31) / 32 + 2;
+        if (layout2(g, kind).total > (size_t)ws->max_smem_optin) continue;
+        C = c;
+        if (getenv("PEEB_DEBUG_GEOM")) {
+            static int printed[2] = {0, 0};
+            if (printed[kind - 4]++ < 1)
+                fprintf(stderr, "[peeb] %dx%dx%d kind %d (cluster): C=%d R=%d nb=%d rpw=%d CW=%d ncol=%d smem=%zu\n", h, w, itemsize, kind, C,
+                        g.R, g.nb, g.rpw, g.CW, g.ncol, layout2(g, kind).total);
+        }
+        return true;
+    }
+    return false;
+}
+
+template <typename K, typename... Args>
+static int launch_cluster(K kernel, int n_units, int C, int threads, size_t smem, cudaStream_t st, Args... args) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 1; }
+    if (C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 1; }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_units * C)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 1; }
+    if (cudaLaunchKernelEx(&cfg, kernel, args...) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return 0;
+}
+
+// 0: launched; 1: this batch does not take the cluster path (the caller goes on with the band kernels)
+static int try_cluster_embed(peeb_ws* ws, const Geom2& gr, PeeBatch bt, int h, int w, int itemsize, int bit_depth, cudaStream_t st) {
+    if (bt.active) return 1;
+    if (bt.lm && ((((uintptr_t)bt.lm | (uint64_t)bt.lm_stride) & 3) || (((w + 7) / 8) & 3))) return 1;
+    for (int max_c : {CLUSTER_MAX, 8}) {  // 16 CTAs per cluster is more than the portable size: fall back to 8
+        Geom2 g; int C = 0;
+        if (!make_geom_cluster(ws, bt.n_units, h, w, itemsize, bit_depth, 4, gr.nb, max_c, g, C)) return 1;
+        g.bulk = g.bulk && gr.bulk;
+        const size_t smem = layout2(g, 4).total;
+        ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+        const int rc = itemsize == 2 ? (g.threads == 512 ? launch_cluster(pee2_cluster_embed_kernel<unsigned short, 512>, bt.n_units, C, 512, smem, st, g, bt, C)
+                                                         : launch_cluster(pee2_cluster_embed_kernel<unsigned short, 256>, bt.n_units, C, 256, smem, st, g, bt, C))
+                                     : (g.threads == 512 ? launch_cluster(pee2_cluster_embed_kernel<unsigned char, 512>, bt.n_units, C, 512, smem, st, g, bt, C)
+                                                         : launch_cluster(pee2_cluster_embed_kernel<unsigned char, 256>, bt.n_units, C, 256, smem, st, g, bt, C));
+        if (rc == 0) return 0;
+        if (C <= 8) return 1;
+    }
+    return 1;
+}
+static int try_cluster_extract(peeb_ws* ws, const Geom2& gr, PeeBatch bt, int h, int w, int itemsize, int bit_depth,
+                               long long zero_words, cudaStream_t st) {
+    for (int max_c : {CLUSTER_MAX, 8}) {
+        Geom2 g; int C = 0;
+        if (!make_geom_cluster(ws, bt.n_units, h, w, itemsize, bit_depth, 5, gr.nb, max_c, g, C)) return 1;
+        g.bulk = g.bulk && gr.bulk;
+        const size_t smem = layout2(g, 5).total;
+        ProfScope p(ws, PEEB_K_PEE_EXTRACT, st);
+        const int rc = itemsize == 2 ? (g.threads == 512 ? launch_cluster(pee2_cluster_extract_kernel<unsigned short, 512>, bt.n_units, C, 512, smem, st, g, bt, C, zero_words)
+                                                         : launch_cluster(pee2_cluster_extract_kernel<unsigned short, 256>, bt.n_units, C, 256, smem, st, g, bt, C, zero_words))
+                                     : (g.threads == 512 ? launch_cluster(pee2_cluster_extract_kernel<unsigned char, 512>, bt.n_units, C, 512, smem, st, g, bt, C, zero_words)
+                                                         : launch_cluster(pee2_cluster_extract_kernel<unsigned char, 256>, bt.n_units, C, 256, smem, st, g, bt, C, zero_words));
+        if (rc == 0) return 0;
+        if (C <= 8) return 1;
+    }
+    return 1;
+}
+
 // T == nullptr: the thresholds are chosen on the device (SURVEY Appendix A "threshold selection"): error histogram of
 // every unit -> smallest T whose estimate holds the payload -> embed -> units whose real capacity falls short get
 // T + 1 and are embedded again (only they), until every unit fits or has reached tmax.  The host only reads one
@@ -1698,6 +2091,7 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     bt.steps = ws->step_counters_on ? (unsigned long long*)ws->step_counters.ptr : nullptr;
     bt.active = active;
     if (!auto_T) {
+        if (try_cluster_embed(ws, g, bt, h, w, itemsize, bit_depth, st) == 0) return PEEB_OK;
         rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
         if (rc) return rc;
         PEEB_CUDA(cudaGetLastError());
@@ -1755,6 +2149,7 @@ int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, 
     // may come with a buffer that is only as long as its own payload (stride unused)
     const size_t pb0 = peeb_payload_bytes(n_bits[0]);
     const long long zero_words = (long long)((n_units == 1 && (size_t)payload_stride < pb0) ? pb0 : (size_t)payload_stride) / 4;
+    if (try_cluster_extract(ws, g, bt, h, w, itemsize, bit_depth, zero_words, st) == 0) return PEEB_OK;
     rc = PEEB_DISPATCH2(launch_extract2, ws, g, bt, nbands, stage_bits, stage_cnt, zero_words, st);
     if (rc) return rc;
     PEEB_CUDA(cudaGetLastError());

@@ -36,9 +36,17 @@ def _check_one(img, T, bd, frac, seed):
     assert np.array_equal(p1, pay), "payload differs"
 
 
+@pytest.fixture(params=["bands", "cluster"])
+def kernel_path(request, monkeypatch):
+    """Both families of PEE kernels: the band kernels (batches) and the cluster path for small images (one thread-block
+    cluster per image); PEEB_CLUSTER forces the choice where an image qualifies for both."""
+    monkeypatch.setenv("PEEB_CLUSTER", "1" if request.param == "cluster" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("bulk", [True, False])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_parity_shapes(shape, bulk):
+def test_parity_shapes(shape, bulk, kernel_path):
     _cabi.workspace().set_option("bulk", bulk)
     try:
         h, w = shape
@@ -51,7 +59,7 @@ def test_parity_shapes(shape, bulk):
         _cabi.workspace().set_option("bulk", True)
 
 
-def test_parity_reference_fixtures(golden_images):
+def test_parity_reference_fixtures(golden_images, kernel_path):
     for name, bd in (("pe", 12), ("pe", 16), ("torax", 8)):
         for T in (1, 4, 16):
             _check_one(golden_images[name], T, bd, 0.97, 7)
@@ -63,7 +71,7 @@ def test_parity_reference_fixtures(golden_images):
     assert info["n_flagged"] == 1127
 
 
-def test_full_capacity_and_empty_payload():
+def test_full_capacity_and_empty_payload(kernel_path):
     img = synth_image(96, 160, 4095, 9)
     for T in (1, 5):
         # a payload longer than any capacity, truncated to what fits: every carrier takes a real bit
@@ -145,7 +153,7 @@ def test_sweep_matches_oracle():
         assert g["mse"] == w_["mse"] and abs(g["psnr"] - w_["psnr"]) <= 1e-9 * abs(w_["psnr"])
 
 
-def test_batch_matches_oracle_per_unit():
+def test_batch_matches_oracle_per_unit(kernel_path):
     imgs = synth_batch(7, 130, 264, 4095, 40)
     Ts = np.array([1, 2, 3, 4, 5, 6, 7], np.int32)
     nb = np.array([0, 50, 400, 1000, 2000, 33, 777], np.int64)

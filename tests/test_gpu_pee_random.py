@@ -32,8 +32,14 @@ def _one(rng, h, w, bd, itemsize):
     assert np.array_equal(r1, img) and np.array_equal(p1, pay), (h, w, bd, T, n_bits)
 
 
+@pytest.fixture(params=["bands", "cluster"])
+def kernel_path(request, monkeypatch):
+    monkeypatch.setenv("PEEB_CLUSTER", "1" if request.param == "cluster" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("seed", range(6))
-def test_random_small_shapes(seed):
+def test_random_small_shapes(seed, kernel_path):
     rng = np.random.default_rng(seed)
     for _ in range(25):
         h, w = int(rng.integers(3, 90)), int(rng.integers(3, 400))
@@ -42,7 +48,7 @@ def test_random_small_shapes(seed):
 
 
 @pytest.mark.parametrize("w", [1024, 2048, 3000, 4096, 5000, 8192, 1000, 6001])
-def test_wide_rows(w):
+def test_wide_rows(w, kernel_path):
     rng = np.random.default_rng(w)
     for bd, itemsize in ((12, 2), (8, 1)):
         _one(rng, int(rng.integers(20, 70)), w, bd, itemsize)
