@@ -341,18 +341,44 @@ template <typename PixT> __device__ __forceinline__ void st8q(PixT* p, const uin
 // VEC: rows are 16-byte (8-bit pixels: 8-byte) aligned and w % 8 == 0: a lane streams its row through
 // two register queues (eight pixels in, eight out, the next block and location-map byte prefetched
 // one block ahead), so no memory latency sits on the wavefront's dependency chain.
+// Cluster form (CS = 2): the 32-row groups of an image are dealt to the warps of TWO CTAs (blocks of nwarps
+// consecutive groups per CTA), so that a few large images use twice as many SMs.  Every CTA keeps the whole ring of
+// line buffers; a group's last row is written into the shared memory of the CTA that runs the next group
+// (st.shared::cluster when that is the peer: one group in nwarps), which polls it locally as before.  The per-row
+// carrier counts go to both CTAs, which then share the rows of the final concatenation.  CS = 1 is the plain launch.
+__device__ __forceinline__ unsigned med_cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void med_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned med_peer_addr(const void* own, unsigned cta) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(own)), "r"(cta));
+    return remote;
+}
+__device__ __forceinline__ void st_peer_v4(unsigned addr, const uint4& v) {
+    asm volatile("st.volatile.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_peer_u32(unsigned addr, unsigned v) {
+    asm volatile("st.volatile.shared::cluster.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+
 template <typename PixT, bool VEC>
-__global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits) {
+__global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt, unsigned* __restrict__ stage_bits, int CS) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const MedSmem L = med_layout(g, nwarps);
+    const int rank = CS > 1 ? (int)med_cluster_rank() : 0, allwarps = CS * nwarps;
+    const MedSmem L = med_layout(g, allwarps);
     // line buffers: one 32-bit entry per column = recovered value | tag << 16.  The tag (group + 2; row 0:
     // 1; never written: 0) makes an entry its own "ready" flag, so handing a row to the next group needs
     // neither a fence nor a separate progress counter.
     unsigned* line = reinterpret_cast<unsigned*>(smem_raw + L.line);
     int* rowoff = reinterpret_cast<int*>(smem_raw + L.rowoff);
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
-    const int unit = blockIdx.x, h = g.h, w = g.w, nslot = nwarps + 1;
+    const int unit = blockIdx.x / CS, h = g.h, w = g.w, nslot = allwarps + 1;
     const PixT* marked = reinterpret_cast<const PixT*>(bt.src + (long long)unit * bt.src_stride);
     PixT* rec = bt.dst ? reinterpret_cast<PixT*>(bt.dst + (long long)unit * bt.dst_stride) : nullptr;
     const unsigned char* lm = bt.lm + (long long)unit * bt.lm_stride;
@@ -365,12 +391,13 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
     for (int j = threadIdx.x; j < w; j += blockDim.x) {
         const unsigned v = marked[j];
         line[(size_t)(nslot - 1) * w + j] = v | (1u << 16);
-        if (rec) rec[j] = (PixT)v;
+        if (rec && rank == 0) rec[j] = (PixT)v;
     }
     __syncthreads();
+    if (CS > 1) med_cluster_sync();  // the peer's line buffers are cleared before anything is written into them
 
     const int ngroups = (h - 1 + 31) / 32;
-    for (int grp = warp; grp < ngroups; grp += nwarps) {
+    for (int grp = rank * nwarps + warp; grp < ngroups; grp += allwarps) {
         const int rowi = 1 + 32 * grp + lane;
         const bool valid = rowi < h;
         const int rowc = valid ? rowi : 1;
@@ -383,6 +410,11 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
         const volatile unsigned* upline = line + (size_t)((grp + nslot - 1) % nslot) * w;
         const unsigned mytag = (unsigned)(grp + 2) << 16, uptag = (unsigned)(grp + 1);
         const bool writer = lane == lastl;
+        // the next group runs in the CTA of warp (grp + 1) mod allwarps: its copy of this group's line is written
+        const int cons = ((grp + 1) % allwarps) / nwarps;
+        const bool remote = cons != rank;
+        const unsigned peerline = remote ? med_peer_addr(const_cast<const unsigned*>(myline), (unsigned)cons) : 0u;
+        const unsigned peeroff = CS > 1 ? med_peer_addr(rowoff, (unsigned)(rank ^ 1)) : 0u;
         if (VEC) {
             // ---- four columns per lane and step (skew of four columns per lane): the step overhead -- shuffles,
             // the poll of the line above, queue handling, loop control -- is paid once per four pixels.
@@ -453,7 +485,8 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
                     if (writer) {
                         uint4 e;
                         e.x = (unsigned)vals[0] | mytag; e.y = (unsigned)vals[1] | mytag; e.z = (unsigned)vals[2] | mytag; e.w = (unsigned)vals[3] | mytag;
-                        sts128_volatile(const_cast<unsigned*>(myline) + jb, e);
+                        if (remote) st_peer_v4(peerline + 4u * (unsigned)jb, e);
+                        else sts128_volatile(const_cast<unsigned*>(myline) + jb, e);
                     }
                     if (!second) { oA = curA; oB = curB; }
                     else {  // block of eight done: write it, switch to the prefetched one, fetch the one after
@@ -468,6 +501,7 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
             if (valid) {
                 if (nW) *srow = (unsigned)(Wq << (32 - nW));
                 rowoff[rowi] = ncar;
+                if (CS > 1) st_peer_u32(peeroff + 4u * (unsigned)rowi, (unsigned)ncar);
             }
             continue;
         }
@@ -513,7 +547,10 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
                     }
                 }
                 cur2 = cur1; cur1 = val; aprev = val;
-                if (writer) myline[j] = (unsigned)val | mytag;
+                if (writer) {
+                    if (remote) st_peer_u32(peerline + 4u * (unsigned)j, (unsigned)val | mytag);
+                    else myline[j] = (unsigned)val | mytag;
+                }
                 if (VEC) {
                     o.x = __funnelshift_r(o.x, o.y, 16); o.y = __funnelshift_r(o.y, o.z, 16);
                     o.z = __funnelshift_r(o.z, o.w, 16); o.w = (o.w >> 16) | ((unsigned)val << 16);
@@ -530,21 +567,23 @@ __global__ void __launch_bounds__(512) med_extract_kernel(MedGeom g, PeeBatch bt
         if (valid) {
             if (nW) *srow = W << (32 - nW);
             rowoff[rowi] = ncar;
+            if (CS > 1) st_peer_u32(peeroff + 4u * (unsigned)rowi, (unsigned)ncar);
         }
     }
     __syncthreads();
+    if (CS > 1) med_cluster_sync();  // both CTAs now hold every row's count; the staged bits are visible to the peer
 
     // ---- concatenate the rows' bit streams (raster order) into the unit's payload, MSB-first
     const int total = block_excl_scan(rowoff, h, misc);
     __syncthreads();
     const long long n_bits = bt.n_bits[unit];
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && rank == 0) {
         long long* info = bt.info + (long long)unit * PEEB_INFO;
         info[0] = T; info[1] = n_bits; info[2] = total; info[3] = total; info[4] = 0; info[5] = 0; info[6] = 0;
         info[7] = n_bits > total ? PEEB_E_CAPACITY : 0;
     }
     unsigned* out = reinterpret_cast<unsigned*>(bt.payload_out + (long long)unit * bt.payload_stride);
-    for (int r = 1 + warp; r < h; r += nwarps) {
+    for (int r = 1 + rank * nwarps + warp; r < h; r += allwarps) {
         const long long before = rowoff[r];
         const int cnt = (r + 1 < h ? rowoff[r + 1] : total) - rowoff[r];
         if (cnt == 0 || before >= n_bits) continue;
@@ -671,7 +710,17 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
     if (const char* e = getenv("PEEB_MED_WARPS")) maxw = std::max(1, std::min(16, atoi(e)));
     int nwarps = std::max(1, std::min(maxw, (h - 1 + 31) / 32));
     while (nwarps > 1 && med_layout(g, nwarps).total > (size_t)ws->max_smem_optin) nwarps /= 2;
-    const size_t smem = med_layout(g, nwarps).total;
+    // few large images: two CTAs (a cluster) per image, the same ring of line buffers in each; up to 32 warps per image
+    // when the lines are short enough
+    int CS = (2 * n_units <= ws->sm_count && nwarps >= 8) ? 2 : 1;
+    if (const char* e = getenv("PEEB_MED_CLUSTER")) CS = atoi(e) == 2 ? 2 : 1;
+    int allwarps = nwarps;
+    if (CS == 2) {
+        const int want = std::min(32, (h - 1 + 31) / 32);
+        while (allwarps * 2 <= want && med_layout(g, allwarps * 2).total <= (size_t)ws->max_smem_optin) allwarps *= 2;
+        if (allwarps < 2) CS = 1; else nwarps = allwarps / 2;
+    }
+    const size_t smem = med_layout(g, CS * nwarps).total;
     PEEB_REQUIRE(smem <= (size_t)ws->max_smem_optin, "peeb_pee_med_extract_batch: image %dx%d needs more shared memory than one SM has", h, w);
     // vector path: every row of every unit starts on a 16-byte (8-bit pixels: 8-byte) boundary
     const uintptr_t al = 8 * (uintptr_t)itemsize - 1;
@@ -681,7 +730,14 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
 #define PEEB_MED_LAUNCH(PIXT, VEC)                                                                                          \
     do {                                                                                                                    \
         PEEB_CUDA(cudaFuncSetAttribute(med_extract_kernel<PIXT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        med_extract_kernel<PIXT, VEC><<<n_units, nwarps * 32, smem, st>>>(g, bt, (unsigned*)ws->pbits[0].ptr);                \
+        cudaLaunchConfig_t cfg{};                                                                                           \
+        cfg.gridDim = dim3((unsigned)(n_units * CS)); cfg.blockDim = dim3((unsigned)(nwarps * 32));                         \
+        cfg.dynamicSmemBytes = smem; cfg.stream = st;                                                                       \
+        cudaLaunchAttribute attr{};                                                                                         \
+        attr.id = cudaLaunchAttributeClusterDimension;                                                                      \
+        attr.val.clusterDim.x = (unsigned)CS; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;                         \
+        cfg.attrs = &attr; cfg.numAttrs = 1;                                                                                \
+        PEEB_CUDA(cudaLaunchKernelEx(&cfg, med_extract_kernel<PIXT, VEC>, g, bt, (unsigned*)ws->pbits[0].ptr, CS));         \
     } while (0)
     if (itemsize == 2) { if (vec) PEEB_MED_LAUNCH(unsigned short, true); else PEEB_MED_LAUNCH(unsigned short, false); }
     else { if (vec) PEEB_MED_LAUNCH(unsigned char, true); else PEEB_MED_LAUNCH(unsigned char, false); }

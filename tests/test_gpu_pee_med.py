@@ -19,8 +19,16 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["one_cta", "cluster_of_two"])
+def extract_form(request, monkeypatch):
+    """The wavefront extract as one CTA per image and as a cluster of two CTAs per image (line buffers handed over
+    through distributed shared memory); PEEB_MED_CLUSTER forces the form."""
+    monkeypatch.setenv("PEEB_MED_CLUSTER", "2" if request.param == "cluster_of_two" else "1")
+    return request.param
+
+
 @pytest.mark.parametrize("idx", range(len(CASES)))
-def test_med_gpu_vs_oracle(idx):
+def test_med_gpu_vs_oracle(idx, extract_form):
     img, bd, T = CASES[idx]
     pay = random_payload(img.size, 200 + idx)
     cap = pee_c.embed(img, pay, img.size, T, bd, predictor="med")[2]["capacity"]
@@ -53,7 +61,7 @@ def test_med_embed_multi_row_items(rows, monkeypatch):
         assert np.array_equal(rec, img) and np.array_equal(np.unpackbits(out)[:cap], np.unpackbits(pay)[:cap])
 
 
-def test_med_batch_and_auto_threshold():
+def test_med_batch_and_auto_threshold(extract_form):
     imgs = synth_batch(5, 96, 160, 4095, 31)
     pays = np.stack([random_payload(imgs[0].size, 70 + k) for k in range(5)])
     nb = np.array([0, 100, 2000, 2900, 50], np.int64)
