@@ -712,7 +712,9 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
     while (nwarps > 1 && med_layout(g, nwarps).total > (size_t)ws->max_smem_optin) nwarps /= 2;
     // few large images: two CTAs (a cluster) per image, the same ring of line buffers in each; up to 32 warps per image
     // when the lines are short enough
-    int CS = (2 * n_units <= ws->sm_count && nwarps >= 8) ? 2 : 1;
+    // (measured, scripts/bench_med.py: 64 radiographs of 3000x3000 6.23 -> 5.26 ms; 16 images of 1024x1024 0.95 -> 0.98 ms:
+    // only large images take it)
+    int CS = (2 * n_units <= ws->sm_count && nwarps >= 8 && (long long)h * w >= (4ll << 20)) ? 2 : 1;
     if (const char* e = getenv("PEEB_MED_CLUSTER")) CS = atoi(e) == 2 ? 2 : 1;
     int allwarps = nwarps;
     if (CS == 2) {
