@@ -321,7 +321,12 @@ def _tile_argmax_from_moments(plane, sbs, sums, shape=None):
     tw = np.minimum(sbs, w - np.arange(tx) * sbs)
     npx = (th[:, None] * tw[None, :]).reshape(-1).astype(np.int64)
     s1, s2 = sums[:, 0], sums[:, 1]
-    approx = (npx.astype(np.float64) * s2 - s1.astype(np.float64) ** 2) / (npx.astype(np.float64) ** 2)
+    if float(npx.max()) * float(s2.max() if s2.size else 0) < 2.0 ** 52:
+        approx = (npx.astype(np.float64) * s2 - s1.astype(np.float64) ** 2) / (npx.astype(np.float64) ** 2)
+    else:
+        # n * sum(v^2) no longer fits a float64 mantissa (16-bit planes with large tiles): the difference would cancel
+        # to less than the shortlist's margin, so the scores are the correctly rounded exact rationals
+        approx = np.array([float(Fraction(int(n) * int(q) - int(a) ** 2, int(n) ** 2)) for n, a, q in zip(npx, s1, s2)])
     top = approx.max()
     short = np.flatnonzero(approx >= top - abs(top) * 1e-9 - 1e-300)
     # exact values once per distinct (n, sum, sum of squares)
@@ -525,7 +530,7 @@ def extract_message(stego_array, metadata, device=None):
 
 # ------------------------------------------------------------------ the reference's encode flow, device resident
 def embed_pipeline(image_array, message_bits, beta=0.8, search_block_size=16, align_across_planes=False,
-                   hybrid=True, nbits=None, device=None):
+                   hybrid=True, nbits=None, device=None, bitmaps_as=None):
     """Steps 3-5 of the reference's ``main()`` (src/codec.py:868-880) in one call:
     ``adaptive_modalities_decomposition`` -> ``lsb_embed_block_then_multiplane`` (or
     ``lsb_embed_multi_plane`` with ``hybrid=False``) -> ``merge_modalities``, with the bit planes
@@ -534,7 +539,14 @@ def embed_pipeline(image_array, message_bits, beta=0.8, search_block_size=16, al
 
     -> ``(stego_image, bitmaps (s, h, w) uint8, meta)`` with ``meta = {'s', 'segments_lengths',
     'segments_indices', 'total_used', 'start_offset'}`` (what ``create_header`` needs, :895-905).
+
+    ``bitmaps_as="pbr"``: the bitmaps come back as the "PBR1" blob ``container.pack_bitmaps(...,
+    coding="pbr")`` would make of them (step 7 of ``main()``, src/codec.py:887-889, folded in): they are coded
+    where they are, in device memory, and only the blob -- a few kilobytes for a text message instead of
+    ``s * h * w`` bytes -- crosses PCIe.  ``container.unpack_bitmaps(blob, s)`` restores the arrays.
     """
+    if bitmaps_as not in (None, "pbr"):
+        raise ValueError("bitmaps_as must be None or 'pbr'")
     img = _cabi.as_image(image_array, "image_array")
     if img.ndim != 2:
         raise ValueError("A imagem deve ser 2D (grayscale).")  # src/codec.py:34
@@ -605,7 +617,16 @@ def embed_pipeline(image_array, message_bits, beta=0.8, search_block_size=16, al
     d_stego = _cabi.DeviceBuffer(ws, npx * out_dtype().itemsize)
     check(L.peeb_planes_pack(ws.handle, d_out.ptr, npx, item, nb, d_stego.ptr, st), "peeb_planes_pack")
     stego = d_stego.download(np.empty((h, w), out_dtype))
-    bitmaps = d_bm.download(np.empty((s, h, w), np.uint8))
+    if bitmaps_as == "pbr":
+        import ctypes as C
+        cap = int(L.peeb_bitmap_blob_bound(s * npx))
+        d_blob = _cabi.DeviceBuffer(ws, cap)
+        got = C.c_int64(0)
+        check(L.peeb_bitmap_encode(ws.handle, d_bm.ptr, s * npx, 0, d_blob.ptr, cap, C.byref(got), st), "peeb_bitmap_encode")
+        bitmaps = d_blob.download(np.empty(got.value, np.uint8)).tobytes()
+        d_blob.free()
+    else:
+        bitmaps = d_bm.download(np.empty((s, h, w), np.uint8))
     for b in (d_img, d_hist, d_planes, d_pay, d_out, d_bm, d_stego):
         b.free()
     meta = {"s": s, "segments_lengths": sizes if hybrid else [int(v) for v in lens],

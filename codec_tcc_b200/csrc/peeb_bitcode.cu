@@ -9,10 +9,11 @@
 //
 //   L0[j]  32 elements per 32-bit word, bytes in np.packbits order (element 32j+8k+i -> bit 7-i of byte k)
 //   L1[i]  bit t (LSB first) = (L0[32i+t] != 0)           L2[k]  bit t = (L1[32k+t] != 0)
-//   blob = "PBR1" | u32 0 | u64 n | u32 nz1 | u32 nz0 | L2[all] | non-zero L1 words | non-zero L0 words   (LE)
+//   C0[k]  number of non-zero L0 words under L2[k] (<= 1024): lets the decoder find every CTA's words with one scan
+//   blob = "PBR1" | u32 0 | u64 n | u32 nz1 | u32 nz0 | L2[all] | C0[all] | non-zero L1 words | non-zero L0 words   (LE)
 //
-// A run of 1024 zero elements costs one bit, a run of 32768 nothing; a dense random map costs n/8 * (1 + 1/32
-// + 1/1024) bytes.  One CTA of 1024 threads owns one L2 word = 32768 elements: warp ballots give L1 and L2,
+// A run of 1024 zero elements costs one bit, a run of 32768 eight bytes; a dense random map costs n/8 * (1 + 1/32
+// + 1/512) bytes.  One CTA of 1024 threads owns one L2 word = 32768 elements: warp ballots give L1 and L2,
 // the two compactions take one small scan over the CTAs' counts.  HBM-bound: the encoder reads one byte per
 // element (or one bit, for maps that are already packed such as the PEE location map) and writes <= 1/8.
 // (The CPU restatement the tests check this against lives with the test infrastructure.)
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(PBR_CTA) pbr_pack_kernel(const unsigned char* 
         for (int o = 16; o > 0; o >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, o);
         if (lane == 0) {
             l2[b] = p2;
+            l2[gridDim.x + b] = (unsigned)c0;   // C0 follows L2 in the blob (gridDim.x = number of L2 words)
             counts[b] = make_int2(__popc(p2), c0);
         }
     }
@@ -158,8 +160,8 @@ __global__ void __launch_bounds__(PBR_CTA) pbr_compact_kernel(const unsigned* __
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int2 off = offs[b];
     const unsigned nz1 = totals[0];
-    unsigned* out1 = body + n2;
-    unsigned* out0 = body + n2 + nz1;
+    unsigned* out1 = body + 2 * n2;
+    unsigned* out0 = body + 2 * n2 + nz1;
     const unsigned mine = (b * 32 + lane < n1) ? l1[b * 32 + lane] : 0u;  // lane k: L1 word k of this CTA
     int before = lane < warp ? __popc(mine) : 0;                          // non-zero L0 words of the warps before this one
 #pragma unroll
@@ -173,49 +175,37 @@ __global__ void __launch_bounds__(PBR_CTA) pbr_compact_kernel(const unsigned* __
     }
 }
 
-// D1 (one CTA): per L2 word, where its non-zero L1 words and their non-zero L0 words start; err = totals disagree
+// D1 (one CTA): per L2 word, where its non-zero L1 words and their non-zero L0 words start = exclusive scans of
+// popc(L2[k]) and C0[k]; err = the totals disagree with the header
 __global__ void __launch_bounds__(1024) pbr_plan_kernel(const unsigned* __restrict__ body, long long n2, unsigned nz1,
                                                         unsigned nz0, int2* __restrict__ offs, int* __restrict__ err) {
-    __shared__ unsigned s_w[32];
+    __shared__ unsigned s_w[2][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned* nzl1 = body + n2;
-    for (int pass = 0; pass < 2; ++pass) {
-        unsigned carry = 0;
-        for (long long base = 0; base < n2; base += 1024) {
-            const long long k = base + threadIdx.x;
-            unsigned c = 0;
-            if (k < n2) {
-                if (pass == 0) c = __popc(body[k]);
-                else {
-                    const unsigned o1 = (unsigned)offs[k].x, m = __popc(body[k]);
-                    for (unsigned q = 0; q < m; ++q)
-                        if (o1 + q < nz1) c += __popc(nzl1[o1 + q]);
-                }
-            }
-            unsigned incl = c;
+    unsigned carry1 = 0, carry0 = 0;
+    for (long long base = 0; base < n2; base += 1024) {
+        const long long k = base + threadIdx.x;
+        const unsigned c1 = k < n2 ? (unsigned)__popc(body[k]) : 0u;
+        unsigned c0 = k < n2 ? body[n2 + k] : 0u;
+        if (c0 > 1024u) { *err = 1; c0 = 0u; }
+        unsigned i1 = c1, i0 = c0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (lane == 31) s_w[warp] = incl;
-            __syncthreads();
-            unsigned bsum = 0, tsum = 0;
-            for (int q = 0; q < 32; ++q) {
-                const unsigned a = s_w[q];
-                if (q < warp) bsum += a;
-                tsum += a;
-            }
-            if (k < n2) {
-                if (pass == 0) offs[k].x = (int)(carry + bsum + incl - c);
-                else offs[k].y = (int)(carry + bsum + incl - c);
-            }
-            carry += tsum;
-            __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t1 = __shfl_up_sync(0xffffffffu, i1, o), t0 = __shfl_up_sync(0xffffffffu, i0, o);
+            if (lane >= o) { i1 += t1; i0 += t0; }
         }
-        if (threadIdx.x == 0 && carry != (pass == 0 ? nz1 : nz0)) *err = 1;
+        if (lane == 31) { s_w[0][warp] = i1; s_w[1][warp] = i0; }
+        __syncthreads();
+        unsigned b1 = 0, b0 = 0, t1 = 0, t0 = 0;
+        for (int q = 0; q < 32; ++q) {
+            const unsigned a1 = s_w[0][q], a0 = s_w[1][q];
+            if (q < warp) { b1 += a1; b0 += a0; }
+            t1 += a1; t0 += a0;
+        }
+        if (k < n2) offs[k] = make_int2((int)(carry1 + b1 + i1 - c1), (int)(carry0 + b0 + i0 - c0));
+        carry1 += t1; carry0 += t0;
         __syncthreads();
     }
+    if (threadIdx.x == 0 && (carry1 != nz1 || carry0 != nz0)) *err = 1;
 }
 
 // D2: one CTA per L2 word -> its 32768 elements as 0/1 bytes or as packed bits
@@ -226,8 +216,8 @@ __global__ void __launch_bounds__(PBR_CTA) pbr_expand_kernel(const unsigned* __r
                                                              int* __restrict__ err) {
     const long long b = blockIdx.x, j = b * PBR_CTA + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned* nzl1 = body + n2;
-    const unsigned* nzl0 = body + n2 + nz1;
+    const unsigned* nzl1 = body + 2 * n2;
+    const unsigned* nzl0 = body + 2 * n2 + nz1;
     const unsigned p2 = body[b];
     const int2 off = offs[b];
     unsigned mine = 0;  // lane k: L1 word k of this CTA
@@ -235,9 +225,13 @@ __global__ void __launch_bounds__(PBR_CTA) pbr_expand_kernel(const unsigned* __r
         const unsigned at = (unsigned)off.x + __popc(p2 & lanemask_lt());
         if (at < nz1) mine = nzl1[at]; else *err = 1;
     }
-    int before = lane < warp ? __popc(mine) : 0;
+    int before = lane < warp ? __popc(mine) : 0, all = __popc(mine);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        all += __shfl_xor_sync(0xffffffffu, all, o);
+    }
+    if (threadIdx.x == 0 && (unsigned)all != body[n2 + b]) *err = 1;  // the count the offsets were built from
     const unsigned p1 = __shfl_sync(0xffffffffu, mine, warp);
     unsigned w = 0;
     if ((p1 >> lane) & 1u) {
@@ -275,7 +269,7 @@ static int parse_header(const unsigned char* h, int64_t blob_bytes, int64_t n, P
     sz = pbr_sizes(n);
     nz1 = f[4]; nz0 = f[5];
     PEEB_REQUIRE((long long)nz1 <= sz.n1 && (long long)nz0 <= sz.n0, "peeb_bitmap_decode: corrupt header");
-    PEEB_REQUIRE(blob_bytes == PBR_HEADER + 4 * (sz.n2 + (long long)nz1 + (long long)nz0),
+    PEEB_REQUIRE(blob_bytes == PBR_HEADER + 4 * (2 * sz.n2 + (long long)nz1 + (long long)nz0),
                  "peeb_bitmap_decode: blob size %lld does not match its header", (long long)blob_bytes);
     return PEEB_OK;
 }
@@ -320,7 +314,7 @@ extern "C" {
 size_t peeb_bitmap_blob_bound(int64_t n) {
     if (n < 0) n = 0;
     const PbrSizes sz = pbr_sizes(n);
-    return (size_t)PBR_HEADER + 4 * (size_t)(sz.n2 + sz.n1 + sz.n0);
+    return (size_t)PBR_HEADER + 4 * (size_t)(2 * sz.n2 + sz.n1 + sz.n0);
 }
 
 int peeb_bitmap_encode(peeb_ws* ws, const uint8_t* src, int64_t n, int packed_input, uint8_t* blob,
@@ -364,7 +358,7 @@ int peeb_bitmap_encode(peeb_ws* ws, const uint8_t* src, int64_t n, int packed_in
     PEEB_CUDA(cudaGetLastError());
     PEEB_CUDA(cudaMemcpyAsync(totals_h, totals, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     PEEB_CUDA(cudaStreamSynchronize(st));
-    *blob_bytes = PBR_HEADER + 4 * (sz.n2 + (int64_t)totals_h[0] + (int64_t)totals_h[1]);
+    *blob_bytes = PBR_HEADER + 4 * (2 * sz.n2 + (int64_t)totals_h[0] + (int64_t)totals_h[1]);
     return PEEB_OK;
 }
 

@@ -126,13 +126,15 @@ __global__ void __launch_bounds__(1024) hist16_kernel(const unsigned char* __res
     if (!packed) flush();
 }
 
-// plane_ones[b] = sum over values v with bit b set of hist[v]  (one block)
+// plane_ones[b] += sum over values v with bit b set of hist[v]; one CTA per 1024 bins (plane_ones zeroed by the caller;
+// the first version walked all 65 536 bins with one CTA: 77 us, the longest launch of a small call)
 __global__ void __launch_bounds__(256) hist_to_planes_kernel(const unsigned* __restrict__ hist, int nbins,
                                                              unsigned long long* __restrict__ plane_ones) {
     unsigned long long acc[16];
 #pragma unroll
     for (int b = 0; b < 16; ++b) acc[b] = 0;
-    for (int v = threadIdx.x; v < nbins; v += blockDim.x) {
+    const int v_end = min(nbins, ((int)blockIdx.x + 1) * 1024);
+    for (int v = (int)blockIdx.x * 1024 + threadIdx.x; v < v_end; v += blockDim.x) {
         const unsigned long long c = hist[v];
 #pragma unroll
         for (int b = 0; b < 16; ++b) acc[b] += ((v >> b) & 1) ? c : 0ull;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) hist_to_planes_kernel(const unsigned* __r
     if (threadIdx.x < 16) {
         unsigned long long t = 0;
         for (int k = 0; k < 8; ++k) t += sm[threadIdx.x][k];
-        plane_ones[threadIdx.x] = t;
+        if (t) atomicAdd(plane_ones + threadIdx.x, t);
     }
 }
 
@@ -173,7 +175,8 @@ static int launch_hist(peeb_ws* ws, const void* img, int64_t n, int itemsize, ui
                 hist_kernel<1><<<grid, 256, smem, st>>>((const unsigned char*)img, n, win, hist);
             }
         }
-        hist_to_planes_kernel<<<1, 256, 0, st>>>(hist, nbins, (unsigned long long*)ones);
+        PEEB_CUDA(cudaMemsetAsync(ones, 0, 16 * sizeof(uint64_t), st));
+        hist_to_planes_kernel<<<(nbins + 1023) / 1024, 256, 0, st>>>(hist, nbins, (unsigned long long*)ones);
     }
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;

@@ -8,9 +8,10 @@ bit-packed / run-length format of its own, so the FORMAT is this repository's (p
 is unpinned); what is pinned is the round trip: decode(encode(m)) equals the reference's own
 bitmaps on the golden cases (tests/test_bitcode.py).
 
-Layout (little endian):  b"PBR1" | u32 0 | u64 n | u32 nz1 | u32 nz0 | L2 | non-zero L1 | non-zero L0
+Layout (little endian):  b"PBR1" | u32 0 | u64 n | u32 nz1 | u32 nz0 | L2 | C0 | non-zero L1 | non-zero L0
   L0[j]  32 elements per word, bytes as np.packbits makes them
   L1[i]  bit t (LSB first) = L0[32 i + t] != 0;   L2[k] likewise over L1
+  C0[k]  number of non-zero L0 words among the 1024 under L2[k] (one scan then places every block's words)
 Only product code path allowed to import this module: none (tests, smoke and bench checks only).
 """
 from __future__ import annotations
@@ -49,7 +50,10 @@ def encode(elements, packed: bool = False, n: int | None = None) -> bytes:
     l1 = _presence(l0)
     l2 = _presence(l1)
     nz1, nz0 = l1[l1 != 0], l0[l0 != 0]
-    return (MAGIC + struct.pack("<IQII", 0, n, nz1.size, nz0.size) + l2.astype("<u4").tobytes()
+    per_block = np.zeros(l2.size * 1024, np.uint32)
+    per_block[:l0.size] = l0 != 0
+    c0 = per_block.reshape(-1, 1024).sum(axis=1).astype("<u4") if l2.size else np.zeros(0, "<u4")
+    return (MAGIC + struct.pack("<IQII", 0, n, nz1.size, nz0.size) + l2.astype("<u4").tobytes() + c0.tobytes()
             + nz1.astype("<u4").tobytes() + nz0.astype("<u4").tobytes())
 
 
@@ -72,12 +76,16 @@ def decode(blob: bytes, n: int, packed: bool = False) -> np.ndarray:
     n0 = (n + 31) // 32
     n1 = (n0 + 31) // 32
     n2 = (n1 + 31) // 32
-    if len(blob) != HEADER + 4 * (n2 + c1 + c0):
+    if len(blob) != HEADER + 4 * (2 * n2 + c1 + c0):
         raise ValueError("PBR1 blob size mismatch")
     body = np.frombuffer(blob, "<u4", offset=HEADER)
-    l2, nz1, nz0 = body[:n2], body[n2:n2 + c1], body[n2 + c1:]
+    l2, cnt, nz1, nz0 = body[:n2], body[n2:2 * n2], body[2 * n2:2 * n2 + c1], body[2 * n2 + c1:]
     l1 = _expand(l2, nz1, n1)
     l0 = _expand(l1, nz0, n0)
+    per_block = np.zeros(n2 * 1024, np.uint32)
+    per_block[:n0] = l0 != 0
+    if n2 and not np.array_equal(per_block.reshape(-1, 1024).sum(axis=1), cnt):
+        raise ValueError("corrupt PBR1 blob: block counts disagree")
     by = l0.astype("<u4").view(np.uint8)
     if packed:
         return by[:(n + 7) // 8].copy()

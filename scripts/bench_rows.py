@@ -164,6 +164,36 @@ rows.append({"row": "a5-a8", "kernel": "hist + planes_unpack + tile_moments + ls
              "api": "codec.embed_pipeline (numpy image + '0'/'1' string in, stego image + uint8 bitmaps out) against the chained "
                     "restatements of adaptive_modalities_decomposition, lsb_embed_block_then_multiplane, merge_modalities; outputs equal"})
 
+# ---- N2: the same flow with the bitmaps coded on the device (PBR1 blob instead of s*h*w bytes over PCIe), beside the
+# reference's zlib blob step on the host (src/codec.py:887-889)
+import zlib  # noqa: E402
+from codec_tcc_b200 import container  # noqa: E402
+from oracle import bitcode_numpy as BN  # noqa: E402
+t_api = wall(lambda: codec.embed_pipeline(imgs[0], bits, beta=0.8, search_block_size=16, bitmaps_as="pbr"), reps=2)
+_, blob, _ = codec.embed_pipeline(imgs[0], bits, beta=0.8, search_block_size=16, bitmaps_as="pbr")
+assert blob == BN.encode(p_bm) and all(np.array_equal(a, b.ravel()) for a, b in zip(container.unpack_bitmaps(blob, len(p_bm)), p_bm))
+t0 = time.perf_counter(); zb = zlib.compress(np.stack(p_bm).tobytes()); t_z = time.perf_counter() - t0
+rows.append({"row": "a5-a8 + N2", "kernel": "... + pbr_pack / pbr_scan / pbr_compact (bitmaps coded in device memory)",
+             "workload": f"3000x3000 u16 (12-bit), {pay_bits / 1e6:.1f} Mbit payload, s={s}", "api_ms": t_api * 1e3,
+             "api_mpixel_s": npx / t_api / 1e6, "blob_bytes": len(blob), "zlib_blob_bytes": len(zb), "cpu_zlib_ms": t_z * 1e3,
+             "api": "codec.embed_pipeline(bitmaps_as='pbr'): stego image + PBR1 blob out; the blob decodes to the plain call's bitmaps; "
+                    "cpu_zlib_ms = the reference's zlib.compress(np.stack(bitmaps).tobytes()) on these bitmaps, 1 core"})
+d_maps = torch.from_numpy(np.stack(p_bm).reshape(-1)).to(dev)
+d_blob = torch.empty(int(L.peeb_bitmap_blob_bound(d_maps.numel())), dtype=torch.uint8, device=dev)
+from codec_tcc_b200 import device as D  # noqa: E402
+ws.prof_enable(True)
+for _ in range(5):
+    bl = D.bitmap_encode_device(d_maps, blob=d_blob)
+    D.bitmap_decode_device(bl, d_maps.numel())
+torch.cuda.synchronize()
+prof = ws.prof_report(); ws.prof_enable(False)
+for key, label in (("bitmap_encode", "pbr_pack + pbr_scan + pbr_compact"), ("bitmap_decode", "pbr_plan + pbr_expand")):
+    ms = prof[key][0] / prof[key][1]
+    rows.append({"row": "N2", "kernel": label, "workload": f"s={s} bitmaps of 3000x3000 ({d_maps.numel() / 1e6:.0f} MB, one byte per element)",
+                 "device_ms": ms, "algorithmic_gb_s": d_maps.numel() * 1.125 / 1e9 / (ms * 1e-3),
+                 "frac_of_measured_peak": d_maps.numel() * 1.125 / 1e9 / (ms * 1e-3) / peak,
+                 "note": "algorithmic bytes: one byte per element read (written for decode) + at most one bit per element on the other side"})
+
 # ---- a9: decode_message
 meta = {"s": s, "segments_indices": got[4], "segments_lengths": got[3]}
 t_api = wall(lambda: codec.decode_message(got[0], got[1], meta), reps=1)

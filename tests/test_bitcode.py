@@ -35,14 +35,15 @@ def test_oracle_round_trip_and_forms():
 
 def test_oracle_format_known_answers():
     # an empty map of 36 M elements is its header + the top level only
-    assert len(BN.encode(np.zeros(36_000_000, np.uint8))) == 24 + 4 * 1099
-    # one set element: header, L2 (1 word), one L1 word, one L0 word; element 9 = bit 6 of packed byte 1
+    assert len(BN.encode(np.zeros(36_000_000, np.uint8))) == 24 + 4 * 2 * 1099
+    # one set element: header, L2 (1 word), C0 (1 word: one non-zero L0 word), one L1 word, one L0 word;
+    # element 9 = bit 6 of packed byte 1
     blob = BN.encode(np.eye(1, 40, 9, dtype=np.uint8))
     assert blob == b"PBR1" + bytes(4) + (40).to_bytes(8, "little") + (1).to_bytes(4, "little") * 2 \
-        + (1).to_bytes(4, "little") + (1).to_bytes(4, "little") + (0x4000).to_bytes(4, "little")
+        + (1).to_bytes(4, "little") + (1).to_bytes(4, "little") + (1).to_bytes(4, "little") + (0x4000).to_bytes(4, "little")
     a = _map(70_001, 0.01, 5)
     frozen = BN.encode(a)   # frozen with the first version of the format: a change of layout must be deliberate
-    assert len(frozen) == 2852 and hashlib.sha256(frozen).hexdigest()[:16] == "257855928b3365b8"
+    assert len(frozen) == 2864 and hashlib.sha256(frozen).hexdigest()[:16] == "b4e7fc60f53caa49"
     with pytest.raises(ValueError):
         BN.decode(blob[:-4], 40)
     with pytest.raises(ValueError):
@@ -151,6 +152,10 @@ def test_gpu_decoder_refuses_corrupt_blobs():
         container.decode_bitmap(b"ZLIB" + bytes(blob[4:]), 100_000)
     bad = bytearray(blob)
     bad[24] ^= 0xFF          # the top level no longer matches the counts in the header
+    with pytest.raises(ValueError):
+        container.decode_bitmap(bytes(bad), 100_000)
+    bad = bytearray(blob)
+    bad[24 + 4 * 4] ^= 0x01  # a block count (C0) that disagrees with the level-1 words
     with pytest.raises(ValueError):
         container.decode_bitmap(bytes(bad), 100_000)
     assert np.array_equal(container.decode_bitmap(bytes(blob), 100_000), (a != 0).astype(np.uint8))

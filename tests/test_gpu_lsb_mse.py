@@ -266,3 +266,32 @@ def test_true_inverse_vs_restatement(idx):
     if used == 8 * len(msg):  # message_to_bits is one byte per character (src/codec.py:239-240): latin-1 text only
         text = codec.extract_message(codec.merge_modalities(g, sp).astype(img.dtype), {"s": s, "segments_indices": order, "segments_lengths": lens})
         assert text.encode("utf-8", errors="replace") is not None
+
+
+def test_embed_pipeline_with_device_coded_bitmaps(golden_images):
+    """bitmaps_as="pbr": the blob equals container.pack_bitmaps(bitmaps, coding="pbr") of the plain call and decodes
+    to the same arrays (N2: the bitmaps never cross PCIe as one byte per pixel)."""
+    from codec_tcc_b200 import container
+    from oracle import bitcode_numpy as BN
+    for name in ("pe", "synth12_300x200"):
+        img = golden_images[name]
+        bits = codec.message_to_bits("Mensagem de teste para esteganografia!")
+        stego0, bm0, meta0 = codec.embed_pipeline(img, bits, beta=0.4, search_block_size=16)
+        stego1, blob, meta1 = codec.embed_pipeline(img, bits, beta=0.4, search_block_size=16, bitmaps_as="pbr")
+        assert np.array_equal(stego0, stego1) and meta0 == meta1
+        assert blob == BN.encode(bm0)
+        back = container.unpack_bitmaps(blob, meta0["s"])
+        assert all(np.array_equal(b, m.ravel()) for b, m in zip(back, bm0))
+        assert len(blob) < bm0.size // 64
+
+
+def test_tile_search_on_bright_16_bit_planes_with_large_tiles():
+    """n * sum(v^2) beyond 2^53 (16-bit values, 256x256 tiles): the tile search still picks the reference's tile (exact
+    scores for the shortlist instead of a float64 difference that cancels)."""
+    rng = np.random.default_rng(17)
+    for seed in range(3):
+        base = rng.integers(60000, 65536, (700, 900)).astype(np.uint16)
+        base[256:512, 256:512] -= rng.integers(0, 3, (256, 256)).astype(np.uint16) * 20000   # the widest spread
+        base[0:256, 512:768] -= rng.integers(0, 3, (256, 256)).astype(np.uint16) * 19999      # a close second
+        assert codec.hybrid_start_offset(base, 256) == OC.best_tile_offset(base, 256)
+        assert codec.hybrid_start_offset(base, 128) == OC.best_tile_offset(base, 128)
