@@ -92,6 +92,27 @@ def cpu_port_throughput(name, n_sample, repeats=1):
     return px, times, procs
 
 
+def cpu_c_throughput(name, n_sample):
+    """The scalar C restatement (oracle/pee_ref.c, OpenMP over images) on the same workload: what a compiled CPU
+    implementation of the same specification does on this box's cores -- context for the numpy figure."""
+    from codec_tcc_b200.synth import synth_batch
+    from oracle import pee_c
+
+    n, h, w, maxval, bd, T = WORKLOADS[name]
+    imgs = synth_batch(n_sample, h, w, maxval, 1000)
+    stride = (h * w + 7) // 8 + 8
+    pays = np.random.default_rng(99).integers(0, 256, (n_sample, stride), dtype=np.uint8)
+    _, _, info = pee_c.embed_batch(imgs, pays, np.full(n_sample, h * w, np.int64), T, bd)  # every carrier takes a payload bit
+    cap = info[:, 2].copy()
+    t0 = time.perf_counter()
+    marked, lm, info = pee_c.embed_batch(imgs, pays, cap, T, bd)
+    out, rec, rc = pee_c.extract_batch(marked, lm, T, cap, stride)
+    sec = time.perf_counter() - t0
+    assert rc == 0 and np.array_equal(rec, imgs)
+    return {"value": n_sample * h * w / sec / 1e6, "unit": UNIT, "cores": int(pee_c.threads()),
+            "what": f"oracle/pee_ref.c embed + extract of {n_sample} images, OpenMP over images"}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference is pure numpy and ships no PEE code
     (SURVEY.md F2), so the CPU arm is the numpy oracle port of the same path on
@@ -620,6 +641,11 @@ def run_gpu_arm(args):
         cpu_baseline = {"value": px / times[0] / 1e6, "unit": UNIT, "cores": procs, "kind": "port",
                         "sample": f"{n_sample} images of {h}x{w} from the same generator, numpy oracle "
                                   f"(oracle/pee_numpy.py) embed+extract, fork pool of {procs}, {times[0]:.1f} s wall"}
+        try:
+            cpu_baseline["c_restatement"] = cpu_c_throughput(name if name in ("ct512", "dx3000", "slice") else "ct512",
+                                                             4 if big else 128)
+        except Exception as exc:  # noqa: BLE001
+            cpu_baseline["c_restatement"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     import torch
     import torch.distributed as dist
