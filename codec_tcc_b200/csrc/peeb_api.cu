@@ -86,7 +86,8 @@ int peeb_ws_create(int device, peeb_ws** out) {
     if (const char* pr = getenv("PEEB_PIPE_ROLES")) ws->pipe_roles = pr[0] != '0';
     for (int i = 0; i < 4; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->ev[i], cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreate(&ws->prof_ev[i]));
-    for (int i = 0; i < 2; ++i) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i)
+        for (int k = 0; k < peeb_ws::kTableRing; ++k) PEEB_CUDA(cudaEventCreateWithFlags(&ws->pev[i][k], cudaEventDisableTiming));
     const char* nb = getenv("PEEB_NO_BULK");
     ws->use_bulk = !(nb && nb[0] == '1');
     *out = ws;
@@ -107,10 +108,10 @@ int peeb_ws_destroy(peeb_ws* ws) {
     scratch_free(ws->info_h, true);
     for (int i = 0; i < 2; ++i) {
         scratch_free(ws->ptables[i]);
-        scratch_free(ws->ptables_h[i], true);
+        for (int k = 0; k < peeb_ws::kTableRing; ++k) scratch_free(ws->ptables_h[i][k], true);
         scratch_free(ws->pbits[i]);
         if (i == 0) { scratch_free(ws->step_counters); scratch_free(ws->hist); }
-        if (ws->pev[i]) cudaEventDestroy(ws->pev[i]);
+        for (int k = 0; k < peeb_ws::kTableRing; ++k) if (ws->pev[i][k]) cudaEventDestroy(ws->pev[i][k]);
     }
     for (int i = 0; i < 4; ++i) if (ws->ev[i]) cudaEventDestroy(ws->ev[i]);
     for (int i = 0; i < 2; ++i) if (ws->prof_ev[i]) cudaEventDestroy(ws->prof_ev[i]);

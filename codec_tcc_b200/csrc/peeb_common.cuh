@@ -54,9 +54,13 @@ struct peeb_ws {
     // PEE launches use one of two independent table sets, so that two chunks of a host batch
     // can be in flight on the two streams at once
     peeb::Scratch ptables[2];        // device: T/n_bits per unit, band counts, look-back status, tickets
-    peeb::Scratch ptables_h[2];      // pinned host mirrors of the per-unit tables
+    static constexpr int kTableRing = 4;
+    peeb::Scratch ptables_h[2][kTableRing];  // pinned host mirrors of the per-unit tables: a ring per table set, so that a call
+                                             // only waits for the upload issued four calls earlier (the host can run ahead)
+    int ptable_seq[2] = {0, 0};
+    void* ptable_h_cur[2] = {nullptr, nullptr};  // the mirror the latest upload used (callers keep a pinned word behind it)
     peeb::Scratch pbits[2];          // device: extract per-band bit staging
-    cudaEvent_t pev[2] = {nullptr, nullptr};
+    cudaEvent_t pev[2][kTableRing] = {};
     peeb::Scratch info_h;            // pinned landing zone for per-unit info rows (keeps every copy of a
                                      // host batch asynchronous even when the caller's info array is pageable)
     int use_bulk = 1;                // TMA bulk copies (PEEB_NO_BULK=1 disables)

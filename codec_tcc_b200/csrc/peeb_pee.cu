@@ -31,11 +31,13 @@ int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, con
     const size_t head = align_up((size_t)n_units * 8, 256);
     int rc = scratch_reserve(ws->ptables[slot], head + extra_bytes + 256);
     if (rc) return rc;
-    // the pinned mirror is reused by the next call: wait until the previous upload has been consumed
-    PEEB_CUDA(cudaEventSynchronize(ws->pev[slot]));
-    rc = scratch_reserve(ws->ptables_h[slot], head + 256, true);  // (+ a pinned word behind the tables for callers)
+    // the pinned mirrors are a ring: wait until the upload that last used this entry (four calls ago) has been consumed
+    const int ring = ws->ptable_seq[slot]++ % peeb_ws::kTableRing;
+    PEEB_CUDA(cudaEventSynchronize(ws->pev[slot][ring]));
+    rc = scratch_reserve(ws->ptables_h[slot][ring], head + 256, true);  // (+ a pinned word behind the tables for callers)
     if (rc) return rc;
-    int* hT = (int*)ws->ptables_h[slot].ptr;
+    ws->ptable_h_cur[slot] = ws->ptables_h[slot][ring].ptr;
+    int* hT = (int*)ws->ptables_h[slot][ring].ptr;
     unsigned* hN = (unsigned*)(hT + n_units);
     const int tmax = 1 << (bit_depth - 1);
     for (int u = 0; u < n_units; ++u) {
@@ -45,7 +47,7 @@ int upload_unit_tables(peeb_ws* ws, int slot, int n_units, const int32_t* T, con
         hN[u] = (unsigned)n_bits[u];
     }
     PEEB_CUDA(cudaMemcpyAsync(ws->ptables[slot].ptr, hT, (size_t)n_units * 8, cudaMemcpyHostToDevice, st));
-    PEEB_CUDA(cudaEventRecord(ws->pev[slot], st));
+    PEEB_CUDA(cudaEventRecord(ws->pev[slot][ring], st));
     *dT = (int*)ws->ptables[slot].ptr;
     *dN = (unsigned*)((int*)ws->ptables[slot].ptr + n_units);
     *extra = (char*)ws->ptables[slot].ptr + head;

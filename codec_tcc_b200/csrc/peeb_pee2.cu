@@ -2105,7 +2105,7 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
     rc = hist_batch_impl2(ws, src, src_stride, n_units, h, w, itemsize, bit_depth, hist, st);
     if (rc) return rc;
     pee2_pick_T_kernel<<<n_units, 256, 0, st>>>(hist, tmax, dN, dT, active);  // every unit takes part in round one
-    int* remaining_h = (int*)((char*)ws->ptables_h[slot].ptr + align_up((size_t)n_units * 8, 256));  // pinned, behind the tables
+    int* remaining_h = (int*)((char*)ws->ptable_h_cur[slot] + align_up((size_t)n_units * 8, 256));  // pinned, behind the tables
     int* remaining = active + n_units;
     for (int round = 0; round <= tmax; ++round) {
         rc = PEEB_DISPATCH2(launch_embed2, ws, g, bt, nbands, band_cnt, rowcnt, ticket, status, st);
