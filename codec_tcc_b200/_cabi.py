@@ -269,6 +269,60 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     return arr
 
 
+# Large result arrays of the numpy API live in page-locked memory taken from a small pool: a device->host copy into a
+# fresh pageable array runs at a few GB/s (staged by the driver, plus the page faults of first touch), page-locking
+# itself costs milliseconds per call -- a pooled pinned block costs neither.  A block goes back to the pool when the
+# array (and every view of it) is gone.  PEEB_PINNED_POOL_MB caps what the pool keeps (default 2048; 0: plain numpy).
+_pool_lock = threading.Lock()
+_pool_free: dict = {}
+_pool_bytes = 0
+_POOL_MIN = 4 << 20
+_POOL_GRAIN = 2 << 20
+
+
+def _pool_cap() -> int:
+    return int(os.environ.get("PEEB_PINNED_POOL_MB", "2048")) << 20
+
+
+def _pool_release(addr: int, nbytes: int) -> None:
+    global _pool_bytes
+    with _pool_lock:
+        if _pool_bytes + nbytes <= _pool_cap():
+            _pool_free.setdefault(nbytes, []).append(addr)
+            _pool_bytes += nbytes
+            return
+    try:
+        lib().peeb_host_free(_vp(addr))
+    except Exception:  # noqa: BLE001 -- interpreter shutdown
+        pass
+
+
+def out_empty(shape, dtype) -> np.ndarray:
+    """An uninitialised result array: pooled page-locked memory for large results, ``np.empty`` for small ones."""
+    global _pool_bytes
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    n = count * dtype.itemsize
+    if n < _POOL_MIN or _pool_cap() == 0:
+        return np.empty(shape, dtype)
+    bucket = (n + _POOL_GRAIN - 1) // _POOL_GRAIN * _POOL_GRAIN
+    addr = None
+    with _pool_lock:
+        free = _pool_free.get(bucket)
+        if free:
+            addr = free.pop()
+            _pool_bytes -= bucket
+    if addr is None:
+        p = _vp()
+        rc = lib().peeb_host_alloc(bucket, C.byref(p))
+        if rc != PEEB_OK:      # the host would not pin more memory: an ordinary array works, only slower
+            return np.empty(shape, dtype)
+        addr = p.value
+    buf = (C.c_ubyte * bucket).from_address(addr)
+    weakref.finalize(buf, _pool_release, addr, bucket)
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
 def payload_bytes(n_bits: int) -> int:
     return int(lib().peeb_payload_bytes(int(n_bits)))
 

@@ -197,7 +197,7 @@ def calculate_mutual_information(bit_plane, image_array):
 def extract_bit_plane(image, bit, device=None):
     """(image >> bit) & 1 with the image's dtype (src/codec.py:571)."""
     img = _cabi.as_image(image, "image")
-    out = np.empty((1,) + img.shape, img.dtype)
+    out = _cabi.out_empty((1,) + img.shape, img.dtype)
     ws = workspace(device)
     check(lib().peeb_planes_unpack_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, int(bit), 1, ptr(out)),
           "peeb_planes_unpack_h")
@@ -236,7 +236,7 @@ def adaptive_modalities_decomposition(image_array, beta=0.8, nbits=None):
     if VERBOSE:
         print(f"   - Informação total da imagem: {total_info:.4f}")
         print(f"   - Meta de retenção ({beta*100}%): {beta * total_info:.4f}")
-    planes = np.empty((max(nbits, 0),) + img.shape, img.dtype)
+    planes = _cabi.out_empty((max(nbits, 0),) + img.shape, img.dtype)
     if nbits > 0 and img.size:
         ws = workspace()
         check(lib().peeb_planes_unpack_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, 0, nbits, ptr(planes)),
@@ -255,15 +255,15 @@ def merge_modalities(global_planes, local_planes):
     planes, shape, dt = _plane_stack(allp, "planes")
     total_bits = len(planes)
     out_dtype = np.uint16 if total_bits > 8 else np.uint8
-    out = np.zeros(shape, out_dtype)
+    out = _cabi.out_empty(shape, out_dtype)
     use = planes[:16]  # a uint16 shifted by >= 16 contributes nothing
     n = int(np.prod(shape)) if len(shape) else 1
     if n == 0:
-        return out
+        return np.zeros(shape, out_dtype)
     ws = workspace()
     if total_bits > 16:
         # keep the uint16 output decision while packing only the first 16 planes
-        tmp = np.zeros(shape, np.uint16)
+        tmp = _cabi.out_empty(shape, np.uint16)
         check(lib().peeb_planes_pack_h(ws.handle, _ptr_array(use), n, dt.itemsize, 16, ptr(tmp)), "peeb_planes_pack_h")
         return tmp
     check(lib().peeb_planes_pack_h(ws.handle, _ptr_array(use), n, dt.itemsize, len(use), ptr(out)), "peeb_planes_pack_h")
@@ -274,7 +274,7 @@ def extract_local_planes(stego_array, s):
     """src/codec.py:789-793: the ``s`` least significant bit planes."""
     img = _cabi.as_image(stego_array, "stego_array")
     s = int(s)
-    planes = np.empty((max(s, 0),) + img.shape, img.dtype)
+    planes = _cabi.out_empty((max(s, 0),) + img.shape, img.dtype)
     if s > 0 and img.size:
         ws = workspace()
         check(lib().peeb_planes_unpack_h(ws.handle, ptr(img), img.size, img.dtype.itemsize, 0, s, ptr(planes)),
@@ -374,8 +374,8 @@ def _embed(local_planes, message_bits, start_offset, advance, device=None):
         if advance and npx:
             start_offset = (start_offset + nb) % npx
     payload = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
-    out_planes = np.empty((s, h, w), dt)
-    bitmaps = np.empty((s, h, w), np.uint8)
+    out_planes = _cabi.out_empty((s, h, w), dt)
+    bitmaps = _cabi.out_empty((s, h, w), np.uint8)
     if npx:
         ws = workspace(device)
         check(lib().peeb_lsb_embed_h(ws.handle, _ptr_array(planes), npx, dt.itemsize, s, ptr(start), ptr(length),
@@ -500,7 +500,7 @@ def recover_cover(stego_array, bitmaps, device=None):
     for b in maps:
         if b.dtype != np.uint8 or b.size != img.size:
             raise ValueError("bitmaps must be uint8 arrays of the image's size")
-    out = np.empty_like(img)
+    out = _cabi.out_empty(img.shape, img.dtype)
     if img.size:
         ws = workspace(device)
         check(lib().peeb_lsb_recover_h(ws.handle, ptr(img), _ptr_array(maps), img.size, img.dtype.itemsize, s, ptr(out)),
@@ -616,7 +616,7 @@ def embed_pipeline(image_array, message_bits, beta=0.8, search_block_size=16, al
     out_dtype = np.uint16 if nb > 8 else np.uint8
     d_stego = _cabi.DeviceBuffer(ws, npx * out_dtype().itemsize)
     check(L.peeb_planes_pack(ws.handle, d_out.ptr, npx, item, nb, d_stego.ptr, st), "peeb_planes_pack")
-    stego = d_stego.download(np.empty((h, w), out_dtype))
+    stego = d_stego.download(_cabi.out_empty((h, w), out_dtype))
     if bitmaps_as == "pbr":
         import ctypes as C
         cap = int(L.peeb_bitmap_blob_bound(s * npx))
@@ -626,7 +626,7 @@ def embed_pipeline(image_array, message_bits, beta=0.8, search_block_size=16, al
         bitmaps = d_blob.download(np.empty(got.value, np.uint8)).tobytes()
         d_blob.free()
     else:
-        bitmaps = d_bm.download(np.empty((s, h, w), np.uint8))
+        bitmaps = d_bm.download(_cabi.out_empty((s, h, w), np.uint8))
     for b in (d_img, d_hist, d_planes, d_pay, d_out, d_bm, d_stego):
         b.free()
     meta = {"s": s, "segments_lengths": sizes if hybrid else [int(v) for v in lens],

@@ -139,11 +139,11 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
     marked = None
     if want_marked:
         marked = (_check_out(out_marked, "out_marked", (n, h, w), imgs.dtype) if out_marked is not None
-                  else np.empty((n, h, w), imgs.dtype))
+                  else _cabi.out_empty((n, h, w), imgs.dtype))
     lm = None
     if want_lm:
         lm = (_check_out(out_lm, "out_lm", (n, h, (w + 7) // 8), np.uint8) if out_lm is not None
-              else np.empty((n, h, (w + 7) // 8), np.uint8))
+              else _cabi.out_empty((n, h, (w + 7) // 8), np.uint8))
     info = np.zeros((n, INFO), np.int64)
     ws = workspace(device)
     flags = (1 if shared_cover else 0) | (2 if shared_payload else 0)
@@ -195,7 +195,7 @@ def pee_extract_batch(marked, lm, T, n_bits, bit_depth=None, *, want_recovered=T
     rec = None
     if want_recovered:
         rec = (_check_out(out_recovered, "out_recovered", (n, h, w), marked.dtype) if out_recovered is not None
-               else np.empty((n, h, w), marked.dtype))
+               else _cabi.out_empty((n, h, w), marked.dtype))
     info = np.zeros((n, INFO), np.int64)
     ws = workspace(device)
     # a zero-width payload array still needs a valid pointer
