@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import WORKLOADS  # noqa: E402
+from bench import WORKLOADS, workload_images  # noqa: E402
 from codec_tcc_b200 import _cabi, device as D  # noqa: E402
 from codec_tcc_b200.synth import synth_batch  # noqa: E402
 
@@ -21,7 +21,7 @@ if name.startswith("custom:"):  # custom:n,h,w,bit_depth,T
 else:
     n, h, w, maxval, bd, T = WORKLOADS[name]
 dev = torch.device("cuda:0")
-imgs = synth_batch(n, h, w, maxval, 2)
+imgs = synth_batch(n, h, w, maxval, 2) if name.startswith("custom:") or name in ("ct512", "dx3000", "slice") else workload_images(name, n, h, w, maxval, 2)[0]
 d_imgs = torch.from_numpy(imgs.view(np.int16) if imgs.dtype == np.uint16 else imgs).to(dev)
 stride = D.payload_stride(h * w)
 d_pays = torch.from_numpy(np.random.default_rng(7).integers(0, 256, (n, stride), dtype=np.uint8)).to(dev)
