@@ -985,6 +985,18 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     const int p0_lo = max(r0 - 1, 1), p0_hi = min(r0 + g.R + 1, g.h - 1);
     const int s_lo = max(r0 - 2, 0), s_hi = min(r0 + g.R + 2, g.h);
     PHASE_INIT;
+#ifndef PEEB_AB_NOPREFETCH
+    // the table rows of the warp's first item and the unit's band totals are wanted right after this: their lines are
+    // asked for BEFORE the band's bulk copies, behind which small loads would otherwise wait (phase timing: 8 % of a
+    // band's wall time went to the first item's table rows, which arrived when the 60-200 KB of rows had)
+    if (warp < g.nic && p0_hi > p0_lo) {
+        const Lane2 l = lane_of(g, p0_lo, p0_hi, warp);
+        const unsigned char* ta = rowcnt + ((long long)unit * g.h + l.rowa) * g.tpitch;
+        if (l.rowa_in) asm volatile("prefetch.global.L1 [%0];" :: "l"(ta));
+        if (l.rowb_in) asm volatile("prefetch.global.L1 [%0];" :: "l"(ta + g.tpitch));
+    }
+    if (lane * 32 < g.nb) asm volatile("prefetch.global.L1 [%0];" :: "l"(band_cnt + unit * g.nb + lane * 32));
+#endif
     issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
     PHASE_MARK(16);  // copies issued
     // every warp: carriers of pass 0 in the earlier bands, and in the whole unit (cap0), from the count kernel's band
