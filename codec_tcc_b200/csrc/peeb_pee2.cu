@@ -794,10 +794,19 @@ struct Hist2 {
             const int e = q >> 2;
             ok = ok && (unsigned)P::template add4x<Q, S>(M, q) < 4u * (unsigned)g.maxval;  // 0 <= x + e < maxval
             ok = ok && e >= -tmax && e < tmax;
+#ifdef PEEB_HIST_MATCH
+            // warp-aggregated form: lanes with the same error elect one of them to add their number
+            const bool inwin = ok && e >= -HWIN && e < HWIN;
+            const unsigned key = inwin ? (unsigned)(e + HWIN) : (0x80000000u | (threadIdx.x & 31));
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (inwin && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(sh + e + HWIN, (unsigned)__popc(peers));
+            if (ok && !inwin) atomicAdd(gh + e + tmax, 1u);
+#else
             if (ok) {
                 if (e >= -HWIN && e < HWIN) atomicAdd(sh + e + HWIN, 1u);
                 else atomicAdd(gh + e + tmax, 1u);
             }
+#endif
         });
     }
     template <int QA>
