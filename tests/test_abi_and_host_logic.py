@@ -143,3 +143,18 @@ def test_payload_packing_and_threshold_estimate():
     hist = PN.error_histogram(img, 12)
     for nb in (0, 10, 500, 2000, 10 ** 7):
         assert pee.estimate_threshold(hist, nb) == PN.estimate_T(hist, nb)
+
+
+def test_result_arrays_come_from_the_pool_or_plain_numpy():
+    """_cabi.out_empty: small results are ordinary arrays; large ones are page-locked blocks from a pool when a device is
+    there, ordinary arrays when the host will not pin memory (no GPU here) -- either way a writable array of the shape."""
+    a = _cabi.out_empty((3, 5), np.uint16)
+    assert a.shape == (3, 5) and a.dtype == np.uint16 and a.flags.writeable
+    b = _cabi.out_empty((3000, 3000), np.uint8)
+    assert b.shape == (3000, 3000) and b.dtype == np.uint8 and b.flags.c_contiguous
+    b[...] = 7
+    assert int(b.sum()) == 7 * 9_000_000
+    del b
+    c = _cabi.out_empty((3000, 3000), np.uint8)   # a released block may be handed out again
+    c[0, 0] = 1
+    assert c[0, 0] == 1
