@@ -72,7 +72,7 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind_ /*0 count, 1 
     const int kind = kind_ == 4 ? 1 : kind_ == 5 ? 2 : kind_;
     L.img = o; o += align_up((size_t)16 + (size_t)(g.R + 5) * g.pitch + 192, 16);
     L.lm = o;
-    if (kind == 2 || (kind == 1 && !g.lm_direct)) o += align_up((size_t)(g.R + 2) * g.lmpitch + 16, 16);
+    if (kind == 2 || (kind == 1 && !g.lm_direct)) o += align_up((size_t)(g.R + 2) * g.lmpitch + 16 + (kind_ == 2 ? 48 : 0), 16);
     L.tab = o;
     if (kind == 1) o += (size_t)(g.R + 2) * g.tpitch;   // pass-1 carriers per (row, cell), one byte each
     if (kind == 3) o += (size_t)4 * HWIN * sizeof(unsigned);  // [colour][e + HWIN]
@@ -1293,7 +1293,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Smem2 L = layout2(g, 2);
     unsigned char* simg = smem_raw + L.img;
-    unsigned char* slm = smem_raw + L.lm;
+    unsigned char* slm = smem_raw + L.lm + 16;  // (16 bytes of slack in front: the unaligned copy may start a piece early)
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     unsigned char* tn0 = smem_raw + L.tn0;
     unsigned char* tn1 = smem_raw + L.tn1;
@@ -1316,7 +1316,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         (void)lane; (void)warp; (void)nwarps;
-        if (g.lmpitch == g.lmw && ((uintptr_t)glm & 15) == 0) {
+        if (g.lmpitch == g.lmw && (g.lmw & 15) == 0 && ((uintptr_t)glm & 15) == 0) {
             // rows of whole 16-byte pieces, no padding between them: one flat copy of the rows inside the image, two
             // pieces per thread in flight (a cell that sticks out of its row then sees the first bytes of the next
             // row: columns past the image run with T = 0 whatever their flag says)
@@ -1362,6 +1362,37 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
                 sq[k] = v;
                 lm_any |= (v.x | v.y | v.z | v.w) != 0u;
             }
+        } else if (g.lmpitch == g.lmw) {
+            // any row length and alignment (3000 columns: 375 bytes per row): the rows inside the image are one byte
+            // range in global memory; it is copied in whole 16-byte pieces to a shared copy with the SAME alignment
+            // modulo 16 (slm is moved by up to 15 bytes), rows back to back.  The few foreign bytes of the first and
+            // last piece belong to neighbouring rows of the map and can only make the vote say "look" needlessly.
+            const unsigned char* gfirst = glm + (size_t)l_lo * g.lmw;
+            const int first = l_lo - (r0 - 1);                                   // shared row of image row l_lo
+            slm += (unsigned)(((uintptr_t)gfirst - (uintptr_t)first * g.lmw) & 15);   // S(r) = slm + r * lmw, S(first) = gfirst mod 16
+            const int head = (int)((uintptr_t)gfirst & 15);
+            const int nbytes = (l_hi - l_lo) * g.lmw;
+            const int npieces = nbytes > 0 ? (head + nbytes + 15) >> 4 : 0;
+            const uint4* gq = reinterpret_cast<const uint4*>(gfirst - head);
+            uint4* sq = reinterpret_cast<uint4*>(slm + (size_t)first * g.lmw - head);
+            const int k0 = threadIdx.x, k1 = threadIdx.x + blockDim.x;
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            const uint4 v0 = k0 < npieces ? __ldg(gq + k0) : zero4, v1 = k1 < npieces ? __ldg(gq + k1) : zero4;
+            issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
+            if (k0 < npieces) sq[k0] = v0;
+            if (k1 < npieces) sq[k1] = v1;
+            lm_any = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0u;
+            for (int k = threadIdx.x + 2 * blockDim.x; k < npieces; k += blockDim.x) {
+                const uint4 v = __ldg(gq + k);
+                sq[k] = v;
+                lm_any |= (v.x | v.y | v.z | v.w) != 0u;
+            }
+            // rows of the copy outside the image (first / last band): read by idle lanes only, zero.  (Bytes, behind
+            // a barrier-free guarantee: they do not overlap the pieces above except in the pieces' foreign bytes,
+            // which nobody needs.)
+            if (first > 0)
+                for (int k = threadIdx.x; k < first * g.lmw - head; k += blockDim.x) slm[k] = 0;
+            for (int k = (l_hi - (r0 - 1)) * g.lmw + 16 + (int)threadIdx.x; k < (g.R + 2) * g.lmw; k += blockDim.x) slm[k] = 0;
         } else {
             issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
             for (int r = warp; r < g.R + 2; r += nwarps) {
@@ -1808,7 +1839,8 @@ static int make_geom2(peeb_ws* ws, int h, int w, int itemsize, int bit_depth, in
     // (one 16-byte piece of padding per row measured 6 % faster on the 512-slice batch than rows back to back:
     // scripts/ab_variants.sh, gpurun_out/r02_ab11.log; PEEB_LM_PAD overrides it for such runs)
     g.lmpitch = (kind == 2 && (g.lmw & 15) == 0) ? g.lmw + (getenv("PEEB_LM_PAD") ? atoi(getenv("PEEB_LM_PAD")) : 16)
-                                                  : (int)align_up((size_t)g.lmw, 4) + 12;
+                : (kind == 2 && !getenv("PEEB_LM_BYTES")) ? g.lmw   // rows back to back: one unaligned range, copied in 16-byte pieces
+                                                          : (int)align_up((size_t)g.lmw, 4) + 12;
     g.lm_direct = (kind == 1 && lm_direct_ok && (g.lmw & 3) == 0 && !getenv("PEEB_LM_SHARED")) ? 1 : 0;
     const int pxs = 16 / itemsize;
     const int nsteps = (g.rowbytes + 15) / 16;
