@@ -62,7 +62,7 @@ struct Geom2 {
 };
 
 struct Smem2 {
-    size_t img, lm, tab, misc, bar, tn0, tn1, tw0, tw1, stream, tab0, xch, total;
+    size_t img, lm, tab, misc, bar, tn0, tn1, tw0, tw1, stream, tab0, xch, pre, total;
 };
 constexpr int CLUSTER_MAX = 16;  // CTAs of one image's cluster (small-image path)
 constexpr int HWIN = 512;  // errors -HWIN <= e < HWIN of the threshold-selection histogram are counted in shared memory
@@ -87,6 +87,9 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind_ /*0 count, 1 
         L.tw1 = o; o += align_up(cells * sizeof(unsigned), 16);
         L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
     }
+    L.pre = o;
+    // wide images (more than 16 cells per row): per-(row, table word) prefixes and row totals of the current pass
+    if (kind_ == 1 && g.tpitch > 16) o += align_up((size_t)(g.R + 2) * (g.tpitch >> 2) * sizeof(unsigned short) + (size_t)(g.R + 2) * sizeof(int), 16);
     L.tab0 = L.xch = o;
     if (kind_ == 4) { L.tab0 = o; o += (size_t)(g.R + 2) * g.tpitch; }   // pass-0 carriers per (row, cell)
     if (kind_ >= 4) { L.xch = o; o += (size_t)8 * CLUSTER_MAX * sizeof(unsigned); }  // what the CTAs of a cluster tell each other
@@ -224,6 +227,36 @@ template <bool GLOBAL>
 __device__ __noinline__ CellPrefix cell_prefix(const Geom2& g, const unsigned char* ta, bool rowa_in, bool rowb_in,
                                                int cell) {
     return cell_prefix_inl<GLOBAL>(g, ta, rowa_in, rowb_in, cell);
+}
+
+// Wide images: a row of the count table has more than 16 cells, and summing it per lane and item (cell_prefix_inl) was
+// 14 % of the embed kernel's instructions on 3000-pixel rows.  Once per pass the CTA turns the table into what a lane
+// needs: wpre[row][word] = carriers of the cells left of that table word (4 cells), rowtot[row] = carriers of the row;
+// a lane then reads its own table word, one prefix and one total per row.  Every thread of the CTA calls this (one
+// barrier at the end); nrows <= R + 2 rows starting at `tab`.
+template <bool GLOBAL>
+__device__ __forceinline__ void build_prefix(const Geom2& g, const unsigned char* tab, int nrows, unsigned short* wpre, int* rowtot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, wpr = g.tpitch >> 2;
+    for (int r = warp; r < nrows; r += nwarps) {
+        const unsigned* row = reinterpret_cast<const unsigned*>(tab + (size_t)r * g.tpitch);
+        int carry = 0;
+        for (int j0 = 0; j0 < wpr; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned w = 0u;
+            if (j < wpr) w = GLOBAL ? __ldg(row + j) : row[j];
+            const int sum = idp4_sum(w, 0x01010101u, 0);
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (j < wpr) wpre[r * wpr + j] = (unsigned short)(carry + incl - sum);
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) rowtot[r] = carry;
+    }
+    __syncthreads();
 }
 
 // Decoupled look-back over the bands of a unit, run by a whole warp (every warp of the CTA may run it: all of
@@ -637,6 +670,9 @@ struct Apply2 {
                     // the unit's rows in global memory (null: the caller wants no map)
     int lm_row0, lmwords;
     Stats2* st;
+    const unsigned short* wpre = nullptr;  // wide images: build_prefix's tables of this pass (row pre_row0 first), else null
+    const int* rowtot = nullptr;
+    int pre_row0 = 0;
     KE ka, kb;
     unsigned Wa, Wb;
     long long ssea, sseb;
@@ -648,7 +684,24 @@ struct Apply2 {
     __device__ __forceinline__ void begin_order(int rowa, int cell, bool a, bool b, bool rowa_in, bool rowb_in, int T) {
         sta = a; stb = b;
         ka = kb = make_ke(T);
-        const CellPrefix cp = cell_prefix<GTAB>(g, tab + (long long)(rowa - row0) * g.tpitch, rowa_in, rowb_in, cell);
+        CellPrefix cp;
+        if (wpre) {
+            const int ra = rowa - pre_row0, jc = cell >> 2, wpr = g.tpitch >> 2;
+            const unsigned partial = 0x01010101u & ((1u << (8 * (cell & 3))) - 1u);
+            const unsigned* ta = reinterpret_cast<const unsigned*>(tab + (long long)(rowa - row0) * g.tpitch) + jc;
+            int tota = 0, totb = 0, prea = 0, preb = 0;
+            if (rowa_in) {
+                tota = rowtot[ra];
+                prea = idp4_sum(GTAB ? __ldg(ta) : *ta, partial, (int)wpre[ra * wpr + jc]);
+            }
+            if (rowb_in) {
+                totb = rowtot[ra + 1];
+                preb = idp4_sum(GTAB ? __ldg(ta + wpr) : ta[wpr], partial, (int)wpre[(ra + 1) * wpr + jc]);
+            }
+            cp = prefix_scan(g, tota, totb, prea, preb);
+        } else {
+            cp = cell_prefix<GTAB>(g, tab + (long long)(rowa - row0) * g.tpitch, rowa_in, rowb_in, cell);
+        }
         offa = cp.offa - (halo ? cp.row0_total : 0);
         offb = cp.offb - (halo ? cp.row0_total : 0);
         owna = a && rowa >= own_lo && rowa < own_hi;
@@ -969,6 +1022,9 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool use_pre = g.tpitch > 16;
+    int* rowtot = reinterpret_cast<int*>(smem_raw + L.pre);
+    unsigned short* wpre = reinterpret_cast<unsigned short*>(smem_raw + L.pre + (size_t)(g.R + 2) * sizeof(int));
 
     // in-order ticket: a band only ever waits on bands with smaller tickets
     if (threadIdx.x == 0) {
@@ -1040,6 +1096,10 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     {
         Apply2<PixT, true> body{g, 0, own_lo, own_hi, rowcnt + (long long)unit * g.h * g.tpitch, payload, n_bits,
                                 0u, p0_lo < own_lo, lmbase, lmrow0, lmwords, &st};
+        if (use_pre) {  // wide rows: the table of the band's rows (count kernel, global memory) -> prefixes, once
+            build_prefix<true>(g, rowcnt + ((long long)unit * g.h + p0_lo) * g.tpitch, max(p0_hi - p0_lo, 0), wpre, rowtot);
+            body.wpre = wpre; body.rowtot = rowtot; body.pre_row0 = p0_lo;
+        }
         sweep2_prime_order(g, p0_lo, p0_hi, T, body);
         PHASE_MARK(17);  // pass-0 order of the first item
         int before0 = 0;
@@ -1077,6 +1137,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     PHASE_MARK(4);  // count 1
     __syncthreads();
     PHASE_MARK(5);  // barrier
+    if (use_pre) build_prefix<false>(g, tab, max(own_hi - own_lo, 0), wpre, rowtot);  // (pass 0 is done with them: barrier above)
     {
         const unsigned total = (unsigned)table_total(g, tab, max(own_hi - own_lo, 0));
         const unsigned before1 = warp_lookback(status + (long long)unit * g.nb, band, total, warp == 0);
@@ -1090,6 +1151,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
         PHASE_MARK(6);  // look-back
         Apply2<PixT, false> body{g, own_lo, own_lo, own_hi, tab, payload, n_bits, (unsigned)cap0 + before1, false,
                                  lmbase, lmrow0, lmwords, &st};
+        if (use_pre) { body.wpre = wpre; body.rowtot = rowtot; body.pre_row0 = own_lo; }
         sweep2_colour<PixT>(g, simg, r_first, 1, own_lo, own_hi, T, body);
         PHASE_MARK(7);  // apply 1
     }
