@@ -88,8 +88,8 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind_ /*0 count, 1 
         L.stream = o; o += align_up((size_t)2 * g.bandwords * sizeof(unsigned), 16);
     }
     L.pre = o;
-    // wide images (more than 16 cells per row): per-(row, table word) prefixes and row totals of the current pass
-    if (kind_ == 1 && g.tpitch > 16) o += align_up((size_t)(g.R + 2) * (g.tpitch >> 2) * sizeof(unsigned short) + (size_t)(g.R + 2) * sizeof(int), 16);
+    // wide images (more than 32 cells per row): per-(row, table word) prefixes and row totals of the current pass
+    if (kind_ == 1 && g.tpitch > 32) o += align_up((size_t)(g.R + 2) * (g.tpitch >> 2) * sizeof(unsigned short) + (size_t)(g.R + 2) * sizeof(int), 16);
     L.tab0 = L.xch = o;
     if (kind_ == 4) { L.tab0 = o; o += (size_t)(g.R + 2) * g.tpitch; }   // pass-0 carriers per (row, cell)
     if (kind_ >= 4) { L.xch = o; o += (size_t)8 * CLUSTER_MAX * sizeof(unsigned); }  // what the CTAs of a cluster tell each other
@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_embed_kernel(Geom2 g, PeeBatch 
     int* misc = reinterpret_cast<int*>(smem_raw + L.misc);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool use_pre = g.tpitch > 16;
+    const bool use_pre = g.tpitch > 32;  // (32 cells per row: two 16-byte loads per table row are as cheap as the prefix pass; measured on the 2048-wide sweep)
     int* rowtot = reinterpret_cast<int*>(smem_raw + L.pre);
     unsigned short* wpre = reinterpret_cast<unsigned short*>(smem_raw + L.pre + (size_t)(g.R + 2) * sizeof(int));
 
