@@ -35,6 +35,7 @@ int embed_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_un
 // T = NULL: thresholds are chosen on the device (Appendix A: histogram estimate, then verify and increment)
 int hist_batch_impl2(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w, int itemsize,
                      int bit_depth, uint32_t* hist, cudaStream_t st);
+int threshold_retry_round(int n_units, int tmax, long long* info, int* T, int* active, int* remaining, int* remaining_h, cudaStream_t st);
 int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, int n_units, int h, int w,
                         int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* lm,
                         int64_t lm_stride, uint8_t* payload_out, int64_t payload_stride, void* recovered,

@@ -953,8 +953,19 @@ __global__ void pee2_retry_kernel(int n_units, int tmax, long long* __restrict__
     int again = 0;
     if (active[u] == 2) info[(long long)u * PEEB_INFO + 7] = PEEB_E_CAPACITY;
     else if (active[u] && info[(long long)u * PEEB_INFO + 7] == PEEB_E_CAPACITY && T[u] < tmax) { T[u] += 1; again = 1; }
+    if (again) { info[(long long)u * PEEB_INFO + 5] = 0; info[(long long)u * PEEB_INFO + 6] = 0; }  // summed with atomics by the causal kernels
     active[u] = again;
     if (again) atomicAdd(remaining, 1);
+}
+
+// host side of a verify-and-increment round, for the other translation unit (causal predictor): units that fell
+// short get T + 1 and stay active; *remaining_h (pinned) = how many; synchronises the stream
+int threshold_retry_round(int n_units, int tmax, long long* info, int* T, int* active, int* remaining, int* remaining_h, cudaStream_t st) {
+    PEEB_CUDA(cudaMemsetAsync(remaining, 0, sizeof(int), st));
+    pee2_retry_kernel<<<(n_units + 255) / 256, 256, 0, st>>>(n_units, tmax, info, T, active, remaining);
+    PEEB_CUDA(cudaMemcpyAsync(remaining_h, remaining, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PEEB_CUDA(cudaStreamSynchronize(st));
+    return PEEB_OK;
 }
 
 // ------------------------------------------------------------------ K_A: pass-0 counts

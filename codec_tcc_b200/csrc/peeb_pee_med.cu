@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <vector>
+
 #include "peeb_common.cuh"
 #include "peeb_pee.cuh"
 
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(256) med_embed_kernel(MedGeom g, PeeBatch bt, 
     const long long per_unit = (long long)nblk * g.nchunk;
     if (item >= per_unit * bt.n_units) return;
     const int unit = (int)(item / per_unit);
+    if (bt.active && !bt.active[unit]) return;  // threshold search: this unit is done
     const int rem = (int)(item - (long long)unit * per_unit);
     const int blk = rem / g.nchunk, chunk = rem - blk * g.nchunk;
     const int row0 = blk * rb, row1 = min(row0 + rb, g.h);
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(1024) med_scan_kernel(MedGeom g, PeeBatch bt, 
                                                         unsigned* __restrict__ off) {
     __shared__ int ws[33];
     const int unit = blockIdx.x;
+    if (bt.active && !bt.active[unit]) return;  // threshold search: this unit is done
     const long long ne = (long long)g.h * g.nchunk;
     const unsigned short* c = cnt + unit * ne;
     unsigned* o = off + unit * ne;
@@ -633,7 +637,7 @@ int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, i
                              int bit_depth, const int32_t* T, const int64_t* n_bits, const uint8_t* payload,
                              int64_t payload_stride, void* marked, int64_t marked_stride, uint8_t* lm, int64_t lm_stride,
                              int64_t* info, void* stream) {
-    PEEB_REQUIRE(ws && src && T && n_bits && payload && info, "peeb_pee_med_embed_batch: null pointer");
+    PEEB_REQUIRE(ws && src && n_bits && payload && info, "peeb_pee_med_embed_batch: null pointer");  // T may be null: searched on the device
     PEEB_REQUIRE(n_units >= 1, "peeb_pee_med_embed_batch: n_units must be >= 1");
     PEEB_REQUIRE(((uintptr_t)payload & 3) == 0 && (payload_stride & 3) == 0, "peeb_pee_med_embed_batch: payload must be 4-byte aligned");
     PEEB_CUDA(cudaSetDevice(ws->device));
@@ -645,10 +649,17 @@ int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, i
     PEEB_REQUIRE(ne < (1ll << 31), "peeb_pee_med_embed_batch: batch too large");
     int* dT; unsigned* dN; char* extra;
     const size_t cnt_bytes = align_up((size_t)ne * sizeof(unsigned short), 256), off_bytes = align_up((size_t)ne * sizeof(unsigned), 256);
-    rc = upload_unit_tables(ws, 0, n_units, T, n_bits, bit_depth, cnt_bytes + off_bytes, st, &dT, &dN, &extra);
+    // T == NULL: every unit starts at T = 1 and is embedded again at T + 1 while its payload does not
+    // fit -- on the device, only the units that fall short take part in a round (the causal predictor has no histogram estimate)
+    const bool auto_T = T == nullptr;
+    const size_t act_bytes = auto_T ? align_up((size_t)(n_units + 1) * sizeof(int), 256) : 0;
+    std::vector<int32_t> ones;
+    if (auto_T) ones.assign((size_t)n_units, 1);
+    rc = upload_unit_tables(ws, 0, n_units, auto_T ? ones.data() : T, n_bits, bit_depth, cnt_bytes + off_bytes + act_bytes, st, &dT, &dN, &extra);
     if (rc) return rc;
     unsigned short* cnt = (unsigned short*)extra;
     unsigned* off = (unsigned*)(extra + cnt_bytes);
+    int* active = auto_T ? (int*)(extra + cnt_bytes + off_bytes) : nullptr;
     PEEB_CUDA(cudaMemsetAsync(info, 0, sizeof(int64_t) * PEEB_INFO * n_units, st));
     PeeBatch bt{};
     bt.src = (const unsigned char*)src; bt.src_stride = src_stride;
@@ -656,6 +667,8 @@ int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, i
     bt.lm = lm; bt.lm_stride = lm_stride;
     bt.payload = payload; bt.payload_stride = payload_stride;
     bt.T = dT; bt.n_bits = dN; bt.info = (long long*)info; bt.n_units = n_units;
+    bt.active = active;
+    if (auto_T) PEEB_CUDA(cudaMemsetAsync(active, 0x01, (size_t)n_units * sizeof(int), st));  // every unit takes part in round one
     // rows per warp item: long enough to amortise the set-up, short enough to leave ~8 items per
     // resident warp slot for load balance
     int rb = 16;
@@ -663,14 +676,22 @@ int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, i
     if (const char* e = getenv("PEEB_MED_ROWS")) rb = std::max(1, atoi(e));
     const long long nitems = (long long)n_units * ((h + rb - 1) / rb) * g.nchunk;
     const unsigned blocks = (unsigned)((nitems + 7) / 8);
-    { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
-      if (itemsize == 2) med_embed_kernel<unsigned short, false><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off);
-      else med_embed_kernel<unsigned char, false><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off); }
-    med_scan_kernel<<<n_units, 1024, 0, st>>>(g, bt, cnt, off);
-    { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
-      if (itemsize == 2) med_embed_kernel<unsigned short, true><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off);
-      else med_embed_kernel<unsigned char, true><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off); }
-    PEEB_CUDA(cudaGetLastError());
+    const int tmax = 1 << (bit_depth - 1);
+    int* remaining_h = auto_T ? (int*)((char*)ws->ptable_h_cur[0] + align_up((size_t)n_units * 8, 256)) : nullptr;
+    for (int round = 0; round <= (auto_T ? tmax : 0); ++round) {
+        { ProfScope p(ws, PEEB_K_PEE_COUNT, st);
+          if (itemsize == 2) med_embed_kernel<unsigned short, false><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off);
+          else med_embed_kernel<unsigned char, false><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off); }
+        med_scan_kernel<<<n_units, 1024, 0, st>>>(g, bt, cnt, off);
+        { ProfScope p(ws, PEEB_K_PEE_EMBED, st);
+          if (itemsize == 2) med_embed_kernel<unsigned short, true><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off);
+          else med_embed_kernel<unsigned char, true><<<blocks, 256, 0, st>>>(g, bt, rb, cnt, off); }
+        PEEB_CUDA(cudaGetLastError());
+        if (!auto_T) break;
+        rc = threshold_retry_round(n_units, tmax, (long long*)info, dT, active, active + n_units, remaining_h, st);
+        if (rc) return rc;
+        if (*remaining_h == 0) break;
+    }
     return PEEB_OK;
 }
 
@@ -752,7 +773,7 @@ int peeb_pee_med_extract_batch(peeb_ws* ws, const void* marked, int64_t marked_s
 static int peeb_pee_med_embed_h_impl(peeb_ws* ws, const void* src_host, int n_units, int h, int w, int itemsize, int bit_depth,
                          const int32_t* T, const int64_t* n_bits, const uint8_t* payload_host, int64_t payload_stride,
                          void* marked_host, uint8_t* lm_host, int64_t* info_host) {
-    PEEB_REQUIRE(ws && src_host && T && n_bits && info_host, "peeb_pee_med_embed_h: null pointer");
+    PEEB_REQUIRE(ws && src_host && n_bits && info_host, "peeb_pee_med_embed_h: null pointer");
     PEEB_REQUIRE(n_units >= 1 && h >= 1 && w >= 1 && (itemsize == 1 || itemsize == 2) && payload_stride >= 0, "peeb_pee_med_embed_h: bad sizes");
     PEEB_CUDA(cudaSetDevice(ws->device));
     cudaStream_t st = ws->stream;

@@ -51,8 +51,8 @@ def pee_embed_device(imgs, payloads, n_bits, T, bit_depth, marked=None, lm=None,
             raise ValueError("n_bits must have one entry per image")
         _, h, w = imgs.shape
         src_stride = h * w * item
-    if T is None and (shared_cover or predictor != "rhombus"):
-        raise ValueError("T=None needs one cover per unit and the rhombus predictor")
+    if T is None and shared_cover:
+        raise ValueError("T=None needs one cover per unit")
     Ts = None if T is None else np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.int32), (n,)))
     if payloads.dtype != torch.uint8 or payloads.dim() != 2 or payloads.shape[0] != n:
         raise ValueError("payloads must be (n, stride) uint8")

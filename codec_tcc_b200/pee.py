@@ -98,7 +98,8 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
     payloads  (n, stride) uint8, packed MSB first; row u holds unit u's bits
               (one row of (1, stride) or (stride,) with ``shared_payload=True``)
     n_bits    (n,) ints; T scalar or (n,) ints, or None: every unit gets the smallest threshold that holds its
-              payload (histogram estimate, then verify-and-increment, all on the device); see info[:, 0]
+              payload (rhombus: histogram estimate, then verify-and-increment; med: from T = 1 upwards -- all on the
+              device); see info[:, 0]
     -> (marked (n,h,w) or None, lm_packed (n,h,ceil(w/8)) or None, info (n, 8) int64)
     ``info[:, 7]`` is 0 or PEEB_E_CAPACITY (-2): nothing is raised here, the
     embed of an oversize payload is the zero-padded embed of what fits.
@@ -125,8 +126,8 @@ def pee_embed_batch(imgs, payloads, n_bits, T, bit_depth=None, *, shared_cover=F
         Ts = np.ascontiguousarray(np.broadcast_to(np.asarray(T, dtype=np.int32), (n,)))
         for t in np.unique(Ts):
             _check_T(t, bd)
-    elif shared_cover or predictor != "rhombus":
-        raise ValueError("T=None needs one cover per unit and the rhombus predictor")
+    elif shared_cover:
+        raise ValueError("T=None needs one cover per unit")
     payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
     if shared_payload:
         payloads = payloads.reshape(1, -1)
@@ -249,21 +250,13 @@ def pee_embed(img, payload, T=None, bit_depth=None, n_bits=None, device=None, pr
         marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], t, bd, device=device, predictor=predictor)
         return marked[0], lm[0], info[0]
 
-    if T is None and predictor == "rhombus":
-        # threshold selection runs on the device (histogram estimate, verify and increment)
-        marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], None, bd, device=device)
+    if T is None:
+        # the threshold search runs on the device: histogram estimate, then verify and increment (rhombus predictor);
+        # from T = 1 upwards (causal predictor, which has no estimate) -- only units that fall short are embedded again
+        marked, lm, info = pee_embed_batch(img[None], pay2d, [n_bits], None, bd, device=device, predictor=predictor)
         marked, lm, info = marked[0], lm[0], info[0]
         if info[7] == PEEB_E_CAPACITY:
             raise ValueError("payload exceeds capacity at every threshold")
-    elif T is None:
-        T = 1  # the causal predictor has no histogram estimate: the search starts at T = 1
-        while True:
-            marked, lm, info = run(T)
-            if info[7] == 0:
-                break
-            T += 1
-            if T > tmax:
-                raise ValueError("payload exceeds capacity at every threshold")
     else:
         T = _check_T(T, bd)
         marked, lm, info = run(T)

@@ -266,7 +266,9 @@ int peeb_pee_hist_h(peeb_ws* ws, const void* src_host, int n_units, int h, int w
  * The embedder predicts from original pixels (parallel); the extractor from
  * recovered ones (anti-diagonal wavefront, one CTA per image).  Same argument
  * lists as peeb_pee_embed_batch / peeb_pee_extract_batch and their host-buffer
- * forms (src_stride != 0: no shared cover); info: cap0 = capacity, cap1 = 0.   */
+ * forms (src_stride != 0: no shared cover); info: cap0 = capacity, cap1 = 0.
+ * T may be NULL in the embed calls: every unit is embedded at T = 1, 2, ... until its
+ * payload fits (only the units that fall short take part in a round); T in info[u][0]. */
 int peeb_pee_med_embed_batch(peeb_ws* ws, const void* src, int64_t src_stride, int n_units, int h, int w,
                              int itemsize, int bit_depth, const int32_t* T, const int64_t* n_bits,
                              const uint8_t* payload, int64_t payload_stride, void* marked, int64_t marked_stride,

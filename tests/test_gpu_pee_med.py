@@ -79,3 +79,24 @@ def test_med_batch_and_auto_threshold(extract_form):
     assert info["capacity"] >= 4000 and (info["T"] == 1 or pee_c.embed(img, bits, 4000, info["T"] - 1, 12, predictor="med")[2]["status"] == -2)
     out, rec = pee.pee_extract(m, lmp, info["T"], 4000, 12, predictor="med")
     assert np.array_equal(rec, img) and np.array_equal(np.unpackbits(out)[:4000], np.unpackbits(bits)[:4000])
+
+
+def test_med_batch_threshold_search_on_the_device():
+    """T=None for a batch with the causal predictor: every unit gets the smallest T (from 1 upwards) whose capacity
+    holds its payload; same T, marked image and location map as the oracle run at that T, smaller T do not fit."""
+    imgs = synth_batch(6, 80, 120, 4095, 77)
+    pays = np.stack([random_payload(imgs[0].size, 500 + k) for k in range(6)])
+    caps = [pee_c.embed(imgs[u], pays[u], imgs[0].size, 2048, 12, predictor="med")[2]["capacity"] for u in range(6)]
+    nb = np.array([0, 30, int(caps[2] * 0.2), int(caps[3] * 0.5), int(caps[4] * 0.8), imgs[0].size], np.int64)
+    marked, lm, info = pee.pee_embed_batch(imgs, pays, nb, None, 12, predictor="med")
+    for u in range(5):
+        T = int(info[u, 0])
+        assert int(info[u, 7]) == 0 and int(info[u, 2]) >= nb[u], u
+        m0, lm0, i0 = pee_c.embed(imgs[u], pays[u], int(nb[u]), T, 12, predictor="med")
+        assert i0["status"] == 0 and np.array_equal(marked[u], m0) and np.array_equal(lm[u], lm0), u
+        if T > 1:
+            assert pee_c.embed(imgs[u], pays[u], int(nb[u]), T - 1, 12, predictor="med")[2]["status"] != 0, u
+    assert int(info[5, 7]) == pee.PEEB_E_CAPACITY and int(info[5, 0]) == 2048
+    ok = info[:, 7] == 0
+    out, rec, _ = pee.pee_extract_batch(marked[ok], lm[ok], info[ok, 0].astype(np.int32), nb[ok], 12, predictor="med")
+    assert np.array_equal(rec, imgs[ok])
