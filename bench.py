@@ -411,6 +411,9 @@ def other_roundtrip(name, rank, dev, steps=5):
         torch.cuda.synchronize(dev)
         if time.perf_counter() - t0 > 0.04:
             break
+    if rt.flush is not None:
+        rt.timed_steps(steps)  # (small workloads: one untimed window with the L2 flush in the loop; the first one measured 80-90 us
+                               # against 51 us for every later one, scripts/slice_latency.py)
     ms = rt.timed_steps(steps) / steps
     checked = rt.check(4 if rt.h * rt.w > 1 << 20 else 16)
     kernels, _, generic = rt.kernel_times(3)
@@ -424,6 +427,19 @@ def other_roundtrip(name, rank, dev, steps=5):
            "oracle_units_checked": checked}
     if name == "slice":
         out["latency_us_per_round_trip"] = ms * 1e3
+        out["path"] = "cluster kernels (one launch per direction)" if "pee_count" not in kernels else "band kernels"
+        # the same slice through the band kernels (count, embed, extract, gather), for comparison
+        prev = os.environ.get("PEEB_CLUSTER")
+        os.environ["PEEB_CLUSTER"] = "0"
+        try:
+            for _ in range(3):
+                rt.step()
+            out["latency_us_band_kernels"] = rt.timed_steps(steps) / steps * 1e3
+        finally:
+            if prev is None:
+                os.environ.pop("PEEB_CLUSTER", None)
+            else:
+                os.environ["PEEB_CLUSTER"] = prev
     return out
 
 

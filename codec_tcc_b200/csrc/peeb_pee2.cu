@@ -2125,16 +2125,31 @@ static bool make_geom_cluster(peeb_ws* ws, int n_units, int h, int w, int itemsi
 
 template <typename K, typename... Args>
 static int launch_cluster(K kernel, int n_units, int C, int threads, size_t smem, cudaStream_t st, Args... args) {
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 1; }
-    if (C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 1; }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(n_units * C)); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr{};
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = (unsigned)C; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) { cudaGetLastError(); return 1; }
+    // attributes and the "can a cluster of this shape be placed at all" query once per (kernel, shape): they cost tens of
+    // microseconds of host time, which a single-slice call would wait for
+    struct Seen { const void* k; int C, threads; size_t smem; int ok; };
+    static thread_local Seen seen[8];
+    static thread_local int nseen = 0;
+    int known = -1;
+    for (int i = 0; i < nseen; ++i)
+        if (seen[i].k == (const void*)kernel && seen[i].C == C && seen[i].threads == threads && seen[i].smem >= smem) known = seen[i].ok;
+    if (known < 0) {
+        int ok = 1;
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) ok = 0;
+        if (ok && C > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = 0;
+        int nclusters = 0;
+        if (ok && (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1)) ok = 0;
+        if (!ok) cudaGetLastError();
+        if (nseen < 8) seen[nseen++] = Seen{(const void*)kernel, C, threads, smem, ok};
+        known = ok;
+    }
+    if (!known) return 1;
     if (cudaLaunchKernelEx(&cfg, kernel, args...) != cudaSuccess) { cudaGetLastError(); return 1; }
     return 0;
 }
