@@ -159,3 +159,23 @@ def test_gpu_decoder_refuses_corrupt_blobs():
     with pytest.raises(ValueError):
         container.decode_bitmap(bytes(bad), 100_000)
     assert np.array_equal(container.decode_bitmap(bytes(blob), 100_000), (a != 0).astype(np.uint8))
+
+
+def test_oracle_properties_random_maps():
+    """Property test of the restatement (hypothesis): decode(encode(m)) == m for arbitrary lengths and densities, the packed
+    and the byte form give the same blob, the blob never exceeds its bound and shrinks with sparsity."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 70_000), st.floats(0.0, 1.0), st.integers(0, 2 ** 31 - 1))
+    def prop(n, density, seed):
+        a = _map(n, density ** 3, seed)
+        blob = BN.encode(a)
+        n0 = (n + 31) // 32; n1 = (n0 + 31) // 32; n2 = (n1 + 31) // 32
+        assert len(blob) <= 24 + 4 * (2 * n2 + n1 + n0)
+        assert np.array_equal(BN.decode(blob, n), (a != 0).astype(np.uint8))
+        assert BN.encode(np.packbits(a != 0), packed=True, n=n) == blob
+        if not a.any():
+            assert len(blob) == 24 + 8 * n2
+
+    prop()
