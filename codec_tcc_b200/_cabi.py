@@ -87,6 +87,7 @@ SIGNATURES = {
     "peeb_bitmap_decode": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32, _vp]),
     "peeb_bitmap_encode_h": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _vp]),
     "peeb_bitmap_decode_h": (_i32, [_vp, _vp, _i64, _vp, _i64, _i32]),
+    "peeb_debug_bounds": (_i32, [_vp, _i32]),
 }
 
 _lib = None
@@ -98,7 +99,22 @@ class PeebError(RuntimeError):
 
 
 def library_path() -> str:
+    """The in-tree build; PEEB_LIBRARY names another build of the same sources (the bounds-checked one,
+    tests/test_gpu_bounds_build.py) -- it must exist, nothing is substituted for it."""
+    alt = os.environ.get("PEEB_LIBRARY")
+    if alt:
+        if not os.path.exists(alt):
+            raise PeebError(f"PEEB_LIBRARY={alt} does not exist")
+        return alt
     return _build.LIBPATH
+
+
+def debug_bounds(reset: bool = False) -> dict:
+    """Counters of a bounds-checked build (see peeb_debug_bounds in include/peeb200.h)."""
+    out = (C.c_ulonglong * 6)()
+    check(lib().peeb_debug_bounds(out, 1 if reset else 0), "peeb_debug_bounds")
+    return {"violations": int(out[0]), "first_site": int(out[1]), "first_offset": int(C.c_longlong(out[2]).value),
+            "first_limit": int(out[3]), "items_checked": int(out[4]), "checking": bool(out[5])}
 
 
 def lib():

@@ -56,5 +56,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIBPATH
 
 
+BOUNDS_LIBPATH = os.path.join(LIBDIR, "bounds", "libpeeb200.so")
+
+
+def build_bounds(force: bool = False) -> str:
+    """The bounds-checked build of the PEE band kernels (-DPEEB_DEBUG_BOUNDS, see peeb_pee2.cu): same objects as
+    the product library except peeb_pee2.  Loaded only by tests/test_gpu_bounds_build.py through PEEB_LIBRARY."""
+    build(force=False)
+    os.makedirs(os.path.dirname(BOUNDS_LIBPATH), exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(INCLUDE, "peeb200.h"))
+    nvcc = _nvcc()
+    spath = os.path.join(CSRC, "peeb_pee2.cu")
+    opath = os.path.join(LIBDIR, "bounds", "peeb_pee2.o")
+    if force or _stale(opath, [spath] + headers):
+        subprocess.run([nvcc, *NVCC_FLAGS, "-DPEEB_DEBUG_BOUNDS", "-I", INCLUDE, "-c", spath, "-o", opath], check=True)
+    objs = [opath if src == "peeb_pee2.cu" else os.path.join(LIBDIR, src.replace(".cu", ".o")) for src in SOURCES]
+    if force or _stale(BOUNDS_LIBPATH, objs):
+        subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", BOUNDS_LIBPATH, *objs], check=True)
+    return BOUNDS_LIBPATH
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--bounds" in sys.argv:
+        print(build_bounds(force="--force" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

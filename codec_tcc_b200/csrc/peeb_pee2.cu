@@ -24,6 +24,7 @@
 // separate count kernel, decoupled look-back for pass 1, per-band bit staging + gather for extract.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
@@ -41,6 +42,28 @@ __device__ unsigned long long g_phase[32];
 #else
 #define PHASE_MARK(i) do {} while (0)
 #define PHASE_INIT do {} while (0)
+#endif
+
+#ifdef PEEB_DEBUG_BOUNDS
+// Bounds-checked build (-DPEEB_DEBUG_BOUNDS; codec_tcc_b200/build.py --bounds, tests/test_gpu_bounds_build.py): the
+// memory checker of the toolkit cannot be run on the boxes these kernels are developed on, so every index the band
+// kernels derive from the geometry -- staged rows and the slack reads around a cell, count tables, location-map
+// rows, band streams, staging slots, payload words -- is compared with the size of the region it points into.  A
+// violation is counted (the first one is kept: site, byte offset, limit) and the access still happens; the parity
+// suite is then run against this build and peeb_debug_bounds() must report none.
+__device__ unsigned long long g_bounds[6];  // violations, first site, first offset, its limit, checks done (items), -
+__device__ unsigned long long g_bounds_site[128];  // violations per site (printed by peeb_debug_bounds)
+__device__ __noinline__ void bounds_fail(int site, long long off, long long lim) {
+    atomicAdd(&g_bounds_site[site & 127], 1ull);
+    if (atomicAdd(&g_bounds[0], 1ull) == 0ull) { g_bounds[1] = (unsigned long long)site; g_bounds[2] = (unsigned long long)off; g_bounds[3] = (unsigned long long)lim; }
+}
+// bytes [off, off + n) must lie inside [0, lim)
+#define BOUNDS(site, off, n, lim) do { const long long _o = (long long)(off), _l = (long long)(lim); \
+    if (_o < 0 || _o + (long long)(n) > _l) bounds_fail(site, _o, _l); } while (0)
+#define BOUNDS_TICK() do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_bounds[4], 1ull); } while (0)
+#else
+#define BOUNDS(site, off, n, lim) do {} while (0)
+#define BOUNDS_TICK() do {} while (0)
 #endif
 
 struct Geom2 {
@@ -97,6 +120,7 @@ __host__ __device__ inline Smem2 layout2(const Geom2& g, int kind_ /*0 count, 1 
     return L;
 }
 
+__device__ __forceinline__ long long img_region_bytes(const Geom2& g) { return (long long)align_up((size_t)16 + (size_t)(g.R + 5) * g.pitch + 192, 16); }
 // byte offset of shared row `rs` (0 = image row r_first); every second group of 8 rows is shifted
 // by 16 bytes so that lanes two rows apart (the row-pair layout) still hit distinct banks
 __device__ __forceinline__ int row_off(const Geom2& g, int rs) { return 16 + rs * g.pitch + ((rs & 8) << 1); }
@@ -108,6 +132,9 @@ template <typename PixT>
 __device__ __forceinline__ void issue_rows2(const Geom2& g, const unsigned char* usrc, unsigned char* simg, int r_first,
                                             int lo, int hi, uint64_t* bar) {
     if (hi <= lo) return;
+    BOUNDS(12, lo, 0, g.h + 1); BOUNDS(12, hi, 0, g.h + 1);
+    BOUNDS(13, row_off(g, lo - r_first), g.rowbytes, img_region_bytes(g));
+    BOUNDS(13, row_off(g, hi - 1 - r_first), g.rowbytes, img_region_bytes(g));
     if (g.bulk) {
         // a warp issues its bulk copies one lane after the other: spread the rows over the warps,
         // four lanes each (the transaction count may be posted after the first copies complete)
@@ -296,6 +323,9 @@ __device__ __forceinline__ unsigned warp_lookback(unsigned long long* stt, int b
 __device__ __forceinline__ unsigned payload_window(const unsigned* __restrict__ pay, unsigned p, unsigned n_bits) {
     const unsigned wi = p >> 5;
     unsigned w0 = 0u, w1 = 0u;
+    // (a payload row holds peeb_payload_bytes(n_bits) = the bytes of its bits rounded up to whole words)
+    if ((wi << 5) < n_bits) BOUNDS(11, 4ll * wi, 4, 4ll * ((n_bits + 31u) >> 5));
+    if (((wi + 1u) << 5) < n_bits) BOUNDS(11, 4ll * wi + 4, 4, 4ll * ((n_bits + 31u) >> 5));
     if ((wi << 5) < n_bits) w0 = __byte_perm(__ldg(pay + wi), 0, 0x0123);
     if (((wi + 1u) << 5) < n_bits) w1 = __byte_perm(__ldg(pay + wi + 1), 0, 0x0123);
     const unsigned r0 = n_bits - (wi << 5);             // valid bits from the start of w0 (when w0 was loaded)
@@ -311,6 +341,9 @@ template <typename PixT>
 __device__ __forceinline__ void store_rows2_issue(const Geom2& g, unsigned char* udst, const unsigned char* simg,
                                                   int r_first, int lo, int hi) {
     if (hi <= lo) return;
+    BOUNDS(14, lo, 0, g.h + 1); BOUNDS(14, hi, 0, g.h + 1);
+    BOUNDS(15, row_off(g, lo - r_first), g.rowbytes, img_region_bytes(g));
+    BOUNDS(15, row_off(g, hi - 1 - r_first), g.rowbytes, img_region_bytes(g));
     if (g.bulk) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         if (lane < 4) {
@@ -556,6 +589,16 @@ __device__ __forceinline__ void sweep2(const Geom2& g, unsigned char* simg, int 
         unsigned char* pb = pa + (row_off(g, rs + 1) - oa);
         const unsigned char* pd = pa + (row_off(g, rs + 2) - oa);
         const int c0 = l.cell * g.CW;
+#ifdef PEEB_DEBUG_BOUNDS
+        {   // every step reads 16 bytes of four rows, the word before the first step and the word after each step,
+            // and stores 16 bytes of the two middle rows: the whole walk must stay inside the staged band
+            const long long lim = img_region_bytes(g), walk = 16ll * g.cws;
+            BOUNDS(1, pu - simg, walk, lim); BOUNDS(1, pd - simg, walk, lim);
+            BOUNDS(2, (pa - simg) - 4, walk + 4 + 4, lim); BOUNDS(2, (pb - simg) - 4, walk + 4 + 4, lim);
+            BOUNDS(3, rs - 1, 0, g.R + 5); BOUNDS(3, rs + 2, 1, g.R + 5);
+            BOUNDS_TICK();
+        }
+#endif
         if (!body.primed) body.begin(l.rowa, l.cell, l.acta, l.actb, l.rowa_in, l.rowb_in, T);
         body.primed = false;
         // Steps that touch a border column (or, for extract, cells with location-map bits) take the generic code:
@@ -642,6 +685,9 @@ struct Count2 {
         }
     }
     __device__ __forceinline__ void end() {
+        // (the table of the count kernel has a row per image row, a band's shared table R + 2 rows)
+        if (acta) BOUNDS(4, ia, 1, (long long)(GLOBAL ? g.h : g.R + 2) * g.tpitch);
+        if (actb) BOUNDS(4, ia + g.tpitch, 1, (long long)(GLOBAL ? g.h : g.R + 2) * g.tpitch);
         if (acta) tab[ia] = (unsigned char)na;
         if (actb) tab[ia + g.tpitch] = (unsigned char)nb;
         if (GLOBAL) total += (acta ? na : 0) + (actb ? nb : 0);
@@ -685,6 +731,12 @@ struct Apply2 {
         sta = a; stb = b;
         ka = kb = make_ke(T);
         CellPrefix cp;
+        {
+            [[maybe_unused]] const long long tlim = (long long)(GTAB ? g.h : g.R + 2) * g.tpitch;
+            if (rowa_in) BOUNDS(5, (long long)(rowa - row0) * g.tpitch, g.tpitch, tlim);
+            if (rowb_in) BOUNDS(5, (long long)(rowa + 1 - row0) * g.tpitch, g.tpitch, tlim);
+            BOUNDS(5, cell, 1, g.tpitch);
+        }
         if (wpre) {
             const int ra = rowa - pre_row0, jc = cell >> 2, wpr = g.tpitch >> 2;
             const unsigned partial = 0x01010101u & ((1u << (8 * (cell & 3))) - 1u);
@@ -771,7 +823,11 @@ struct Apply2 {
             const int d = nv - x;
             sse += (long long)d * (long long)d;
             if (own && !ok && kk.T != 0) {
-                if (lmrow) atomicOr(lmrow + (col >> 5), lm_bitmask(col));
+                if (lmrow) {
+                    BOUNDS(6, col >> 5, 1, lmwords);
+                    BOUNDS(6, (lmrow - slm) / lmwords, 1, g.lm_direct ? g.h : g.R + 2);
+                    atomicOr(lmrow + (col >> 5), lm_bitmask(col));
+                }
                 ++st->flagged;
             }
             P::template setx<Q, S>(O, nv);
@@ -1240,7 +1296,7 @@ struct Extract2 {
     bool sta, stb, reca, recb, primed;
     unsigned long long la, lb;  // location-map bytes of this lane's cell in rows a and b (byte k = columns 8k..8k+7 of the cell)
                // some pixel of the band's (or its halo rows') location-map rows is flagged
-    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool, bool, int T) {
+    __device__ __forceinline__ void begin(int rowa, int cell, bool a, bool b, bool, bool rowb_in, int T) {
         sta = a; stb = b;
         ka = kb = make_kx(T);
         Wa = Wb = 0u; na = nb = 0;
@@ -1250,7 +1306,13 @@ struct Extract2 {
         recb = b && rowa + 1 >= own_lo && rowa + 1 < own_hi;
         la = lb = 0ull;
         if (has_lm) {  // flagged pixels are rare: most bands have none at all
-            const ulonglong2 v = fetch_lm_bytes(slm + (size_t)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3), g.lmpitch,
+            // (rows a and b of the shared copy: R + 2 rows of lmpitch bytes and the slack layout2 leaves behind them)
+            // (a sweep with an odd number of rows has no row b in its last pair: row a is read twice, nothing of that
+            // row b is kept.  The copy has 32 bytes of slack behind its last row for cells that stick out of the image.)
+            const int to_b = rowb_in ? g.lmpitch : 0;
+            BOUNDS(7, (long long)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3), to_b + g.cws * (P::PXS >> 3),
+                   (long long)(g.R + 2) * g.lmpitch + 32);
+            const ulonglong2 v = fetch_lm_bytes(slm + (size_t)(rowa - lm_row0) * g.lmpitch + ((cell * g.CW) >> 3), to_b,
                                                 g.cws * (P::PXS >> 3));
             la = v.x; lb = v.y;
         }
@@ -1295,6 +1357,8 @@ struct Extract2 {
         if (stb) sts128(pb, B);
     }
     __device__ __forceinline__ void end() {
+        if (reca) { BOUNDS(8, in, 1, (long long)g.R * g.tpitch); BOUNDS(8, ia, 1, (long long)g.R * g.ncol); }
+        if (recb) { BOUNDS(8, in + g.tpitch, 1, (long long)g.R * g.tpitch); BOUNDS(8, ia + g.ncol, 1, (long long)g.R * g.ncol); }
         if (reca) { tn[in] = (unsigned char)na; tw[ia] = Wa; }
         if (recb) { tn[in + g.tpitch] = (unsigned char)nb; tw[ia + g.ncol] = Wb; }
     }
@@ -1350,6 +1414,7 @@ __device__ __forceinline__ void assemble_streams(const Geom2& g, int nrows, cons
                 if (cc > 0) {
                     const int sh = o & 31;
                     const unsigned long long v = (unsigned long long)tw[i] << (64 - cc - sh);
+                    BOUNDS(9, o >> 5, (unsigned)v ? 2 : 1, g.bandwords);
                     atomicOr(out + (o >> 5), (unsigned)(v >> 32));
                     if ((unsigned)v) atomicOr(out + (o >> 5) + 1, (unsigned)v);
                     o += cc;
@@ -1547,6 +1612,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         unsigned* gout = stage_bits + slot * g.bandwords;
         const unsigned* out = stream + (size_t)pass * g.bandwords;
         const int nw = (total + 31) >> 5;
+        BOUNDS(10, 0, nw, g.bandwords);
         for (int k = threadIdx.x; k < nw; k += blockDim.x) gout[k] = out[k];
     }
     PHASE_MARK(5);  // stream assembly + staging writes
@@ -1600,6 +1666,7 @@ __global__ void __launch_bounds__(256) pee2_gather_kernel(int nb, int bandwords,
         const int sh = (int)(before & 31);
         for (long long mw = first + threadIdx.x; mw <= last; mw += blockDim.x) {
             const int i = (int)(mw - first);
+            BOUNDS(16, nsrc, 0, bandwords + 1);
             const unsigned cur = i < nsrc ? src[i] : 0u;
             const unsigned prev = (i >= 1 && i - 1 < nsrc) ? src[i - 1] : 0u;
             unsigned val = __funnelshift_r(cur, prev, sh);  // stream bits [32 mw, 32 mw + 32), first bit on top
@@ -1610,6 +1677,7 @@ __global__ void __launch_bounds__(256) pee2_gather_kernel(int nb, int bandwords,
             }
             if (val == 0) continue;
             const unsigned packed = __byte_perm(val, 0, 0x0123);
+            BOUNDS(17, 4 * mw, 4, 4 * ((n_bits + 31) >> 5));  // never past the words that hold the unit's n_bits
             if (mw == first || mw == last) atomicOr(out + mw, packed);
             else out[mw] = packed;
         }
@@ -2312,6 +2380,40 @@ int extract_batch_impl2(peeb_ws* ws, const void* marked, int64_t marked_stride, 
 }
 
 }  // namespace peeb
+
+#ifdef PEEB_DEBUG_BOUNDS
+namespace peeb {
+// reset = 2: one check that holds and one that does not (4 bytes at offset 16 of a 16-byte region), so that a test
+// can see the checker report before it trusts a clean run
+__global__ void bounds_selftest_kernel() {
+    BOUNDS(99, 0, 16, 16);
+    BOUNDS(99, 16, 4, 16);
+}
+}  // namespace peeb
+#endif
+// peeb200.h: what the bounds-checked build found (all zeros, out6[5] = 0, in a normal build)
+extern "C" __attribute__((visibility("default"))) int peeb_debug_bounds(unsigned long long* out6, int reset) {
+    if (!out6) return PEEB_E_INVALID;
+    for (int i = 0; i < 6; ++i) out6[i] = 0ull;
+#ifdef PEEB_DEBUG_BOUNDS
+    if (reset == 2) peeb::bounds_selftest_kernel<<<1, 1>>>();
+    if (cudaDeviceSynchronize() != cudaSuccess) return PEEB_E_CUDA;
+    if (cudaMemcpyFromSymbol(out6, peeb::g_bounds, sizeof(unsigned long long) * 6) != cudaSuccess) return PEEB_E_CUDA;
+    out6[5] = 1ull;
+    unsigned long long per_site[128];
+    if (cudaMemcpyFromSymbol(per_site, peeb::g_bounds_site, sizeof(per_site)) != cudaSuccess) return PEEB_E_CUDA;
+    for (int i = 0; i < 128; ++i)
+        if (per_site[i] && reset != 2) fprintf(stderr, "peeb bounds: site %d: %llu violations\n", i, per_site[i]);
+    if (reset) {
+        const unsigned long long z[128] = {0};
+        if (cudaMemcpyToSymbol(peeb::g_bounds, z, sizeof(unsigned long long) * 6) != cudaSuccess) return PEEB_E_CUDA;
+        if (cudaMemcpyToSymbol(peeb::g_bounds_site, z, sizeof(z)) != cudaSuccess) return PEEB_E_CUDA;
+    }
+#else
+    (void)reset;
+#endif
+    return PEEB_OK;
+}
 
 #ifdef PEEB_PHASE_TIMING
 extern "C" __attribute__((visibility("default"))) int peeb_debug_phases(unsigned long long* out16, int reset) {

@@ -306,6 +306,15 @@ int peeb_bitmap_encode_h(peeb_ws* ws, const uint8_t* src_host, int64_t n, int pa
 int peeb_bitmap_decode_h(peeb_ws* ws, const uint8_t* blob_host, int64_t blob_bytes, uint8_t* dst_host, int64_t n,
                          int packed_output);
 
+/* ---- bounds-checked build (development aid; no reference counterpart) ---------------------------------------
+ * A library compiled with -DPEEB_DEBUG_BOUNDS (python -m codec_tcc_b200.build --bounds ->
+ * codec_tcc_b200/lib/bounds/libpeeb200.so) compares every shared- and global-memory index of the PEE band kernels
+ * with the size of the region it points into, counts violations and carries on.  out6 = {violations, site of the
+ * first one, its byte offset, its limit, warp items checked, 1 if this build checks at all}; the call synchronises
+ * the device.  A normal build answers all zeros.  reset != 0 clears the counters afterwards; reset == 2 first runs
+ * the checker's self-test (one check that holds, one that does not: exactly one more violation, site 99). */
+int peeb_debug_bounds(unsigned long long* out6, int reset);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -36,3 +36,17 @@ def golden_images():
         "synth8_129x70": synth_image(129, 70, 255, 13),
         "sat12_96x160": synth_saturated(96, 160, 4095, 14),
     }
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """A run against the bounds-checked build (tests/test_gpu_bounds_build.py starts one with
+    PEEB_LIBRARY / PEEB_BOUNDS_REPORT set) leaves the library's counters behind for its parent."""
+    path = os.environ.get("PEEB_BOUNDS_REPORT")
+    if not path:
+        return
+    from codec_tcc_b200 import _cabi
+
+    rep = _cabi.debug_bounds()
+    rep["exitstatus"] = int(exitstatus)
+    with open(path, "w") as f:
+        json.dump(rep, f)
