@@ -33,13 +33,39 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(INCLUDE, "peeb200.h"))
+    return hs
+
+
+def _compile_all(jobs, verbose: bool) -> None:
+    """nvcc runs of independent translation units, side by side (peeb_pee2.cu alone takes minutes)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1, 8)) as pool:
+            list(pool.map(run, jobs))
+
+
+BOUNDS_LIBPATH = os.path.join(LIBDIR, "bounds", "libpeeb200.so")
+BOUNDS_SOURCE = "peeb_pee2.cu"
+
+
+def build(force: bool = False, verbose: bool = False, with_bounds: bool = False) -> str:
+    """-> path of libpeeb200.so.  with_bounds: also the bounds-checked build of the PEE band kernels
+    (-DPEEB_DEBUG_BOUNDS, see peeb_pee2.cu) as lib/bounds/libpeeb200.so -- the same objects except peeb_pee2; it is
+    loaded only by tests/test_gpu_bounds_build.py, through PEEB_LIBRARY."""
     os.makedirs(LIBDIR, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(INCLUDE, "peeb200.h"))
+    headers = _headers()
     nvcc = _nvcc()
     extra = os.environ.get("PEEB_NVCC_EXTRA", "").split()
-    objs = []
+    objs, jobs = [], []
     for src in SOURCES:
         spath = os.path.join(CSRC, src)
         opath = os.path.join(LIBDIR, src.replace(".cu", ".o"))
@@ -48,37 +74,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", spath, "-o", opath]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
-                print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
+    bobj = os.path.join(LIBDIR, "bounds", BOUNDS_SOURCE.replace(".cu", ".o"))
+    if with_bounds:
+        os.makedirs(os.path.dirname(BOUNDS_LIBPATH), exist_ok=True)
+        spath = os.path.join(CSRC, BOUNDS_SOURCE)
+        if force or _stale(bobj, [spath] + headers):
+            jobs.append([nvcc, *NVCC_FLAGS, "-DPEEB_DEBUG_BOUNDS", "-I", INCLUDE, "-c", spath, "-o", bobj])
+    _compile_all(jobs, verbose)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"]
     if force or _stale(LIBPATH, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIBPATH, *objs]
-        subprocess.run(cmd, check=True)
+        subprocess.run([*link, "-o", LIBPATH, *objs], check=True)
+    if with_bounds:
+        bobjs = [bobj if o.endswith(BOUNDS_SOURCE.replace(".cu", ".o")) else o for o in objs]
+        if force or _stale(BOUNDS_LIBPATH, bobjs):
+            subprocess.run([*link, "-o", BOUNDS_LIBPATH, *bobjs], check=True)
     return LIBPATH
 
 
-BOUNDS_LIBPATH = os.path.join(LIBDIR, "bounds", "libpeeb200.so")
-
-
 def build_bounds(force: bool = False) -> str:
-    """The bounds-checked build of the PEE band kernels (-DPEEB_DEBUG_BOUNDS, see peeb_pee2.cu): same objects as
-    the product library except peeb_pee2.  Loaded only by tests/test_gpu_bounds_build.py through PEEB_LIBRARY."""
-    build(force=False)
-    os.makedirs(os.path.dirname(BOUNDS_LIBPATH), exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    headers.append(os.path.join(INCLUDE, "peeb200.h"))
-    nvcc = _nvcc()
-    spath = os.path.join(CSRC, "peeb_pee2.cu")
-    opath = os.path.join(LIBDIR, "bounds", "peeb_pee2.o")
-    if force or _stale(opath, [spath] + headers):
-        subprocess.run([nvcc, *NVCC_FLAGS, "-DPEEB_DEBUG_BOUNDS", "-I", INCLUDE, "-c", spath, "-o", opath], check=True)
-    objs = [opath if src == "peeb_pee2.cu" else os.path.join(LIBDIR, src.replace(".cu", ".o")) for src in SOURCES]
-    if force or _stale(BOUNDS_LIBPATH, objs):
-        subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", BOUNDS_LIBPATH, *objs], check=True)
+    build(force=force, with_bounds=True)
     return BOUNDS_LIBPATH
 
 
 if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, with_bounds="--bounds" in sys.argv))
     if "--bounds" in sys.argv:
-        print(build_bounds(force="--force" in sys.argv))
-    else:
-        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+        print(BOUNDS_LIBPATH)
