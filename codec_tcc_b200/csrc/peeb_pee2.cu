@@ -1455,6 +1455,11 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
         // loads are issued before the band's bulk copies (small reads would otherwise queue behind them)
         const int l_lo = max(r0 - 1, 0), l_hi = min(r0 + g.R + 1, g.h);
         const unsigned char* glm = bt.lm + (long long)unit * bt.lm_stride;
+        // bounds-checked build: global reads stay inside the unit's map (site 18; whole 16-byte pieces may reach up to
+        // 15 bytes into the aligned pieces around it), shared writes inside the copy's region with its slack (site 19)
+        [[maybe_unused]] const long long lm_glim = (long long)g.h * g.lmw;
+        [[maybe_unused]] const unsigned char* const slm0 = slm - 16;
+        [[maybe_unused]] const long long lm_slim = (long long)(g.R + 2) * g.lmpitch + 16 + 48;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         (void)lane; (void)warp; (void)nwarps;
         if (g.lmpitch == g.lmw && (g.lmw & 15) == 0 && ((uintptr_t)glm & 15) == 0) {
@@ -1464,6 +1469,9 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
             const int npieces = (l_hi - l_lo) * (g.lmw >> 4);
             const uint4* gq = reinterpret_cast<const uint4*>(glm + (size_t)l_lo * g.lmw);
             uint4* sq = reinterpret_cast<uint4*>(slm + (size_t)(l_lo - (r0 - 1)) * g.lmw);
+            BOUNDS(18, (long long)l_lo * g.lmw, 16ll * npieces, lm_glim);
+            BOUNDS(19, reinterpret_cast<unsigned char*>(sq) - slm0, 16ll * npieces, lm_slim);
+            BOUNDS(19, slm - slm0, 16ll * (g.R + 2) * (g.lmw >> 4), lm_slim);
             const int k0 = threadIdx.x, k1 = threadIdx.x + blockDim.x;
             const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
             const uint4 v0 = k0 < npieces ? __ldg(gq + k0) : zero4, v1 = k1 < npieces ? __ldg(gq + k1) : zero4;
@@ -1487,6 +1495,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
             auto fetch = [&](int k) {
                 uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 const int r = k / q, j = k - r * q, row = r0 - 1 + r;
+                if (k < npieces && j < qv && row >= l_lo && row < l_hi) BOUNDS(18, (long long)row * g.lmw + 16 * j, 16, lm_glim);
                 if (k < npieces && j < qv && row >= l_lo && row < l_hi)
                     v = __ldg(reinterpret_cast<const uint4*>(glm + (size_t)row * g.lmw) + j);
                 return v;
@@ -1495,6 +1504,7 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
             const uint4 v0 = fetch(k0), v1 = fetch(k1);
             issue_rows2<PixT>(g, usrc, simg, r_first, s_lo, s_hi, bar);
             uint4* sq = reinterpret_cast<uint4*>(slm);
+            BOUNDS(19, slm - slm0, 16ll * npieces, lm_slim);
             if (k0 < npieces) sq[k0] = v0;
             if (k1 < npieces) sq[k1] = v1;
             lm_any = (v0.x | v0.y | v0.z | v0.w | v1.x | v1.y | v1.z | v1.w) != 0u;
@@ -1516,6 +1526,9 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
             const int npieces = nbytes > 0 ? (head + nbytes + 15) >> 4 : 0;
             const uint4* gq = reinterpret_cast<const uint4*>(gfirst - head);
             uint4* sq = reinterpret_cast<uint4*>(slm + (size_t)first * g.lmw - head);
+            BOUNDS(18, (long long)l_lo * g.lmw - head + 15, 16ll * npieces - 15 - (npieces ? 15 : 0), lm_glim);
+            BOUNDS(19, reinterpret_cast<unsigned char*>(sq) - slm0, 16ll * npieces, lm_slim);
+            BOUNDS(19, slm - slm0, (long long)(g.R + 2) * g.lmw, lm_slim);
             const int k0 = threadIdx.x, k1 = threadIdx.x + blockDim.x;
             const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
             const uint4 v0 = k0 < npieces ? __ldg(gq + k0) : zero4, v1 = k1 < npieces ? __ldg(gq + k1) : zero4;
@@ -1540,6 +1553,8 @@ __global__ void __launch_bounds__(NT, MINB) pee2_extract_kernel(Geom2 g, PeeBatc
                 const int row = r0 - 1 + r;
                 const bool valid = row >= l_lo && row < l_hi;
                 for (int k = lane; k < g.lmpitch; k += 32) {
+                    if (valid && k < g.lmw) BOUNDS(18, (long long)row * g.lmw + k, 1, lm_glim);
+                    BOUNDS(19, (slm - slm0) + (long long)r * g.lmpitch + k, 1, lm_slim);
                     const unsigned char v = (valid && k < g.lmw) ? glm[(size_t)row * g.lmw + k] : (unsigned char)0;
                     slm[(size_t)r * g.lmpitch + k] = v;
                     lm_any |= v != 0;
