@@ -542,30 +542,107 @@ __global__ void __launch_bounds__(256) lsb_recover_kernel(const unsigned char* _
 }
 
 // bits_out bit (bit_off[p] + k) = bit p of stego[(start[p] + k) mod n], 0 <= k < len[p]; MSB-first bytes.
-// One thread per 32 segment bits; the word lands at an arbitrary bit offset (two atomicOr).
+//
+// A warp item = 1024 consecutive bits of one segment = 32 output chunks of 32 bits, one per lane; the items of all
+// planes form one list.  Fast form (the item's pixels do not wrap and the image is 16-byte aligned): the pixels are
+// read in ALIGNED blocks of eight (one 16- / 8-byte load per lane, four rounds cover 1024 pixels), a block's
+// plane-p bits are gathered into a byte with one multiply per word, four lanes join their bytes into a word of the
+// aligned bit stream, and the segment's own alignment (start mod 8) is dealt with afterwards, in bits: chunk =
+// funnel shift of two neighbouring words.  About 150 instructions per item.  Generic form (wrap-around, the tail of
+// the image, unaligned images): every lane reads the 32 pixels of round i, a ballot makes chunk i's word -- about
+// 1000 instructions per item, which is what bound this kernel when it was the only form (0.16 of the HBM peak).
+// History: one thread per chunk walking its own 32 pixels, a grid row per plane: 43 us for 18 Mbit; ballots: 37;
+// loads before ballots: 33; one list of items: 27.
 template <int ITEM>
-__global__ void __launch_bounds__(256) lsb_extract_kernel(const unsigned char* __restrict__ stego, long long n,
+__device__ __forceinline__ unsigned plane_bits8(const unsigned char* __restrict__ stego, long long pos, int p) {
+    // plane-p bits of pixels pos .. pos + 7 (pos a multiple of 8), the first pixel in bit 7
+    if (ITEM == 2) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(stego + 2 * pos));
+        constexpr unsigned K = (1u << 17) | 1u;  // bits 0 and 16 of a masked word -> bits 17 and 16 of the product
+        const unsigned a = ((((v.x >> p) & 0x00010001u) * K) >> 16) & 3u, b = ((((v.y >> p) & 0x00010001u) * K) >> 16) & 3u;
+        const unsigned c = ((((v.z >> p) & 0x00010001u) * K) >> 16) & 3u, d = ((((v.w >> p) & 0x00010001u) * K) >> 16) & 3u;
+        return (a << 6) | (b << 4) | (c << 2) | d;
+    } else {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(stego + pos));
+        constexpr unsigned K = (1u << 27) | (1u << 18) | (1u << 9) | 1u;  // bits 0, 8, 16, 24 -> bits 27 .. 24, no carries
+        const unsigned a = ((((v.x >> p) & 0x01010101u) * K) >> 24) & 15u, b = ((((v.y >> p) & 0x01010101u) * K) >> 24) & 15u;
+        return (a << 4) | b;
+    }
+}
+// the bytes of four neighbouring lanes (lane & 3 = 0 first) as one word, in all four lanes
+__device__ __forceinline__ unsigned quad_word(unsigned byte, int lane) {
+    unsigned t = byte << (8 * (3 - (lane & 3)));
+    t |= __shfl_xor_sync(0xffffffffu, t, 1);
+    t |= __shfl_xor_sync(0xffffffffu, t, 2);
+    return t;
+}
+template <int ITEM>
+__global__ void __launch_bounds__(256) lsb_extract_kernel(const unsigned char* __restrict__ stego, long long n, int s,
                                                           LsbSegs segs, unsigned* __restrict__ out) {
-    const int p = blockIdx.y;
-    const LsbSeg sg = segs.s[p];
-    const long long nchunks = (sg.len + 31) >> 5;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
-    for (long long ch = tid; ch < nchunks; ch += nthr) {
-        const long long k0 = ch << 5;
-        const int cnt = (int)min(32ll, sg.len - k0);
-        long long pos = sg.start + k0;
-        if (pos >= n) pos -= n;
-        unsigned v = 0;  // first bit of the chunk on top
-        for (int j = 0; j < cnt; ++j) {
-            const unsigned px = ITEM == 2 ? reinterpret_cast<const unsigned short*>(stego)[pos] : stego[pos];
-            v |= ((px >> p) & 1u) << (31 - j);
-            if (++pos == n) pos = 0;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool base_aligned = ((uintptr_t)stego & 15) == 0;
+    long long total = 0;
+    for (int q = 0; q < s; ++q) total += (segs.s[q].len + 1023) >> 10;
+    for (long long item = warp; item < total; item += nwarps) {
+        int p = 0;
+        long long grp = item;
+        for (; p < s - 1; ++p) {
+            const long long ng = (segs.s[p].len + 1023) >> 10;
+            if (grp < ng) break;
+            grp -= ng;
         }
-        const long long b = sg.bit_off + k0;  // stream bit of the chunk's first bit
-        const int sh = (int)(b & 31);
-        const unsigned hi = v >> sh, lo = sh ? v << (32 - sh) : 0u;
-        if (hi) atomicOr(out + (b >> 5), __byte_perm(hi, 0, 0x0123));
-        if (lo) atomicOr(out + (b >> 5) + 1, __byte_perm(lo, 0, 0x0123));
+        const LsbSeg sg = segs.s[p];
+        const long long nchunks = (sg.len + 31) >> 5;
+        const long long kbase = grp << 10;
+        const long long ch = (grp << 5) + lane;  // this lane's chunk
+        unsigned v = 0;                          // its word, first bit on top
+        const long long a0 = (sg.start & ~7ll) + kbase;  // aligned pixel the item's bit stream starts at
+        const int r = (int)(sg.start & 7);               // ... and the segment's offset inside it, in bits
+        if (base_aligned && a0 + 1024 + 32 <= n) {
+            unsigned w[4];  // w[j]: word 8 j + (lane >> 2) of the aligned stream
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = quad_word(plane_bits8<ITEM>(stego, a0 + 256 * j + 8 * lane, p), lane);
+            // one more word for the last chunk when the segment does not start on a block
+            const unsigned e = quad_word((r != 0 && lane < 4) ? plane_bits8<ITEM>(stego, a0 + 1024 + 8 * lane, p) : 0u, lane);
+            unsigned cur = 0, nxt = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const unsigned x = __shfl_sync(0xffffffffu, w[j], 4 * (lane & 7));
+                const unsigned y = __shfl_sync(0xffffffffu, w[j], 4 * ((lane + 1) & 7));
+                if ((lane >> 3) == j) cur = x;
+                if (((lane + 1) >> 3) == j) nxt = y;
+            }
+            const unsigned e0 = __shfl_sync(0xffffffffu, e, 0);
+            if (lane == 31) nxt = e0;
+            v = r ? __funnelshift_l(nxt, cur, r) : cur;
+            const long long rem = sg.len - (ch << 5);  // bits of the chunk inside the segment
+            if (rem <= 0) v = 0u;
+            else if (rem < 32) v &= ~(0xffffffffu >> (int)rem);
+        } else {
+            unsigned px[32];  // (all loads before the first ballot: 32 memory round trips in a row otherwise)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const long long k = kbase + 32 * i + lane;
+                long long pos = sg.start + k;  // start < n and k < len <= n: one wrap at most
+                if (pos >= n) pos -= n;
+                px[i] = 0u;
+                if (k < sg.len) px[i] = ITEM == 2 ? __ldg(reinterpret_cast<const unsigned short*>(stego) + pos) : __ldg(stego + pos);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const unsigned wd = __brev(__ballot_sync(0xffffffffu, ((px[i] >> p) & 1u) != 0u));
+                if (lane == i) v = wd;
+            }
+        }
+        if (ch < nchunks && v) {
+            const long long b = sg.bit_off + (ch << 5);  // stream bit of the chunk's first bit
+            const int sh = (int)(b & 31);
+            const unsigned hi = v >> sh, lo = sh ? v << (32 - sh) : 0u;
+            if (hi) atomicOr(out + (b >> 5), __byte_perm(hi, 0, 0x0123));
+            if (lo) atomicOr(out + (b >> 5) + 1, __byte_perm(lo, 0, 0x0123));
+        }
     }
 }
 
@@ -840,16 +917,15 @@ int peeb_lsb_extract(peeb_ws* ws, const void* stego, int64_t n, int itemsize, in
     // bits_out: ceil(total_bits/8) bytes rounded up to whole words + one word of slack
     PEEB_CUDA(cudaMemsetAsync(bits_out, 0, align_up((size_t)(total_bits + 7) / 8, 4) + 4, st));
     if (n == 0 || total_bits == 0) return PEEB_OK;
-    int64_t maxlen = 0;
-    for (int p = 0; p < s; ++p) maxlen = len[p] > maxlen ? len[p] : maxlen;
-    long long bx = ((maxlen + 31) / 32 + 255) / 256;
+    long long groups = 0;  // a warp item = 1024 consecutive bits of one segment
+    for (int p = 0; p < s; ++p) groups += (len[p] + 1023) / 1024;
+    long long bx = (groups + 7) / 8;
     const long long cap = (long long)ws->sm_count * 8;
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
-    dim3 grid((unsigned)bx, (unsigned)s);
     ProfScope prof(ws, PEEB_K_LSB_EXTRACT, st);
-    if (itemsize == 2) lsb_extract_kernel<2><<<grid, 256, 0, st>>>((const unsigned char*)stego, n, segs, (unsigned*)bits_out);
-    else lsb_extract_kernel<1><<<grid, 256, 0, st>>>((const unsigned char*)stego, n, segs, (unsigned*)bits_out);
+    if (itemsize == 2) lsb_extract_kernel<2><<<(unsigned)bx, 256, 0, st>>>((const unsigned char*)stego, n, s, segs, (unsigned*)bits_out);
+    else lsb_extract_kernel<1><<<(unsigned)bx, 256, 0, st>>>((const unsigned char*)stego, n, s, segs, (unsigned*)bits_out);
     PEEB_CUDA(cudaGetLastError());
     return PEEB_OK;
 }

@@ -38,6 +38,9 @@ def dev_time(fn, reps=20, warm=3):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the calls queue up behind ~10 ms of spinning: kernels of a few microseconds are then timed at the device's
+    # pace, not at the rate the host can enqueue them (a call costs the host 30-40 us through ctypes)
+    torch.cuda._sleep(20_000_000)
     a.record()
     for _ in range(reps):
         fn()

@@ -295,3 +295,39 @@ def test_tile_search_on_bright_16_bit_planes_with_large_tiles():
         base[0:256, 512:768] -= rng.integers(0, 3, (256, 256)).astype(np.uint16) * 19999      # a close second
         assert codec.hybrid_start_offset(base, 256) == OC.best_tile_offset(base, 256)
         assert codec.hybrid_start_offset(base, 128) == OC.best_tile_offset(base, 128)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_segment_read_back_arbitrary_segments(seed):
+    """peeb_lsb_extract with segments the embedders never produce together: starts at every alignment, segments
+    that wrap around the end of the image, lengths that end inside a 1024-bit warp item, image sizes that are not a
+    multiple of 8, 8- and 16-bit pixels -- the aligned-block form and the generic form of the kernel against numpy."""
+    from codec_tcc_b200 import _cabi
+
+    rng = np.random.default_rng(100 + seed)
+    dtype = np.uint16 if seed % 2 else np.uint8
+    s = int(rng.integers(1, 8 * dtype().itemsize + 1))
+    n = int(rng.integers(3000, 150000))
+    img = rng.integers(0, np.iinfo(dtype).max + 1, n).astype(dtype)
+    start = rng.integers(0, n, s).astype(np.int64)
+    length = rng.integers(0, n + 1, s).astype(np.int64)
+    length[rng.integers(0, s)] = n                      # one segment goes all the way round
+    if s > 2:
+        length[rng.integers(0, s)] = 0
+    order = rng.permutation(s)
+    off = np.zeros(s, np.int64)
+    at = 0
+    for p in order:
+        off[p] = at
+        at += int(length[p])
+    total = at
+    out = np.zeros((total + 7) // 8 + 8, np.uint8)
+    ws = _cabi.workspace(None)
+    _cabi.check(_cabi.lib().peeb_lsb_extract_h(ws.handle, _cabi.ptr(img), n, img.dtype.itemsize, s, _cabi.ptr(start),
+                                               _cabi.ptr(length), _cabi.ptr(off), total, _cabi.ptr(out)), "peeb_lsb_extract_h")
+    want = np.zeros(total, np.uint8)
+    for p in range(s):
+        seg = np.roll(img, -int(start[p]))[:int(length[p])]
+        want[off[p]:off[p] + length[p]] = (seg >> p) & 1
+    assert np.array_equal(np.unpackbits(out)[:total], want)
+    assert not out[(total + 7) // 8:].any()
