@@ -64,3 +64,7 @@ for seed in range(seeds):
     blob = container.encode_bitmap(a)
     assert blob == BN.encode(a) and np.array_equal(container.decode_bitmap(blob, nmap), (a != 0).astype(np.uint8))
 print("stress ok:", n_cases, "embed/extract cases,", seeds, "threshold-selection batches and bitmaps")
+if os.environ.get("PEEB_LIBRARY"):  # the bounds-checked build (python -m codec_tcc_b200.build --bounds): what its checker saw
+    from codec_tcc_b200 import _cabi
+
+    print("bounds:", _cabi.debug_bounds())
